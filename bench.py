@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — Mpixel/s of the CLAHE + denoise + sharpen chain (BASELINE.json metric) on N B200s.
+
+Workload (N=1 and per rank for N>1, weak scaling): BASELINE.json configs[1] —
+batch 256 x 512x512 uint16 CT-like phantom slices, Gaussian (K=9, sigma=1, reflect) ->
+CLAHE (8x8 tiles, clip 2.0) -> unsharp mask (K=9, sigma=1), uint16 out.
+
+One JSON line on stdout (rank 0).  See DESIGN.md §5 for how each field is measured.
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+      bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      # CPU arm: the oracle port on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH, H, W = 256, 512, 512
+PIXELS = BATCH * H * W
+ALG_BYTES_PER_PIXEL = 4  # uint16 in + uint16 out, compulsory traffic only
+METRIC = "Mpixel/s, CLAHE+denoise+sharpen chain"
+UNIT = "Mpixel/s"
+WORKLOAD = ("configs[1]: batch 256 x 512x512 uint16 phantom slices, Gaussian K=9 sigma=1 reflect -> "
+            "CLAHE 8x8 clip 2.0 -> unsharp K=9 sigma=1, uint16 out")
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while `active` is set."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons = index, [], set()
+        self.active = threading.Event()
+        self.stop_flag = threading.Event()
+        self.sm_max = None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # NVML missing: report it rather than inventing clocks
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self.stop_flag.is_set():
+            if self.active.is_set():
+                try:
+                    self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                    try:
+                        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    for bit, name in names.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.005)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable: " + self.err}
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_chain_sample(sample_slices: int, reps: int, budget_s: float):
+    """Times the oracle port of the chain on `sample_slices` phantom slices with all host threads.
+    Returns (best Mpixel/s, cores, description)."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+
+    from mie_b200 import synthetic
+
+    x = synthetic.phantom((sample_slices, 1, H, W), np.uint16, seed=0)
+    cores = os.cpu_count() or 1
+    O.chain_gauss_clahe_unsharp(x[:2])  # warm (builds / loads the oracle)
+    best, t_total = None, 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.chain_gauss_clahe_unsharp(x)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        t_total += dt
+        if t_total > budget_s:
+            break
+    mpx = sample_slices * H * W / best / 1e6
+    return mpx, cores, f"{sample_slices} of {BATCH} slices (same phantom generator, seed 0), best of <= {reps} runs"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 32
+    # every "step" is one bounded sample of the workload
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+
+    from mie_b200 import synthetic
+
+    x = synthetic.phantom((sample, 1, H, W), np.uint16, seed=0)
+    cores = os.cpu_count() or 1
+    for _ in range(max(args.warmup, 1)):
+        O.chain_gauss_clahe_unsharp(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.chain_gauss_clahe_unsharp(x)
+    dt = time.perf_counter() - t0
+    value = sample * H * W * args.steps / dt / 1e6
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "step": f"bounded sample: {sample} of {BATCH} slices per step",
+                   "note": "the reference repository contains no implementation (0 lines of Python); this arm times "
+                           "the in-repo CPU oracle port (C, OpenMP) of the kornia-style chain"},
+        "cpu_baseline": {"value": round(value, 3), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} slices per step x {args.steps} steps, OpenMP over slices"},
+        "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    import mie_b200
+    from mie_b200 import synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # inputs: one distinct batch per rank (weak scaling: per-GPU work fixed)
+    x_host = torch.from_numpy(synthetic.phantom((BATCH, 1, H, W), np.uint16, seed=rank)).pin_memory()
+    y_host = torch.empty_like(x_host).pin_memory()
+    x = x_host.to(dev, non_blocking=True)
+    y = torch.empty_like(x)
+    cfg = mie_b200.ChainConfig()
+    ws = torch.empty(mie_b200.chain_workspace_bytes(BATCH, H, W, cfg.grid_size), dtype=torch.uint8, device=dev)
+    fused = bool(mie_b200._lib().mie_chain_is_fused(H, W, 8, 8, 9, 9, 9, 9))
+    launches_per_step = 2 if fused else 4
+
+    def step():
+        mie_b200.enhance_chain(x, cfg, out=y, workspace=ws)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    sampler.active.set()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * PIXELS / (ms_step * 1e-3) / 1e6
+
+    # ---- per-kernel durations (CUDA events on the launching stream), same inputs, same workspace
+    kern = {}
+    if fused:
+        for name, mask in (("chain_a_kernel", 1), ("chain_b_kernel", 2)):
+            for _ in range(3):
+                mie_b200.enhance_chain(x, cfg, out=y, workspace=ws, stages=mask)
+            torch.cuda.synchronize()
+            reps = max(args.steps, 10)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                mie_b200.enhance_chain(x, cfg, out=y, workspace=ws, stages=mask)
+            a1.record()
+            torch.cuda.synchronize()
+            kern[name] = a0.elapsed_time(a1) / reps
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    def e2e_step():
+        x.copy_(x_host, non_blocking=True)
+        mie_b200.enhance_chain(x, cfg, out=y, workspace=ws)
+        y_host.copy_(y, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    g1.record()
+    barrier()
+    e2e_ms = g0.elapsed_time(g1) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * PIXELS / (e2e_ms * 1e-3) / 1e6
+    _ = time.perf_counter() - t0
+
+    # keep the GPU busy a little longer so that the clock sampler sees the chain under load
+    t_end = time.perf_counter() + 0.3
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            step()
+        torch.cuda.synchronize()
+    sampler.active.clear()
+    sampler.stop_flag.set()
+    checksum = int(y_host.view(torch.int16).flatten()[::997].to(torch.int64).sum().item())
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        roof = None
+        if kern:
+            dom = max(kern, key=kern.get)
+            # chain_a: uint16 in + 1-byte index out; chain_b: 1-byte index in + uint16 out  -> 3 B/pixel each
+            dom_bytes = 3 * PIXELS
+            ach = dom_bytes / (kern[dom] * 1e-3) / 1e9
+            roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "bytes_per_launch": dom_bytes, "ms_per_launch": round(kern[dom], 4),
+                    "kernels_ms": {k: round(v, 4) for k, v in kern.items()}}
+        step_gbs = ALG_BYTES_PER_PIXEL * PIXELS / (ms_step * 1e-3) / 1e9
+        cpu = None
+        if world == 1 or rank == 0:
+            mpx, cores, desc = cpu_chain_sample(sample_slices=32, reps=5, budget_s=20.0)
+            cpu = {"value": round(mpx, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": BATCH, "global_batch": BATCH * world,
+                       "parallelism": f"slice-sharded x{world}, no collective on the data path",
+                       "l2": "inputs larger than L2 (134 MB in + 134 MB out + 67 MB index plane per step vs 126 MB L2)",
+                       "fused_path": fused},
+            "roofline": roof,
+            "roofline_step": {"bound": "hbm", "achieved": round(step_gbs, 1), "peak": peak, "unit": "GB/s",
+                              "frac": round(step_gbs / peak, 4), "frac_of_nominal_8TBs": round(step_gbs / 8000.0, 4),
+                              "bytes_per_step": ALG_BYTES_PER_PIXEL * PIXELS,
+                              "note": "whole chain: 4 B/pixel compulsory traffic / step time"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 2,
+                    "d2h_bytes_per_step": y_host.numel() * 2, "ms_per_step": round(e2e_ms, 4),
+                    "api": "mie_b200.enhance_chain on pinned host uint16 buffers (copy in, chain, copy out)"},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": sampler.summary(),
+            "checksum": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,199 @@
+/*
+ * mie.h — C ABI of libmie_b200.so: the B200 (sm_100a) enhancement hot path.
+ *
+ * The reference repository (GregOratOr/medical-image-enhancement-system) ships no
+ * code of its own (README.md and configs/__init__.py are 0 bytes); its hot path is
+ * the set of third-party functions its dependency list names
+ * (reference pyproject.toml:7-18 — kornia>=0.8.2 at :8, scikit-image>=0.26.0 at :12,
+ * pins in uv.lock:219-230 and uv.lock:619-650).  Each entry point below therefore
+ * cites the upstream function it replaces; there is no reference FFI to copy.
+ *
+ * Conventions
+ *  - Every pointer named src/dst/workspace/luts/hist is a DEVICE pointer on the
+ *    current CUDA device; `wx`, `wy`, `wspace` weight arrays are HOST pointers and
+ *    are copied into kernel parameters at call time.
+ *  - Images are batches of single-channel planes: plane i starts at
+ *    base + i*stride_n, row y at + y*stride_h (strides in ELEMENTS), pixels
+ *    contiguous within a row.  Multi-channel (B,C,H,W) tensors are passed as
+ *    n = B*C planes (all ops here are per-channel).
+ *  - dtype codes: MIE_U8, MIE_U16, MIE_I16, MIE_F32.  Integer pixels are mapped
+ *    to [0,1] as  x01 = (float(v) - lo) / (hi - lo)  (IEEE fp32 ops, in that
+ *    order) and mapped back as  rint(clamp(y,0,1) * (hi - lo)) + lo.  For F32
+ *    planes lo/hi are ignored (kornia behaviour: caller supplies [0,1] data).
+ *    dst_dtype must equal src_dtype or be MIE_F32.
+ *  - All work is enqueued on `stream` (a cudaStream_t passed as void*); nothing
+ *    synchronises; no device memory is allocated or retained by the library.
+ *  - Return 0 on success, a negative MIE_E_* for argument errors detected before
+ *    launch, or a positive cudaError_t passed through.
+ */
+#ifndef MIE_H_
+#define MIE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIE_ABI_VERSION 1
+
+enum mie_dtype { MIE_U8 = 0, MIE_U16 = 1, MIE_I16 = 2, MIE_F32 = 3 };
+
+/* kornia border_type names: 'constant' (zeros), 'reflect' (mirror, edge not
+ * repeated), 'replicate', 'circular'.  scipy.ndimage 'nearest' == replicate. */
+enum mie_border { MIE_BORDER_CONSTANT = 0, MIE_BORDER_REFLECT = 1, MIE_BORDER_REPLICATE = 2, MIE_BORDER_CIRCULAR = 3 };
+
+/* CLAHE semantics selector. */
+enum mie_clahe_semantics { MIE_CLAHE_KORNIA = 0, MIE_CLAHE_OPENCV = 1 };
+
+enum mie_error {
+    MIE_OK = 0,
+    MIE_E_NULL = -1,        /* null pointer argument */
+    MIE_E_DTYPE = -2,       /* unsupported dtype / dtype combination */
+    MIE_E_SHAPE = -3,       /* non-positive or unsupported dimension */
+    MIE_E_STRIDE = -4,      /* stride smaller than the row / plane */
+    MIE_E_GRID = -5,        /* CLAHE grid entry <= 0 */
+    MIE_E_PAD = -6,         /* required padding exceeds the image (kornia ValueError) */
+    MIE_E_KERNEL = -7,      /* kernel size even, <= 0 or beyond the supported maximum */
+    MIE_E_BORDER = -8,      /* unknown border mode, or halo >= image for reflect */
+    MIE_E_WORKSPACE = -9,   /* workspace too small */
+    MIE_E_RANGE = -10,      /* hi <= lo for an integer dtype */
+    MIE_E_UNSUPPORTED = -11 /* valid request this build does not implement */
+};
+
+int mie_abi_version(void);
+const char* mie_error_string(int code);
+/* SM count / compute capability of the current device (for grid sizing, tests). */
+int mie_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ Gaussian / unsharp
+ * Replaces kornia.filters.gaussian_blur2d(input, kernel_size, sigma, border_type,
+ * separable=True) and kornia.filters.unsharp_mask(input, kernel_size, sigma,
+ * border_type) (reference pyproject.toml:8).
+ * wx (kx taps, horizontal) and wy (ky taps, vertical) are the normalised 1-D
+ * weights; kx, ky odd, <= MIE_MAX_TAPS.  Horizontal pass first, then vertical; each
+ * pass accumulates acc = w[0]*x[0]; acc = fma(w[i], x[i], acc) in tap order.
+ * unsharp: out = x + (x - blur(x)).                                              */
+#define MIE_MAX_TAPS 33
+int mie_gaussian2d(const void* src, void* dst, int src_dtype, int dst_dtype,
+                   int64_t n, int h, int w,
+                   int64_t src_stride_n, int64_t src_stride_h,
+                   int64_t dst_stride_n, int64_t dst_stride_h,
+                   const float* wx, int kx, const float* wy, int ky, int border,
+                   float lo, float hi, void* stream);
+int mie_unsharp(const void* src, void* dst, int src_dtype, int dst_dtype,
+                int64_t n, int h, int w,
+                int64_t src_stride_n, int64_t src_stride_h,
+                int64_t dst_stride_n, int64_t dst_stride_h,
+                const float* wx, int kx, const float* wy, int ky, int border,
+                float lo, float hi, void* stream);
+
+/* ------------------------------------------------------------------ CLAHE
+ * Replaces kornia.enhance.equalize_clahe(input, clip_limit, grid_size)
+ * (reference pyproject.toml:8) and, with
+ * semantics = MIE_CLAHE_OPENCV, cv::CLAHE (SURVEY.md §8(a) A1', Appendix A).
+ * 256 bins.  gh x gw = grid_size (rows, cols).  clip_limit <= 0 disables clipping.
+ *
+ * Stage entry points (used by the parity tests to compare integer artefacts
+ * bit-exactly, "teacher forcing"):
+ *   mie_clahe_hist : raw per-tile histograms  hist[n][gh][gw][256] (uint32)
+ *   mie_clahe_luts : clipped/redistributed/cumulated LUTs luts[n][gh][gw][256] (uint8)
+ *   mie_clahe_apply: interpolation pass given LUTs
+ *   mie_clahe      : luts + apply, LUTs kept in `workspace`.                       */
+size_t mie_clahe_workspace_bytes(int64_t n, int h, int w, int gh, int gw);
+int mie_clahe_hist(const void* src, int src_dtype, int64_t n, int h, int w,
+                   int64_t src_stride_n, int64_t src_stride_h,
+                   int gh, int gw, int semantics, float lo, float hi,
+                   uint32_t* hist, void* stream);
+int mie_clahe_luts(const void* src, int src_dtype, int64_t n, int h, int w,
+                   int64_t src_stride_n, int64_t src_stride_h,
+                   int gh, int gw, double clip_limit, int semantics, float lo, float hi,
+                   uint8_t* luts, void* stream);
+int mie_clahe_apply(const void* src, void* dst, int src_dtype, int dst_dtype,
+                    int64_t n, int h, int w,
+                    int64_t src_stride_n, int64_t src_stride_h,
+                    int64_t dst_stride_n, int64_t dst_stride_h,
+                    int gh, int gw, int semantics, float lo, float hi,
+                    const uint8_t* luts, void* stream);
+int mie_clahe(const void* src, void* dst, int src_dtype, int dst_dtype,
+              int64_t n, int h, int w,
+              int64_t src_stride_n, int64_t src_stride_h,
+              int64_t dst_stride_n, int64_t dst_stride_h,
+              int gh, int gw, double clip_limit, int semantics, float lo, float hi,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ global equalisation
+ * Replaces kornia.enhance.equalize(input) == torchvision equalize rule
+ * (reference pyproject.toml:8,16): 256-bin histogram of
+ * trunc(x01*255), step=(N-last_nonzero)//255, lut[k]=clamp((cum[k-1]+step//2)//step),
+ * identity when step==0.  workspace >= mie_equalize_workspace_bytes(n).           */
+size_t mie_equalize_workspace_bytes(int64_t n);
+int mie_equalize(const void* src, void* dst, int src_dtype, int dst_dtype,
+                 int64_t n, int h, int w,
+                 int64_t src_stride_n, int64_t src_stride_h,
+                 int64_t dst_stride_n, int64_t dst_stride_h,
+                 float lo, float hi, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ median
+ * mie_median2d replaces kornia.filters.median_blur(input, kernel_size) (zero
+ * padded, MIE_BORDER_CONSTANT) and skimage.filters.median on 2-D input
+ * (MIE_BORDER_REPLICATE == scipy 'nearest'); SURVEY.md §8(a) A5.  kx, ky in {3,5,7}.
+ * Pure selection: dst_dtype == src_dtype, bit-exact, no normalisation.
+ * mie_median3d replaces skimage.filters.median on a 3-D volume ->
+ * scipy.ndimage.median_filter(footprint=ones((3,3,3)), mode='nearest')
+ * (reference pyproject.toml:12): rank 13 of 27.  The volume is
+ * d planes; halo_lo / halo_hi are the neighbouring slab's boundary planes
+ * (h*w elements, row stride w) or NULL where the slab touches the volume face,
+ * in which case `border` applies (REPLICATE or CONSTANT).                          */
+int mie_median2d(const void* src, void* dst, int dtype, int64_t n, int h, int w,
+                 int64_t src_stride_n, int64_t src_stride_h,
+                 int64_t dst_stride_n, int64_t dst_stride_h,
+                 int ky, int kx, int border, void* stream);
+int mie_median3d(const void* src, void* dst, int dtype, int d, int h, int w,
+                 int64_t src_stride_d, int64_t src_stride_h,
+                 int64_t dst_stride_d, int64_t dst_stride_h,
+                 const void* halo_lo, const void* halo_hi, int border, void* stream);
+
+/* ------------------------------------------------------------------ bilateral
+ * Replaces kornia.filters.bilateral_blur(input, kernel_size, sigma_color,
+ * sigma_space, border_type, color_distance_type) for single-channel planes
+ * (SURVEY.md §8(a) A7).  wspace: ky*kx HOST floats (outer product of the
+ * normalised 1-D Gaussians).  Weight = wspace * mie_exp(coef * d*d),
+ * coef = fp32(-0.5 / sigma_color^2), accumulated in row-major tap order
+ * (num = fma(w, v, num); den += w), out = num / den.  ky, kx odd <= 15.           */
+int mie_bilateral(const void* src, void* dst, int src_dtype, int dst_dtype,
+                  int64_t n, int h, int w,
+                  int64_t src_stride_n, int64_t src_stride_h,
+                  int64_t dst_stride_n, int64_t dst_stride_h,
+                  const float* wspace, int ky, int kx, float sigma_color, int border,
+                  float lo, float hi, void* stream);
+
+/* ------------------------------------------------------------------ fused chain (BASELINE.json config 2)
+ * Gaussian denoise -> CLAHE -> unsharp mask in two launches; equals
+ * mie_gaussian2d -> mie_clahe -> mie_unsharp (F32 intermediates) bit for bit.
+ * wg*: denoise taps, wu*: unsharp taps.  Any geometry is accepted; shapes the
+ * fused kernels do not cover run the same stages unfused inside the library,
+ * using `workspace` for the fp32 intermediates.
+ * `stages`: MIE_CHAIN_ALL runs the chain; MIE_CHAIN_STAGE_A / _B run only the
+ * first / second launch of the fused path against the same workspace (used by
+ * bench.py to time each kernel with CUDA events; MIE_E_UNSUPPORTED when the
+ * geometry takes the unfused path).                                               */
+enum mie_chain_stages { MIE_CHAIN_STAGE_A = 1, MIE_CHAIN_STAGE_B = 2, MIE_CHAIN_ALL = 3 };
+/* 1 if (h, w, grid, kernel sizes) run on the fused two-launch path, else 0. */
+int mie_chain_is_fused(int h, int w, int gh, int gw, int kgx, int kgy, int kux, int kuy);
+size_t mie_chain_workspace_bytes(int64_t n, int h, int w, int gh, int gw);
+int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int dst_dtype,
+                                  int64_t n, int h, int w,
+                                  int64_t src_stride_n, int64_t src_stride_h,
+                                  int64_t dst_stride_n, int64_t dst_stride_h,
+                                  const float* wgx, int kgx, const float* wgy, int kgy,
+                                  int gh, int gw, double clip_limit,
+                                  const float* wux, int kux, const float* wuy, int kuy,
+                                  int border, float lo, float hi, int stages,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIE_H_ */

@@ -1,0 +1,67 @@
+// mie_abi.cu — version / error / device entry points of the C ABI (include/mie.h).
+#include "mie_common.cuh"
+
+extern "C" {
+
+int mie_abi_version(void) { return MIE_ABI_VERSION; }
+
+const char* mie_error_string(int code) {
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    switch (code) {
+        case MIE_OK: return "ok";
+        case MIE_E_NULL: return "null pointer argument";
+        case MIE_E_DTYPE: return "unsupported dtype or dtype combination";
+        case MIE_E_SHAPE: return "invalid or unsupported shape";
+        case MIE_E_STRIDE: return "stride smaller than the row or plane";
+        case MIE_E_GRID: return "grid_size entries must be positive";
+        case MIE_E_PAD: return "cannot compute tiles on the image according to the given grid size";
+        case MIE_E_KERNEL: return "kernel size must be odd, positive and within the supported maximum";
+        case MIE_E_BORDER: return "unknown border mode, or padding not smaller than the image";
+        case MIE_E_WORKSPACE: return "workspace too small";
+        case MIE_E_RANGE: return "value range must satisfy hi > lo";
+        case MIE_E_UNSUPPORTED: return "request not implemented by this build";
+        default: return "unknown error";
+    }
+}
+
+int mie_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    int v = 0;
+    if (sm_count) {
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return (int)e;
+        *sm_count = v;
+    }
+    if (cc_major) {
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev);
+        if (e != cudaSuccess) return (int)e;
+        *cc_major = v;
+    }
+    if (cc_minor) {
+        e = cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMinor, dev);
+        if (e != cudaSuccess) return (int)e;
+        *cc_minor = v;
+    }
+    return MIE_OK;
+}
+
+}  // extern "C"
+
+// ---- temporary: entry points whose kernels land in later commits -------------------------------
+#ifndef MIE_HAVE_EQUALIZE
+extern "C" size_t mie_equalize_workspace_bytes(int64_t) { return 0; }
+extern "C" int mie_equalize(const void*, void*, int, int, int64_t, int, int, int64_t, int64_t, int64_t, int64_t, float,
+                            float, void*, size_t, void*) { return MIE_E_UNSUPPORTED; }
+#endif
+#ifndef MIE_HAVE_MEDIAN
+extern "C" int mie_median2d(const void*, void*, int, int64_t, int, int, int64_t, int64_t, int64_t, int64_t, int, int, int,
+                            void*) { return MIE_E_UNSUPPORTED; }
+extern "C" int mie_median3d(const void*, void*, int, int, int, int, int64_t, int64_t, int64_t, int64_t, const void*,
+                            const void*, int, void*) { return MIE_E_UNSUPPORTED; }
+#endif
+#ifndef MIE_HAVE_BILATERAL
+extern "C" int mie_bilateral(const void*, void*, int, int, int64_t, int, int, int64_t, int64_t, int64_t, int64_t,
+                             const float*, int, int, float, int, float, float, void*) { return MIE_E_UNSUPPORTED; }
+#endif

@@ -1,0 +1,384 @@
+/*
+ * mie_oracle.c — CPU ORACLE (test infrastructure, NOT a product path).
+ *
+ * Plain-C restatement of the enhancement hot path with a fixed fp32 operation
+ * order, used only by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs to check and to time against the CUDA
+ * kernels.  Nothing in the shipped package imports or links this file.
+ *
+ * PARITY UNPINNED: the reference repository contains no implementation, tests or
+ * golden vectors for this path (reference README.md and configs/__init__.py are
+ * 0 bytes).  The algorithms live in third-party packages that are not on disk:
+ *   kornia 0.8.2        (reference pyproject.toml:8,  uv.lock:219-230)
+ *   scikit-image 0.26.0 (reference pyproject.toml:12, uv.lock:619-650)
+ *   scipy 1.17.0        (uv.lock:653-681; scipy 1.18.1 is installed and readable)
+ * Each function below names the upstream function it restates; the kornia /
+ * skimage bodies are restated from their published algorithms (SURVEY.md §8(a),
+ * Appendix A/B).  Pinning available in this image: cv2 4.13 (OpenCV CLAHE, bit
+ * exact), scipy.ndimage (median, Gaussian), torchvision (global equalize) and a
+ * torch-CPU kornia-style twin (oracle/kornia_twin.py) — see tests/test_oracle_*.py.
+ *
+ * Floating point: every multiply-add that the CUDA kernels fuse is an explicit
+ * fmaf() here; compile with -ffp-contract=off so nothing else is fused.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(MIE_ORACLE_NO_CLONES)
+#define MIE_CLONES __attribute__((target_clones("arch=x86-64-v3", "default")))
+#else
+#define MIE_CLONES
+#endif
+
+enum { B_CONSTANT = 0, B_REFLECT = 1, B_REPLICATE = 2, B_CIRCULAR = 3 };
+enum { DT_U8 = 0, DT_U16 = 1, DT_I16 = 2, DT_F32 = 3 };
+
+/* Source index for coordinate i on an axis of length n; -1 = constant (zero). */
+static inline int border_index(int i, int n, int mode) {
+    if (i >= 0 && i < n) return i;
+    if (mode == B_REFLECT) {
+        if (n == 1) return 0;
+        int p = 2 * (n - 1);
+        int m = i % p;
+        if (m < 0) m += p;
+        return m < n ? m : p - m;
+    }
+    if (mode == B_REPLICATE) return i < 0 ? 0 : n - 1;
+    if (mode == B_CIRCULAR) {
+        int m = i % n;
+        return m < 0 ? m + n : m;
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------ pixel <-> [0,1]
+ * x01 = (float(v) - lo) / (hi - lo);  back: rint(clamp(y,0,1)*(hi-lo)) + lo.
+ * This is the normalisation a kornia user applies by hand to integer slices
+ * (SURVEY.md §3 S1, §8(b) "Extensions").                                          */
+MIE_CLONES
+void orc_to01(const void* src, int dtype, int64_t count, float lo, float hi, float* out) {
+    const float rg = hi - lo;
+    int64_t i;
+    switch (dtype) {
+        case DT_U8: for (i = 0; i < count; ++i) out[i] = ((float)((const uint8_t*)src)[i] - lo) / rg; break;
+        case DT_U16: for (i = 0; i < count; ++i) out[i] = ((float)((const uint16_t*)src)[i] - lo) / rg; break;
+        case DT_I16: for (i = 0; i < count; ++i) out[i] = ((float)((const int16_t*)src)[i] - lo) / rg; break;
+        default: memcpy(out, src, (size_t)count * 4); break;
+    }
+}
+
+static inline float quant(float y, float lo, float rg, float tlo, float thi) {
+    float c = fminf(fmaxf(y, 0.0f), 1.0f);
+    float q = rintf(c * rg) + lo;
+    return fminf(fmaxf(q, tlo), thi);
+}
+
+MIE_CLONES
+void orc_from01(const float* in, int dtype, int64_t count, float lo, float hi, void* dst) {
+    const float rg = hi - lo;
+    int64_t i;
+    switch (dtype) {
+        case DT_U8: for (i = 0; i < count; ++i) ((uint8_t*)dst)[i] = (uint8_t)lrintf(quant(in[i], lo, rg, 0.f, 255.f)); break;
+        case DT_U16: for (i = 0; i < count; ++i) ((uint16_t*)dst)[i] = (uint16_t)lrintf(quant(in[i], lo, rg, 0.f, 65535.f)); break;
+        case DT_I16: for (i = 0; i < count; ++i) ((int16_t*)dst)[i] = (int16_t)lrintf(quant(in[i], lo, rg, -32768.f, 32767.f)); break;
+        default: memcpy(dst, in, (size_t)count * 4); break;
+    }
+}
+
+/* ------------------------------------------------------------------ Gaussian / unsharp
+ * kornia.filters.gaussian_blur2d(separable=True) -> filter2d_separable: pad with
+ * border_type, correlate rows with wx, then columns with wy (SURVEY.md §8(a) A3,
+ * Appendix B2).  kornia.filters.unsharp_mask: x + (x - blur) (A4).
+ * Accumulation: acc = w[0]*x[0]; acc = fmaf(w[t], x[t], acc), t = 1..K-1.          */
+MIE_CLONES
+static void sep_plane(const float* in, float* out, float* tmp, int h, int w, const float* wx, int kx,
+                      const float* wy, int ky, int border, int unsharp) {
+    const int rx = kx / 2, ry = ky / 2;
+    for (int y = 0; y < h; ++y) {
+        const float* row = in + (size_t)y * w;
+        for (int x = 0; x < w; ++x) {
+            float acc = 0.f;
+            for (int t = 0; t < kx; ++t) {
+                int sx = border_index(x - rx + t, w, border);
+                float v = sx < 0 ? 0.0f : row[sx];
+                acc = t == 0 ? wx[0] * v : fmaf(wx[t], v, acc);
+            }
+            tmp[(size_t)y * w + x] = acc;
+        }
+    }
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w; ++x) {
+            float acc = 0.f;
+            for (int t = 0; t < ky; ++t) {
+                int sy = border_index(y - ry + t, h, border);
+                float v = sy < 0 ? 0.0f : tmp[(size_t)sy * w + x];
+                acc = t == 0 ? wy[0] * v : fmaf(wy[t], v, acc);
+            }
+            if (unsharp) {
+                float c = in[(size_t)y * w + x];
+                acc = c + (c - acc);
+            }
+            out[(size_t)y * w + x] = acc;
+        }
+    }
+}
+
+int orc_gaussian2d(const float* in, float* out, int64_t n, int h, int w, const float* wx, int kx, const float* wy,
+                   int ky, int border, int unsharp) {
+    int err = 0;
+#pragma omp parallel
+    {
+        float* tmp = (float*)malloc((size_t)h * w * sizeof(float));
+        if (!tmp) {
+#pragma omp atomic write
+            err = 1;
+        } else {
+#pragma omp for schedule(dynamic, 1)
+            for (int64_t i = 0; i < n; ++i)
+                sep_plane(in + (size_t)i * h * w, out + (size_t)i * h * w, tmp, h, w, wx, kx, wy, ky, border, unsharp);
+            free(tmp);
+        }
+    }
+    return err;
+}
+
+/* ------------------------------------------------------------------ CLAHE, kornia semantics
+ * kornia.enhance.equalize_clahe (enhance/equalization.py: _compute_tiles,
+ * _compute_luts, _compute_interpolation_tiles, _compute_equalized_tiles);
+ * SURVEY.md §8(a) A1, Appendix B1.                                                 */
+typedef struct {
+    int h, w, gh, gw, th, tw, hp, wp;
+} geom_t;
+
+/* returns 0 ok, -5 bad grid, -6 padding exceeds the image (kornia ValueError /
+ * torch reflect-pad RuntimeError) */
+static int kornia_geom(int h, int w, int gh, int gw, geom_t* g) {
+    if (gh <= 0 || gw <= 0) return -5;
+    g->h = h; g->w = w; g->gh = gh; g->gw = gw;
+    g->th = (h + gh - 1) / gh; g->tw = (w + gw - 1) / gw;
+    if (g->th & 1) g->th += 1;
+    if (g->tw & 1) g->tw += 1;
+    g->hp = g->th * gh; g->wp = g->tw * gw;
+    if (g->hp - h >= h || g->wp - w >= w) return -6;
+    return 0;
+}
+
+/* torch.histc(tile, bins=256, min=0, max=1): out-of-range and NaN ignored. */
+static inline int kornia_bin(float v) {
+    if (!(v >= 0.0f && v <= 1.0f)) return -1;
+    int b = (int)(v * 256.0f);
+    return b > 255 ? 255 : b;
+}
+
+int orc_clahe_hist_kornia(const float* in, int64_t n, int h, int w, int gh, int gw, uint32_t* hist) {
+    geom_t g;
+    int rc = kornia_geom(h, w, gh, gw, &g);
+    if (rc) return rc;
+    memset(hist, 0, (size_t)n * gh * gw * 256 * sizeof(uint32_t));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < n; ++i) {
+        const float* img = in + (size_t)i * h * w;
+        for (int y = 0; y < g.hp; ++y) {
+            int sy = border_index(y, h, B_REFLECT);
+            int ty = y / g.th;
+            for (int x = 0; x < g.wp; ++x) {
+                int sx = border_index(x, w, B_REFLECT);
+                int b = kornia_bin(img[(size_t)sy * w + sx]);
+                if (b >= 0) hist[(((size_t)i * gh + ty) * gw + x / g.tw) * 256 + b] += 1;
+            }
+        }
+    }
+    return 0;
+}
+
+/* _compute_luts: clamp to max_val, redistribute the excess evenly, residual to
+ * the first bins, cumsum * fp32(255/pixels), clamp, floor. */
+int orc_clahe_luts_from_hist_kornia(const uint32_t* hist, int64_t tiles, int th, int tw, double clip_limit,
+                                    uint8_t* luts) {
+    const int pixels = th * tw;
+    int max_val = 0;
+    if (clip_limit > 0.0) {
+        double q = floor(clip_limit * (double)pixels / 256.0); /* python: clip * pixels // 256 */
+        if (q < 1.0) q = 1.0;
+        max_val = q > 2147483647.0 ? 2147483647 : (int)q;
+    }
+    const float lut_scale = (float)(255.0 / (double)pixels);
+    for (int64_t t = 0; t < tiles; ++t) {
+        int hv[256];
+        for (int b = 0; b < 256; ++b) hv[b] = (int)hist[t * 256 + b];
+        if (max_val > 0) {
+            int sum = 0;
+            for (int b = 0; b < 256; ++b) {
+                if (hv[b] > max_val) hv[b] = max_val;
+                sum += hv[b];
+            }
+            int clipped = pixels - sum;
+            int resid = clipped % 256;
+            int redist = (clipped - resid) / 256;
+            for (int b = 0; b < 256; ++b) hv[b] += redist + (b < resid ? 1 : 0);
+        }
+        int cum = 0;
+        for (int b = 0; b < 256; ++b) {
+            cum += hv[b];
+            float f = (float)cum * lut_scale;
+            f = floorf(fminf(fmaxf(f, 0.0f), 255.0f));
+            luts[t * 256 + b] = (uint8_t)(int)f;
+        }
+    }
+    return 0;
+}
+
+static inline void kornia_axis(int y, int T, int G, int* j0, int* j1, float* wgt) {
+    int hh = T / 2;
+    if (y < hh) {
+        *j0 = *j1 = 0; *wgt = 0.0f;
+    } else if (y >= T * G - hh) {
+        *j0 = *j1 = G - 1; *wgt = 0.0f;
+    } else {
+        int rel = y - hh;
+        *j0 = rel / T;
+        int r = rel - *j0 * T;
+        *j1 = *j0 + 1;
+        *wgt = (float)(T - 1 - r) / (float)(T - 1);
+    }
+}
+
+static inline int kornia_idx(float v) {
+    float f = v * 255.0f;
+    f = fminf(fmaxf(f, 0.0f), 255.0f);
+    return (int)f; /* truncation, like (x*255).long() */
+}
+
+/* _compute_equalized_tiles: gather the <=4 neighbouring LUTs at (x*255).long()
+ * and blend: t = tr + wx*(tl-tr); b = br + wx*(bl-br); out = b + wy*(t-b); /255. */
+MIE_CLONES
+int orc_clahe_apply_kornia(const float* in, float* out, int64_t n, int h, int w, int gh, int gw,
+                           const uint8_t* luts) {
+    geom_t g;
+    int rc = kornia_geom(h, w, gh, gw, &g);
+    if (rc) return rc;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < n; ++i) {
+        const float* img = in + (size_t)i * h * w;
+        float* o = out + (size_t)i * h * w;
+        const uint8_t* nl = luts + (size_t)i * gh * gw * 256;
+        for (int y = 0; y < h; ++y) {
+            int j0, j1; float wy;
+            kornia_axis(y, g.th, gh, &j0, &j1, &wy);
+            for (int x = 0; x < w; ++x) {
+                int i0, i1; float wx;
+                kornia_axis(x, g.tw, gw, &i0, &i1, &wx);
+                int idx = kornia_idx(img[(size_t)y * w + x]);
+                float tl = (float)nl[((size_t)j0 * gw + i0) * 256 + idx], tr = (float)nl[((size_t)j0 * gw + i1) * 256 + idx];
+                float bl = (float)nl[((size_t)j1 * gw + i0) * 256 + idx], br = (float)nl[((size_t)j1 * gw + i1) * 256 + idx];
+                float t = fmaf(wx, tl - tr, tr);
+                float b = fmaf(wx, bl - br, br);
+                float r = fmaf(wy, t - b, b);
+                o[(size_t)y * w + x] = r / 255.0f;
+            }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ CLAHE, OpenCV semantics (uint8)
+ * cv::CLAHE::apply — SURVEY.md §8(a) A1', Appendix A (bit-exact against cv2 4.13). */
+static void opencv_geom(int h, int w, int gh, int gw, geom_t* g) {
+    g->h = h; g->w = w; g->gh = gh; g->gw = gw;
+    g->th = (h + gh - 1) / gh; g->tw = (w + gw - 1) / gw;
+    g->hp = g->th * gh; g->wp = g->tw * gw;
+}
+
+int orc_clahe_hist_opencv_u8(const uint8_t* in, int64_t n, int h, int w, int gh, int gw, uint32_t* hist) {
+    if (gh <= 0 || gw <= 0) return -5;
+    geom_t g;
+    opencv_geom(h, w, gh, gw, &g);
+    memset(hist, 0, (size_t)n * gh * gw * 256 * sizeof(uint32_t));
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t* img = in + (size_t)i * h * w;
+        for (int y = 0; y < g.hp; ++y) {
+            int sy = border_index(y, h, B_REFLECT);
+            for (int x = 0; x < g.wp; ++x) {
+                int sx = border_index(x, w, B_REFLECT);
+                hist[(((size_t)i * gh + y / g.th) * gw + x / g.tw) * 256 + img[(size_t)sy * w + sx]] += 1;
+            }
+        }
+    }
+    return 0;
+}
+
+int orc_clahe_luts_from_hist_opencv(const uint32_t* hist, int64_t tiles, int th, int tw, double clip_limit,
+                                    uint8_t* luts) {
+    const int area = th * tw;
+    int clip = 0;
+    if (clip_limit > 0.0) {
+        double q = clip_limit * (double)area / 256.0;
+        clip = q > 2147483647.0 ? 2147483647 : (int)q;
+        if (clip < 1) clip = 1;
+    }
+    const float lut_scale = 255.0f / (float)area;
+    for (int64_t t = 0; t < tiles; ++t) {
+        int hv[256];
+        for (int b = 0; b < 256; ++b) hv[b] = (int)hist[t * 256 + b];
+        if (clip > 0) {
+            int clipped = 0;
+            for (int b = 0; b < 256; ++b)
+                if (hv[b] > clip) { clipped += hv[b] - clip; hv[b] = clip; }
+            int rb = clipped / 256, res = clipped - rb * 256;
+            for (int b = 0; b < 256; ++b) hv[b] += rb;
+            if (res != 0) {
+                int step = 256 / res;
+                if (step < 1) step = 1;
+                for (int b = 0; b < 256 && res > 0; b += step, --res) hv[b] += 1;
+            }
+        }
+        int cum = 0;
+        for (int b = 0; b < 256; ++b) {
+            cum += hv[b];
+            float f = rintf((float)cum * lut_scale);
+            f = fminf(fmaxf(f, 0.0f), 255.0f);
+            luts[t * 256 + b] = (uint8_t)(int)f;
+        }
+    }
+    return 0;
+}
+
+int orc_clahe_apply_opencv_u8(const uint8_t* in, uint8_t* out, int64_t n, int h, int w, int gh, int gw,
+                              const uint8_t* luts) {
+    if (gh <= 0 || gw <= 0) return -5;
+    geom_t g;
+    opencv_geom(h, w, gh, gw, &g);
+    const float inv_th = 1.0f / (float)g.th, inv_tw = 1.0f / (float)g.tw;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint8_t* img = in + (size_t)i * h * w;
+        uint8_t* o = out + (size_t)i * h * w;
+        const uint8_t* nl = luts + (size_t)i * gh * gw * 256;
+        for (int y = 0; y < h; ++y) {
+            float tyf = (float)y * inv_th - 0.5f;
+            int ty1 = (int)floorf(tyf);
+            float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+            int ty2 = ty1 + 1;
+            if (ty1 < 0) ty1 = 0;
+            if (ty2 > gh - 1) ty2 = gh - 1;
+            for (int x = 0; x < w; ++x) {
+                float txf = (float)x * inv_tw - 0.5f;
+                int tx1 = (int)floorf(txf);
+                float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+                int tx2 = tx1 + 1;
+                if (tx1 < 0) tx1 = 0;
+                if (tx2 > gw - 1) tx2 = gw - 1;
+                int v = img[(size_t)y * w + x];
+                float l11 = nl[((size_t)ty1 * gw + tx1) * 256 + v], l12 = nl[((size_t)ty1 * gw + tx2) * 256 + v];
+                float l21 = nl[((size_t)ty2 * gw + tx1) * 256 + v], l22 = nl[((size_t)ty2 * gw + tx2) * 256 + v];
+                float top = l11 * xa1 + l12 * xa;
+                float bot = l21 * xa1 + l22 * xa;
+                float res = rintf(top * ya1 + bot * ya);
+                res = fminf(fmaxf(res, 0.0f), 255.0f);
+                o[(size_t)y * w + x] = (uint8_t)(int)res;
+            }
+        }
+    }
+    return 0;
+}

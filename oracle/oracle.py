@@ -1,0 +1,236 @@
+"""numpy front-end of the CPU ORACLE (oracle/mie_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; the shipped package never does.
+
+PARITY UNPINNED (see mie_oracle.c header and DESIGN.md §3): the reference holds no
+implementation or golden vectors; kornia 0.8.2 / scikit-image 0.26.0 semantics are
+restated from their published algorithms and pinned against cv2, scipy.ndimage,
+torchvision and oracle/kornia_twin.py where those coincide.
+
+All functions take / return numpy arrays of shape (..., H, W); leading dimensions
+are independent planes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from build import build_oracle  # noqa: E402
+
+_lib = None
+
+BORDERS = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3}
+_DT = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.int16): 2, np.dtype(np.float32): 3}
+_RANGES = {np.dtype(np.uint8): (0.0, 255.0), np.dtype(np.uint16): (0.0, 65535.0), np.dtype(np.int16): (-32768.0, 32767.0)}
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build_oracle())
+        for name in dir(_Sig):
+            if name.startswith("orc_"):
+                fn = getattr(_lib, name)
+                fn.argtypes, fn.restype = getattr(_Sig, name)
+    return _lib
+
+
+_p = C.c_void_p
+_i64, _i, _f, _d = C.c_int64, C.c_int, C.c_float, C.c_double
+
+
+class _Sig:
+    orc_to01 = ([_p, _i, _i64, _f, _f, _p], None)
+    orc_from01 = ([_p, _i, _i64, _f, _f, _p], None)
+    orc_gaussian2d = ([_p, _p, _i64, _i, _i, _p, _i, _p, _i, _i, _i], _i)
+    orc_clahe_hist_kornia = ([_p, _i64, _i, _i, _i, _i, _p], _i)
+    orc_clahe_luts_from_hist_kornia = ([_p, _i64, _i, _i, _d, _p], _i)
+    orc_clahe_apply_kornia = ([_p, _p, _i64, _i, _i, _i, _i, _p], _i)
+    orc_clahe_hist_opencv_u8 = ([_p, _i64, _i, _i, _i, _i, _p], _i)
+    orc_clahe_luts_from_hist_opencv = ([_p, _i64, _i, _i, _d, _p], _i)
+    orc_clahe_apply_opencv_u8 = ([_p, _p, _i64, _i, _i, _i, _i, _p], _i)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _planes(a: np.ndarray, dtype=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if a.ndim < 2:
+        raise ValueError("expected (..., H, W)")
+    h, w = a.shape[-2:]
+    n = int(np.prod(a.shape[:-2], dtype=np.int64)) if a.ndim > 2 else 1
+    return a, n, h, w
+
+
+def _check(rc: int):
+    if rc == -5:
+        raise ValueError("grid_size entries must be positive")
+    if rc == -6:
+        raise ValueError("Cannot compute tiles on the image according to the given grid size")
+    if rc != 0:
+        raise RuntimeError(f"oracle error {rc}")
+
+
+# ------------------------------------------------------------------ pixel mapping
+def default_range(dtype):
+    return _RANGES[np.dtype(dtype)]
+
+
+def to01(a: np.ndarray, value_range=None) -> np.ndarray:
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.float32:
+        return a.copy()
+    lo, hi = value_range if value_range is not None else default_range(a.dtype)
+    out = np.empty(a.shape, np.float32)
+    lib().orc_to01(_ptr(a), _DT[a.dtype], a.size, lo, hi, _ptr(out))
+    return out
+
+
+def from01(y: np.ndarray, dtype, value_range=None) -> np.ndarray:
+    y = np.ascontiguousarray(y, np.float32)
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return y.copy()
+    lo, hi = value_range if value_range is not None else default_range(dtype)
+    out = np.empty(y.shape, dtype)
+    lib().orc_from01(_ptr(y), _DT[dtype], y.size, lo, hi, _ptr(out))
+    return out
+
+
+# ------------------------------------------------------------------ Gaussian / unsharp
+def gaussian_kernel1d(kernel_size: int, sigma: float) -> np.ndarray:
+    """kornia.filters.get_gaussian_kernel1d: x = arange(K) - K//2 (+0.5 if even),
+    exp(-x^2/(2 sigma^2)) normalised.  Evaluated in float64, rounded once to fp32."""
+    k = int(kernel_size)
+    x = np.arange(k, dtype=np.float64) - k // 2
+    if k % 2 == 0:
+        x = x + 0.5
+    g = np.exp(-(x * x) / (2.0 * float(sigma) ** 2))
+    return (g / g.sum()).astype(np.float32)
+
+
+def _pair(v):
+    if isinstance(v, (tuple, list)):
+        return v[0], v[1]
+    return v, v
+
+
+def _sep(x01, kernel_size, sigma, border_type, unsharp):
+    x, n, h, w = _planes(x01, np.float32)
+    ky, kx = _pair(kernel_size)
+    sy, sx = _pair(sigma)
+    wx, wy = gaussian_kernel1d(kx, sx), gaussian_kernel1d(ky, sy)
+    out = np.empty_like(x)
+    rc = lib().orc_gaussian2d(_ptr(x), _ptr(out), n, h, w, _ptr(wx), kx, _ptr(wy), ky, BORDERS[border_type], unsharp)
+    _check(rc)
+    return out
+
+
+def gaussian_blur2d(x01, kernel_size, sigma, border_type="reflect"):
+    return _sep(x01, kernel_size, sigma, border_type, 0)
+
+
+def unsharp_mask(x01, kernel_size, sigma, border_type="reflect"):
+    return _sep(x01, kernel_size, sigma, border_type, 1)
+
+
+# ------------------------------------------------------------------ CLAHE (kornia semantics)
+def kornia_tile_size(h, w, grid_size):
+    gh, gw = grid_size
+    th, tw = -(-h // gh), -(-w // gw)
+    return th + (th & 1), tw + (tw & 1)
+
+
+def clahe_hist(x01, grid_size=(8, 8)) -> np.ndarray:
+    x, n, h, w = _planes(x01, np.float32)
+    gh, gw = grid_size
+    if gh <= 0 or gw <= 0:
+        raise ValueError("grid_size entries must be positive")
+    hist = np.empty((n, gh, gw, 256), np.uint32)
+    _check(lib().orc_clahe_hist_kornia(_ptr(x), n, h, w, gh, gw, _ptr(hist)))
+    return hist.reshape(x.shape[:-2] + (gh, gw, 256))
+
+
+def clahe_luts_from_hist(hist, tile_size, clip_limit) -> np.ndarray:
+    hist = np.ascontiguousarray(hist, np.uint32)
+    luts = np.empty(hist.shape, np.uint8)
+    th, tw = tile_size
+    _check(lib().orc_clahe_luts_from_hist_kornia(_ptr(hist), hist.size // 256, th, tw, float(clip_limit), _ptr(luts)))
+    return luts
+
+
+def clahe_luts(x01, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
+    h, w = x01.shape[-2:]
+    return clahe_luts_from_hist(clahe_hist(x01, grid_size), kornia_tile_size(h, w, grid_size), clip_limit)
+
+
+def clahe_apply(x01, luts, grid_size=(8, 8)) -> np.ndarray:
+    x, n, h, w = _planes(x01, np.float32)
+    gh, gw = grid_size
+    luts = np.ascontiguousarray(luts, np.uint8)
+    assert luts.size == n * gh * gw * 256
+    out = np.empty_like(x)
+    _check(lib().orc_clahe_apply_kornia(_ptr(x), _ptr(out), n, h, w, gh, gw, _ptr(luts)))
+    return out
+
+
+def equalize_clahe(x01, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
+    return clahe_apply(x01, clahe_luts(x01, clip_limit, grid_size), grid_size)
+
+
+# ------------------------------------------------------------------ CLAHE (OpenCV semantics, uint8)
+def opencv_tile_size(h, w, grid_size):
+    gh, gw = grid_size
+    return -(-h // gh), -(-w // gw)
+
+
+def opencv_clahe_hist(img, grid_size=(8, 8)) -> np.ndarray:
+    x, n, h, w = _planes(img, np.uint8)
+    gh, gw = grid_size
+    hist = np.empty((n, gh, gw, 256), np.uint32)
+    _check(lib().orc_clahe_hist_opencv_u8(_ptr(x), n, h, w, gh, gw, _ptr(hist)))
+    return hist.reshape(x.shape[:-2] + (gh, gw, 256))
+
+
+def opencv_clahe_luts(img, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
+    h, w = img.shape[-2:]
+    hist = opencv_clahe_hist(img, grid_size)
+    luts = np.empty(hist.shape, np.uint8)
+    th, tw = opencv_tile_size(h, w, grid_size)
+    _check(lib().orc_clahe_luts_from_hist_opencv(_ptr(hist), hist.size // 256, th, tw, float(clip_limit), _ptr(luts)))
+    return luts
+
+
+def opencv_clahe(img, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
+    """cv2.createCLAHE(clipLimit, tileGridSize=(gw, gh)).apply(img) for uint8; grid_size is (rows, cols)."""
+    x, n, h, w = _planes(img, np.uint8)
+    gh, gw = grid_size
+    luts = opencv_clahe_luts(x, clip_limit, grid_size)
+    out = np.empty_like(x)
+    _check(lib().orc_clahe_apply_opencv_u8(_ptr(x), _ptr(out), n, h, w, gh, gw, _ptr(luts)))
+    return out
+
+
+# ------------------------------------------------------------------ chain (BASELINE.json config 2)
+def chain_gauss_clahe_unsharp(img, denoise_kernel=9, denoise_sigma=1.0, clip_limit=2.0, grid_size=(8, 8),
+                              sharpen_kernel=9, sharpen_sigma=1.0, border_type="reflect", value_range=None,
+                              out_dtype=None, return_stages=False):
+    """Gaussian denoise -> CLAHE -> unsharp mask on [0,1] fp32, quantised once at the end."""
+    img = np.ascontiguousarray(img)
+    out_dtype = np.dtype(out_dtype) if out_dtype is not None else img.dtype
+    x01 = to01(img, value_range)
+    g = gaussian_blur2d(x01, denoise_kernel, denoise_sigma, border_type)
+    luts = clahe_luts(g, clip_limit, grid_size)
+    c = clahe_apply(g, luts, grid_size)
+    u = unsharp_mask(c, sharpen_kernel, sharpen_sigma, border_type)
+    out = from01(u, out_dtype, value_range)
+    if return_stages:
+        return out, {"x01": x01, "gauss": g, "luts": luts, "clahe": c, "unsharp": u}
+    return out

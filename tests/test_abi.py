@@ -1,0 +1,110 @@
+"""CPU-side checks of the C-ABI boundary: the library loads without a GPU, exports every
+symbol include/mie.h declares, and the Python mirror rejects bad arguments like kornia does."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mie.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mie_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import mie_b200
+    from mie_b200 import _ffi
+
+    lib = ctypes.CDLL(_ffi.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mie.h but not exported"
+    assert set(names) == set(_ffi.SIGNATURES), "ctypes signature table out of sync with include/mie.h"
+    assert mie_b200._lib().mie_abi_version() == 1
+
+
+def test_error_strings():
+    from mie_b200 import _ffi
+
+    L = _ffi.lib()
+    assert L.mie_error_string(0) == b"ok"
+    for code in range(-11, 0):
+        assert L.mie_error_string(code) != b"unknown error"
+    with pytest.raises(ValueError):
+        _ffi.check(-6)
+    with pytest.raises(TypeError):
+        _ffi.check(-2)
+    with pytest.raises(NotImplementedError):
+        _ffi.check(-11)
+
+
+def test_workspace_queries_need_no_gpu():
+    from mie_b200 import _ffi
+
+    L = _ffi.lib()
+    assert L.mie_clahe_workspace_bytes(256, 512, 512, 8, 8) == 256 * 64 * 256
+    assert L.mie_chain_workspace_bytes(2, 64, 64, 2, 2) == 2 * 4 * 256 + 2 * 64 * 64 * 4
+    assert L.mie_chain_workspace_bytes(0, 64, 64, 2, 2) == 0
+
+
+def test_argument_errors_match_kornia_types():
+    import mie_b200 as M
+
+    x = torch.zeros(1, 1, 16, 16)
+    with pytest.raises(TypeError):
+        M.equalize_clahe(x, 2, (8, 8))  # clip_limit must be float
+    with pytest.raises(TypeError):
+        M.equalize_clahe(x, 2.0, [8, 8])  # grid_size must be a tuple
+    with pytest.raises(TypeError):
+        M.equalize_clahe(x, 2.0, (8, 8, 8))
+    with pytest.raises(TypeError):
+        M.equalize_clahe(x, 2.0, (8.0, 8))
+    with pytest.raises(ValueError):
+        M.equalize_clahe(x, 2.0, (0, 8))
+    with pytest.raises(NotImplementedError):
+        M.equalize_clahe(x, 2.0, (8, 8), slow_and_differentiable=True)
+    # no CPU path: CPU tensors are refused loudly
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        M.equalize_clahe(x, 2.0, (8, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        M.gaussian_blur2d(x, 9, 1.0)
+    with pytest.raises(ValueError):
+        M.gaussian_blur2d(x.to(torch.float32), 4, 1.0)  # even kernel
+
+
+def test_host_side_argument_validation_of_the_abi():
+    """Argument errors are detected on the host before any launch (no GPU needed)."""
+    from mie_b200 import _ffi
+
+    L = _ffi.lib()
+    import numpy as np
+
+    w = np.ones(9, np.float32) / 9
+    fake = 0x1000  # never dereferenced: validation fails first
+    args = dict(n=1, h=64, w=64)
+    # reflect halo >= image
+    rc = L.mie_gaussian2d(fake, fake, 3, 3, 1, 4, 4, 16, 4, 16, 4, w.ctypes.data, 9, w.ctypes.data, 9, 1, 0.0, 1.0, None)
+    assert rc == -8
+    rc = L.mie_gaussian2d(fake, fake, 3, 3, 1, 64, 64, 4096, 64, 4096, 64, w.ctypes.data, 8, w.ctypes.data, 9, 1, 0.0,
+                          1.0, None)
+    assert rc == -7
+    rc = L.mie_gaussian2d(None, fake, 3, 3, 1, 64, 64, 4096, 64, 4096, 64, w.ctypes.data, 9, w.ctypes.data, 9, 1, 0.0,
+                          1.0, None)
+    assert rc == -1
+    rc = L.mie_gaussian2d(fake, fake, 1, 0, 1, 64, 64, 4096, 64, 4096, 64, w.ctypes.data, 9, w.ctypes.data, 9, 1, 0.0,
+                          65535.0, None)
+    assert rc == -2  # u16 -> u8 not allowed
+    rc = L.mie_clahe_luts(fake, 3, 1, 20, 20, 400, 20, 0, 8, 2.0, 0, 0.0, 1.0, fake, None)
+    assert rc == -5
+    rc = L.mie_clahe_luts(fake, 3, 1, 3, 3, 9, 3, 8, 8, 2.0, 0, 0.0, 1.0, fake, None)
+    assert rc == -6  # kornia: cannot compute tiles
+    rc = L.mie_clahe(fake, fake, 1, 1, 1, 64, 64, 4096, 64, 4096, 64, 8, 8, 2.0, 0, 0.0, 65535.0, fake, 10, None)
+    assert rc == -9
+    rc = L.mie_clahe_luts(fake, 1, 1, 64, 64, 4096, 64, 8, 8, 2.0, 0, 5.0, 5.0, fake, None)
+    assert rc == -10

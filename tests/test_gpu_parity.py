@@ -1,0 +1,269 @@
+"""GPU parity tests (run with -m gpu on a B200): CUDA path through the C ABI vs the CPU oracle.
+
+Bars: integer artefacts (histograms, LUTs, quantised outputs, OpenCV-mode
+pixels) bit-exact; float outputs: the kernels follow the oracle's fp32 operation order, so
+they are asserted bit-exact too, with the north star's tolerance (rel 1e-5) as the documented
+fallback bar `RTOL` used only where an op cannot be made bit-reproducible.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5  # north-star tolerance for floating-point stages (pre-quantisation)
+
+NP2T = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16, np.dtype(np.int16): torch.int16,
+        np.dtype(np.float32): torch.float32}
+
+
+def gpu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def cpu(t):
+    return t.cpu().numpy()
+
+
+def images(kind, shape, dtype, seed=0):
+    from mie_b200 import synthetic
+
+    if dtype == np.float32:
+        if kind == "K":
+            return np.full(shape, 0.25, np.float32)
+        if kind == "U":
+            return np.random.default_rng(seed).random(shape, dtype=np.float32)
+        return (synthetic.phantom(shape, np.uint16, seed).astype(np.float32) / np.float32(4095.0)).astype(np.float32)
+    return synthetic.make(kind, shape, dtype, seed)
+
+
+# ---------------------------------------------------------------------------- CLAHE (kornia semantics)
+CLAHE_CASES = [
+    # (shape, grid, clip)
+    ((2, 1, 512, 512), (8, 8), 2.0),
+    ((1, 1, 512, 512), (8, 8), 40.0),
+    ((1, 2, 100, 130), (4, 6), 2.0),   # padding + odd->even tile bump
+    ((1, 1, 20, 20), (8, 8), 1.0),     # pad (12) larger than a tile (4)
+    ((1, 1, 57, 91), (2, 3), 0.0),     # clipping disabled
+    ((1, 1, 37, 41), (1, 1), 3.0),     # single tile
+    ((1, 1, 256, 1024), (2, 16), 0.7),
+]
+
+
+@pytest.mark.parametrize("kind", ["U", "P", "K"])
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8, np.int16])
+def test_clahe_hist_and_luts_bit_exact(dev, kind, dtype):
+    import mie_b200 as M
+    import oracle as O
+
+    for shape, grid, clip in CLAHE_CASES:
+        x = images(kind, shape, dtype, seed=11)
+        x01 = O.to01(x)
+        h_ref = O.clahe_hist(x01, grid)
+        l_ref = O.clahe_luts(x01, clip, grid)
+        xt = gpu(x, dev)
+        h = cpu(M.clahe_histograms(xt, grid))
+        l = cpu(M.clahe_luts(xt, clip, grid))
+        assert np.array_equal(h.astype(np.uint32), h_ref), (shape, grid)
+        assert np.array_equal(l, l_ref), (shape, grid, clip)
+        # properties: mass conserved, LUT monotone
+        th, tw = O.kornia_tile_size(shape[-2], shape[-1], grid)
+        assert (h.sum(-1) == th * tw).all()
+        assert (np.diff(l.astype(np.int32), axis=-1) >= 0).all()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8, np.int16])
+def test_clahe_apply_teacher_forced(dev, dtype):
+    import mie_b200 as M
+    import oracle as O
+
+    for shape, grid, clip in CLAHE_CASES:
+        x = images("P", shape, dtype, seed=5)
+        x01 = O.to01(x)
+        luts = O.clahe_luts(x01, clip, grid)
+        ref = O.clahe_apply(x01, luts, grid)
+        xt, lt = gpu(x, dev), gpu(luts, dev)
+        got_f = cpu(M.clahe_apply(xt, lt, grid, out_dtype=torch.float32))
+        assert np.array_equal(got_f, ref), f"max abs diff {np.abs(got_f - ref).max()}"
+        if dtype != np.float32:
+            got_q = cpu(M.clahe_apply(xt, lt, grid))
+            assert np.array_equal(got_q, O.from01(ref, dtype))
+
+
+def test_clahe_end_to_end_and_value_range(dev):
+    import mie_b200 as M
+    import oracle as O
+
+    x = images("P", (3, 1, 512, 512), np.int16, seed=2)  # HU-like [-1024, 3071]
+    vr = (-1024.0, 3071.0)
+    ref = O.from01(O.equalize_clahe(O.to01(x, vr), 2.0, (8, 8)), np.int16, vr)
+    got = cpu(M.equalize_clahe(gpu(x, dev), 2.0, (8, 8), value_range=vr))
+    assert np.array_equal(got, ref)
+    # shapes (H,W) and (C,H,W) keep their rank
+    assert M.equalize_clahe(gpu(x[0, 0], dev), 2.0, (8, 8)).shape == (512, 512)
+    assert M.equalize_clahe(gpu(x[:, 0], dev), 2.0, (8, 8)).shape == (3, 512, 512)
+    # kornia raises ValueError when the grid cannot tile the image
+    with pytest.raises(ValueError):
+        M.equalize_clahe(gpu(np.zeros((3, 3), np.float32), dev), 2.0, (8, 8))
+
+
+def test_clahe_constant_image_stays_constant(dev):
+    import mie_b200 as M
+
+    y = cpu(M.equalize_clahe(gpu(np.full((1, 1, 512, 512), 0.5, np.float32), dev), 2.0, (8, 8)))
+    assert (y == y.flat[0]).all()
+
+
+def test_clahe_opencv_semantics_matches_cv2(dev):
+    cv2 = pytest.importorskip("cv2")
+    import mie_b200 as M
+
+    rng = np.random.default_rng(0)
+    for (h, w, g, clip) in [(512, 512, (8, 8), 2.0), (512, 512, (8, 8), 40.0), (300, 500, (8, 8), 2.0),
+                            (1024, 1024, (16, 16), 2.0), (512, 512, (8, 8), 0.0), (512, 512, (4, 4), 300.0),
+                            (37, 53, (3, 5), 1.5)]:
+        yy, xx = np.mgrid[0:h, 0:w]
+        img = np.clip(128 + 60 * np.sin(xx / 37.0) + 50 * np.cos(yy / 23.0) + rng.normal(0, 12, (h, w)), 0, 255)
+        img = img.astype(np.uint8)
+        ref = cv2.createCLAHE(clip, (g[1], g[0])).apply(img)
+        got = cpu(M.equalize_clahe(gpu(img, dev), float(clip), g, semantics="opencv"))
+        assert np.array_equal(got, ref), (h, w, g, clip, int((got != ref).sum()))
+
+
+# ---------------------------------------------------------------------------- Gaussian / unsharp
+GAUSS_CASES = [
+    # (shape, kernel_size, sigma, border)
+    ((2, 1, 512, 512), 9, 1.0, "reflect"),
+    ((1, 1, 100, 130), 7, 1.0, "reflect"),
+    ((1, 2, 65, 63), 5, 1.2, "replicate"),
+    ((1, 1, 64, 64), 3, 0.8, "constant"),
+    ((1, 1, 33, 200), 9, 2.0, "circular"),
+    ((1, 1, 70, 70), 11, 1.5, "reflect"),        # generic path (K > 9)
+    ((1, 1, 50, 60), (3, 9), (0.7, 1.5), "reflect"),  # generic path (non-square)
+    ((1, 1, 9, 9), 9, 1.0, "reflect"),           # halo == dim-1 (largest legal reflect)
+    ((1, 1, 40, 40), 33, 5.0, "replicate"),      # maximum taps
+]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8, np.int16])
+@pytest.mark.parametrize("op", ["gaussian_blur2d", "unsharp_mask"])
+def test_gaussian_and_unsharp_bit_exact(dev, dtype, op):
+    import mie_b200 as M
+    import oracle as O
+
+    for shape, k, s, border in GAUSS_CASES:
+        x = images("U", shape, dtype, seed=7)
+        ref = getattr(O, op)(O.to01(x), k, s, border)
+        xt = gpu(x, dev)
+        got = cpu(getattr(M, op)(xt, k, s, border, out_dtype=torch.float32))
+        assert np.array_equal(got, ref), (shape, k, border, float(np.abs(got - ref).max()))
+        if dtype != np.float32:
+            gq = cpu(getattr(M, op)(xt, k, s, border))
+            assert np.array_equal(gq, O.from01(ref, dtype)), (shape, k, border)
+
+
+def test_gaussian_against_independent_binaries(dev):
+    """cv2.GaussianBlur(BORDER_REFLECT_101) and scipy.ndimage.gaussian_filter(mode='mirror') use the same
+    weights and border; they agree with the kernel to fp32 rounding."""
+    cv2 = pytest.importorskip("cv2")
+    ndi = pytest.importorskip("scipy.ndimage")
+    import mie_b200 as M
+
+    x = np.random.default_rng(3).random((200, 333), dtype=np.float32)
+    got = cpu(M.gaussian_blur2d(gpu(x, dev), 9, 1.0))
+    a = cv2.GaussianBlur(x, (9, 9), 1.0, borderType=cv2.BORDER_REFLECT_101)
+    b = ndi.gaussian_filter(x, 1.0, mode="mirror", radius=4)
+    assert np.abs(got - a).max() <= 5e-7
+    assert np.abs(got - b).max() <= 5e-7
+
+
+def test_pixel_mapping_exhaustive_uint16(dev):
+    """All 65 536 uint16 codes: x01 = v/65535 matches IEEE division; quantise(normalise(v)) == v."""
+    import mie_b200 as M
+
+    v = np.arange(65536, dtype=np.uint16).reshape(256, 256)
+    xt = gpu(v, dev)
+    f = cpu(M.gaussian_blur2d(xt, 1, 1.0, out_dtype=torch.float32))   # one tap of weight 1 = identity
+    assert np.array_equal(f, v.astype(np.float32) / np.float32(65535.0))
+    assert np.array_equal(cpu(M.gaussian_blur2d(xt, 1, 1.0)), v)
+    s = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16).reshape(256, 256)
+    assert np.array_equal(cpu(M.gaussian_blur2d(gpu(s, dev), 1, 1.0)), s)
+
+
+# ---------------------------------------------------------------------------- fused chain
+@pytest.mark.parametrize("kind", ["P", "U", "K"])
+def test_chain_fused_bit_exact_and_equals_composition(dev, kind):
+    import mie_b200 as M
+    import oracle as O
+
+    x = images(kind, (6, 1, 512, 512), np.uint16, seed=21)
+    xt = gpu(x, dev)
+    cfg = M.ChainConfig()
+    got = cpu(M.enhance_chain(xt, cfg))
+    ref, st = O.chain_gauss_clahe_unsharp(x, return_stages=True)
+    assert np.array_equal(got, ref), int((got != ref).sum())
+    # stage by stage on the GPU (fp32 intermediates) == fused
+    g = M.gaussian_blur2d(xt, 9, 1.0, out_dtype=torch.float32)
+    assert np.array_equal(cpu(g), st["gauss"])
+    luts = M.clahe_luts(g, 2.0, (8, 8))
+    assert np.array_equal(cpu(luts), st["luts"])        # "LUT entries differing" must be 0
+    c = M.equalize_clahe(g, 2.0, (8, 8))
+    assert np.array_equal(cpu(c), st["clahe"])
+    u = M.unsharp_mask(c, 9, 1.0)
+    assert np.array_equal(cpu(u), st["unsharp"])
+    assert np.array_equal(O.from01(cpu(u), np.uint16), got)
+    # float output of the fused path
+    gf = cpu(M.enhance_chain(xt, cfg, out_dtype=torch.float32))
+    assert np.array_equal(gf, st["unsharp"])
+
+
+@pytest.mark.parametrize("case", [
+    dict(shape=(2, 1, 500, 300), grid=(8, 8)),                      # CLAHE padding -> unfused path inside the library
+    dict(shape=(1, 1, 256, 256), grid=(4, 4), dk=5, sk=7),          # 64-px tiles, other radii (fused)
+    dict(shape=(1, 1, 128, 192), grid=(4, 4), dk=3, sk=3),          # 32x48 tiles (fused, partial stencil tiles)
+    dict(shape=(1, 1, 512, 512), grid=(2, 2)),                      # 256-px tiles -> unfused
+    dict(shape=(1, 1, 96, 96), grid=(2, 2), dk=11),                 # 11 taps -> unfused
+    dict(shape=(1, 1, 64, 64), grid=(8, 8), border="replicate"),    # 8-px tiles: many LUTs per block
+])
+@pytest.mark.parametrize("dtype", [np.uint16, np.int16, np.uint8, np.float32])
+def test_chain_geometries(dev, case, dtype):
+    import mie_b200 as M
+    import oracle as O
+
+    x = images("P", case["shape"], dtype, seed=4)
+    dk, sk = case.get("dk", 9), case.get("sk", 9)
+    border = case.get("border", "reflect")
+    cfg = M.ChainConfig(denoise_kernel_size=dk, sharpen_kernel_size=sk, grid_size=case["grid"], border_type=border)
+    got = cpu(M.enhance_chain(gpu(x, dev), cfg))
+    ref = O.chain_gauss_clahe_unsharp(x, dk, 1.0, 2.0, case["grid"], sk, 1.0, border)
+    assert np.array_equal(got, ref), int((got != ref).sum())
+
+
+def test_chain_full_config2_batch(dev):
+    """BASELINE.json config 2 at full size (256 x 512 x 512 uint16): bit-exact against the oracle, and
+    batch-independent (a checksum of per-slice checksums equals the one from slice-at-a-time calls)."""
+    import mie_b200 as M
+    import oracle as O
+
+    x = images("P", (256, 1, 512, 512), np.uint16, seed=0)
+    xt = gpu(x, dev)
+    got = cpu(M.enhance_chain(xt))
+    ref = O.chain_gauss_clahe_unsharp(x)
+    assert np.array_equal(got, ref), int((got != ref).sum())
+    whole = hashlib.sha256(b"".join(hashlib.sha256(got[i].tobytes()).digest() for i in range(256))).hexdigest()
+    parts = []
+    for i in range(0, 256, 37):  # ragged chunks
+        parts.append(cpu(M.enhance_chain(xt[i:i + 37])))
+    chunks = np.concatenate(parts)
+    again = hashlib.sha256(b"".join(hashlib.sha256(chunks[i].tobytes()).digest() for i in range(256))).hexdigest()
+    assert whole == again
+
+
+def test_empty_batch(dev):
+    import mie_b200 as M
+
+    x = torch.empty((0, 1, 64, 64), dtype=torch.uint16, device=dev)
+    assert M.enhance_chain(x).shape == (0, 1, 64, 64)
+    assert M.gaussian_blur2d(x, 9, 1.0).shape == (0, 1, 64, 64)
