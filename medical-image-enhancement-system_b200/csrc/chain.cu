@@ -14,8 +14,7 @@
 // intermediates bit for bit (same operation order; tests/test_chain_gpu.py).
 // Shapes the fused kernels do not cover (CLAHE padding needed, tiles > 64 px,
 // non-square or > 9-tap kernels) run those three stages unfused.
-#include "clahe.cuh"
-#include "stencil.cuh"
+#include "chain_fast.cuh"
 
 namespace mie {
 
@@ -29,17 +28,6 @@ int clahe_luts_impl(const void* src, int sd, int64_t n, int h, int w, int64_t ss
 int clahe_apply_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
                      int64_t dsn, int64_t dsh, int gh, int gw, int semantics, float lo, float hi, const uint8_t* luts,
                      cudaStream_t st);
-
-struct ChainAArgs {
-    const void* src;
-    int64_t ssn, ssh;
-    uint8_t* idx;   // n*h*w
-    uint8_t* luts;  // n*gh*gw*256
-    ClaheGeom g;
-    LutParams lp;
-    int border;
-    float lo, rg;
-};
 
 template <typename SrcT, int R>
 __global__ void __launch_bounds__(256)
@@ -108,18 +96,6 @@ chain_a_kernel(ChainAArgs a, Taps wx, Taps wy) {
     for (int i = 0; i < 8; ++i) hv += s_hist[i * kBins + tid];
     a.luts[tile * kBins + tid] = lut_entry_from_count<MIE_CLAHE_KORNIA>(hv, a.lp, s_red);
 }
-
-struct ChainBArgs {
-    const uint8_t* idx;
-    const uint8_t* luts;
-    void* dst;
-    int64_t dsn, dsh;
-    ClaheGeom g;
-    int tiles_x, tiles_y;
-    int border;
-    int max_lut_tiles;  // LUT staging capacity per axis
-    float lo, rg;
-};
 
 struct AxisEntry {
     int o0, o1;  // LUT offsets (bytes) of the two neighbouring tiles along this axis
@@ -321,6 +297,21 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     a.src = src; a.ssn = src_stride_n; a.ssh = src_stride_h; a.idx = plane; a.luts = luts; a.g = g;
     a.lp = make_lut_params(g, clip_limit, MIE_CLAHE_KORNIA);
     a.border = border; a.lo = lo; a.rg = hi - lo;
+    const bool fast = fast_chain_ok(g, src_dtype, dst_dtype, src, src_stride_n, src_stride_h, dst, dst_stride_n,
+                                    dst_stride_h, kgx, kux, border, lo, hi);
+    ChainBArgs b;
+    b.idx = plane; b.luts = luts; b.dst = dst; b.dsn = dst_stride_n; b.dsh = dst_stride_h; b.g = g;
+    b.tiles_x = ceil_div(w, kTile); b.tiles_y = ceil_div(h, kTile); b.border = border; b.max_lut_tiles = lut_cap;
+    b.lo = lo; b.rg = hi - lo;
+    if (n * (int64_t)b.tiles_x * b.tiles_y > 2147483647LL) return MIE_E_SHAPE;
+    if (fast) {
+        if (stages & MIE_CHAIN_STAGE_A) {
+            rc = launch_chain_a_fast(a, src_dtype, tgx, tgy, kgx / 2, n, st);
+            if (rc) return rc;
+        }
+        if (stages & MIE_CHAIN_STAGE_B) rc = launch_chain_b_fast(b, dst_dtype, tux, tuy, kux / 2, n, st);
+        return rc;
+    }
 #define MIE_CHAIN_A(R_)                                                                          \
     MIE_DISPATCH_SRC(src_dtype, rc = (launch_a<SrcT, R_>(a, tgx, tgy, n, st)))
     if (stages & MIE_CHAIN_STAGE_A) {
@@ -333,12 +324,6 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     }
 #undef MIE_CHAIN_A
     if (rc || !(stages & MIE_CHAIN_STAGE_B)) return rc;
-
-    ChainBArgs b;
-    b.idx = plane; b.luts = luts; b.dst = dst; b.dsn = dst_stride_n; b.dsh = dst_stride_h; b.g = g;
-    b.tiles_x = ceil_div(w, kTile); b.tiles_y = ceil_div(h, kTile); b.border = border; b.max_lut_tiles = lut_cap;
-    b.lo = lo; b.rg = hi - lo;
-    if (n * (int64_t)b.tiles_x * b.tiles_y > 2147483647LL) return MIE_E_SHAPE;
 #define MIE_CHAIN_B(R_)                                                                          \
     switch (dst_dtype) {                                                                         \
         case MIE_U8: rc = launch_b<uint8_t, R_>(b, tux, tuy, n, lut_cap, st); break;             \

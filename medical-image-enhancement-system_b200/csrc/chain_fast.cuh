@@ -1,0 +1,240 @@
+// chain_fast.cuh — the tuned fused-chain kernels for the headline geometry
+// (BASELINE.json config 2: 64x64-pixel CLAHE tiles, 9-tap Gaussians, integer
+// slices with their full dtype range).  Same arithmetic, bit for bit, as the
+// generic fused kernels in chain.cu and as oracle/mie_oracle.c; what changes is how
+// few instructions each pixel costs:
+//
+//   * 64/128-bit global loads along x; no haloed input tile in shared memory for
+//     chain_a — the horizontal pass runs straight out of registers;
+//   * integer -> [0,1] without a divide:  v/65535 == fma(t, c, t) with
+//     t = v * 2^-16 (built by OR-ing v into a float's mantissa) and c = RN(1/65535);
+//     exact for all 65 536 codes (tests/test_host_logic.py emulates it exhaustively);
+//   * floor()/trunc()/rint() by adding 2^23 in the matching rounding mode instead
+//     of F2I conversions (which run on the 16-lane conversion pipe);
+//   * x/255 as q0 = x*r; q = fma(fma(-255, q0, x), r, q0) (correctly rounded);
+//   * histogram votes: a warp peels off one distinct bin per iteration
+//     (shfl + ballot + popc) and a single lane adds the population count, so
+//     smooth (blurred) images cost ~1 shared-memory atomic per warp per distinct
+//     bin instead of 32 colliding ones;
+//   * the clip / redistribute / scan -> LUT tail runs in one warp (8 bins per lane);
+//   * chain_b packs the four neighbouring LUTs of each interpolation cell into one
+//     32-bit word per grey level, so a pixel needs ONE shared-memory lookup.
+#pragma once
+
+#include "clahe.cuh"
+#include "stencil.cuh"
+
+namespace mie {
+
+constexpr int kFastThreads = 288;  // 9 warps: (64+2*4) rows x 8 segments = 2 x 288 row-pass items
+
+// Launch arguments shared by the generic (chain.cu) and tuned (chain_fast.cu) fused kernels.
+struct ChainAArgs {
+    const void* src;
+    int64_t ssn, ssh;
+    uint8_t* idx;   // n*h*w lookup indices trunc(G*255)
+    uint8_t* luts;  // n*gh*gw*256
+    ClaheGeom g;
+    LutParams lp;
+    int border;
+    float lo, rg;
+};
+
+struct ChainBArgs {
+    const uint8_t* idx;
+    const uint8_t* luts;
+    void* dst;
+    int64_t dsn, dsh;
+    ClaheGeom g;
+    int tiles_x, tiles_y;
+    int border;
+    int max_lut_tiles;  // LUT staging capacity (generic kernel)
+    float lo, rg;
+};
+
+// Defined in chain_fast.cu.  `fast_chain_ok` tells whether the tuned kernels cover the request.
+bool fast_chain_ok(const ClaheGeom& g, int src_dtype, int dst_dtype, const void* src, int64_t ssn, int64_t ssh,
+                   const void* dst, int64_t dsn, int64_t dsh, int kg, int ku, int border, float lo, float hi);
+int launch_chain_a_fast(const ChainAArgs& a, int src_dtype, const Taps& wx, const Taps& wy, int R, int64_t n,
+                        cudaStream_t st);
+int launch_chain_b_fast(const ChainBArgs& b, int dst_dtype, const Taps& wx, const Taps& wy, int R, int64_t n,
+                        cudaStream_t st);
+
+// ---------------------------------------------------------------- exact default-range pixel mapping
+template <typename T>
+struct Fast;
+
+template <>
+struct Fast<uint16_t> {
+    static constexpr float kC = 1.5259021893143654e-05f;  // RN(1/65535)
+    static __device__ __forceinline__ float from_bits(uint32_t lo16_in_mantissa) {
+        const float t = __fsub_rn(__uint_as_float(lo16_in_mantissa), 128.0f);  // v * 2^-16, exact
+        return __fmaf_rn(t, kC, t);
+    }
+    static __device__ __forceinline__ float one(uint16_t v) { return from_bits(0x43000000u | v); }
+    // 16 consecutive pixels; p is 8-byte aligned and p+4 is 16-byte aligned
+    static __device__ __forceinline__ void load16(const uint16_t* p, float* x) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + 4));
+        const uint2 c = __ldg(reinterpret_cast<const uint2*>(p + 12));
+        const uint32_t w[8] = {a.x, a.y, b.x, b.y, b.z, b.w, c.x, c.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            x[2 * i] = from_bits(__byte_perm(w[i], 0x43000000u, 0x7610));
+            x[2 * i + 1] = from_bits(__byte_perm(w[i], 0x43000000u, 0x7632));
+        }
+    }
+    static __device__ __forceinline__ uint32_t quant(float y) {  // rint(clamp(y,0,1)*65535)
+        const float c = fminf(fmaxf(y, 0.0f), 1.0f);
+        return __float_as_uint(__fadd_rn(__fmul_rn(c, 65535.0f), 8388608.0f)) & 0xFFFFu;
+    }
+    static __device__ __forceinline__ void store4(uint16_t* p, const float* y) {
+        uint2 o;
+        o.x = quant(y[0]) | (quant(y[1]) << 16);
+        o.y = quant(y[2]) | (quant(y[3]) << 16);
+        *reinterpret_cast<uint2*>(p) = o;
+    }
+};
+
+template <>
+struct Fast<int16_t> {
+    static __device__ __forceinline__ float one(int16_t v) {
+        return Fast<uint16_t>::from_bits(0x43000000u | ((uint32_t)(uint16_t)v ^ 0x8000u));
+    }
+    static __device__ __forceinline__ void load16(const int16_t* p, float* x) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + 4));
+        const uint2 c = __ldg(reinterpret_cast<const uint2*>(p + 12));
+        const uint32_t w[8] = {a.x, a.y, b.x, b.y, b.z, b.w, c.x, c.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t u = w[i] ^ 0x80008000u;  // v + 32768 for both halves
+            x[2 * i] = Fast<uint16_t>::from_bits(__byte_perm(u, 0x43000000u, 0x7610));
+            x[2 * i + 1] = Fast<uint16_t>::from_bits(__byte_perm(u, 0x43000000u, 0x7632));
+        }
+    }
+    static __device__ __forceinline__ void store4(int16_t* p, const float* y) {
+        uint2 o;
+        o.x = (Fast<uint16_t>::quant(y[0]) | (Fast<uint16_t>::quant(y[1]) << 16)) ^ 0x80008000u;
+        o.y = (Fast<uint16_t>::quant(y[2]) | (Fast<uint16_t>::quant(y[3]) << 16)) ^ 0x80008000u;
+        *reinterpret_cast<uint2*>(p) = o;
+    }
+};
+
+template <>
+struct Fast<uint8_t> {
+    static constexpr float kC = 0.003921568859368563f;  // RN(1/255)
+    static __device__ __forceinline__ float from_bits(uint32_t lo8_in_mantissa) {
+        const float t = __fsub_rn(__uint_as_float(lo8_in_mantissa), 32768.0f);  // v * 2^-8, exact
+        return __fmaf_rn(t, kC, t);
+    }
+    static __device__ __forceinline__ float one(uint8_t v) { return from_bits(0x47000000u | v); }
+    static __device__ __forceinline__ void load16(const uint8_t* p, float* x) {  // p 4-byte aligned, p+4 8-byte aligned
+        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(p));
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p + 4));
+        const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(p + 12));
+        const uint32_t w[4] = {a, b.x, b.y, c};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            x[4 * i] = from_bits(__byte_perm(w[i], 0x47000000u, 0x7650));
+            x[4 * i + 1] = from_bits(__byte_perm(w[i], 0x47000000u, 0x7651));
+            x[4 * i + 2] = from_bits(__byte_perm(w[i], 0x47000000u, 0x7652));
+            x[4 * i + 3] = from_bits(__byte_perm(w[i], 0x47000000u, 0x7653));
+        }
+    }
+    static __device__ __forceinline__ uint32_t quant(float y) {
+        const float c = fminf(fmaxf(y, 0.0f), 1.0f);
+        return __float_as_uint(__fadd_rn(__fmul_rn(c, 255.0f), 8388608.0f)) & 0xFFu;
+    }
+    static __device__ __forceinline__ void store4(uint8_t* p, const float* y) {
+        *reinterpret_cast<uint32_t*>(p) = quant(y[0]) | (quant(y[1]) << 8) | (quant(y[2]) << 16) | (quant(y[3]) << 24);
+    }
+};
+
+template <>
+struct Fast<float> {
+    static __device__ __forceinline__ float one(float v) { return v; }
+    static __device__ __forceinline__ void load16(const float* p, float* x) {
+        const float4* q = reinterpret_cast<const float4*>(p);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = __ldg(q + i);
+            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        }
+    }
+    static __device__ __forceinline__ void store4(float* p, const float* y) {
+        *reinterpret_cast<float4*>(p) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+};
+
+// ---------------------------------------------------------------- index rules without F2I
+// floor(g*256) and trunc(clamp(g*255)): add 2^23 rounding toward -inf and read the
+// mantissa.  Same values as kornia_bin / kornia_idx (clahe.cuh).
+__device__ __forceinline__ int fast_bin(float g) {  // -1 = not counted (outside [0,1] or NaN)
+    const int n = (int)(__float_as_uint(__fmaf_rd(g, 256.0f, 8388608.0f)) - 0x4B000000u);
+    return (g >= 0.0f && g <= 1.0f) ? min(n, 255) : -1;
+}
+__device__ __forceinline__ uint32_t fast_idx(float g) {
+    const float f = fminf(fmaxf(__fmul_rn(g, 255.0f), 0.0f), 255.0f);
+    return __float_as_uint(__fadd_rd(f, 8388608.0f)) & 0xFFu;
+}
+
+// x / 255, correctly rounded (Markstein: y = RN(1/b), q0 = RN(a*y), r = a - b*q0 exact, RN(q0 + r*y)).
+__device__ __forceinline__ float div255(float x) {
+    constexpr float r = 0.003921568859368563f;
+    const float q0 = __fmul_rn(x, r);
+    return __fmaf_rn(__fmaf_rn(-255.0f, q0, x), r, q0);
+}
+
+// One warp adds `bin` (or nothing when bin < 0) of each lane to its private histogram.
+__device__ __forceinline__ void hist_vote_add(int* s_h, int bin, int lane) {
+    unsigned rem = __ballot_sync(0xffffffffu, bin >= 0);
+    while (rem) {
+        const int leader = __ffs(rem) - 1;
+        const int b0 = __shfl_sync(0xffffffffu, bin, leader);
+        const unsigned m = __ballot_sync(0xffffffffu, bin == b0);
+        if (lane == leader) atomicAdd(&s_h[b0], __popc(m));
+        rem &= ~m;
+    }
+}
+
+// Clip / redistribute / cumulate -> 256 LUT bytes, computed by ONE warp from the
+// block-total histogram in shared memory (lane L owns bins 8L..8L+7).
+__device__ __forceinline__ void warp_build_lut(const int* s_tot, const LutParams& p, uint8_t* lut_out, int lane) {
+    int hv[8];
+    {
+        const int4 a = *reinterpret_cast<const int4*>(s_tot + 8 * lane);
+        const int4 b = *reinterpret_cast<const int4*>(s_tot + 8 * lane + 4);
+        hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
+    }
+    if (p.clip > 0) {
+        int local = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { hv[k] = min(hv[k], p.clip); local += hv[k]; }
+        const int clipped = p.pixels - warp_sum(local);
+        const int resid = clipped & 255;
+        const int redist = (clipped - resid) >> 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hv[k] += redist + ((8 * lane + k) < resid ? 1 : 0);
+    }
+#pragma unroll
+    for (int k = 1; k < 8; ++k) hv[k] += hv[k - 1];
+    int incl = hv[7];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int excl = incl - hv[7];
+    uint32_t w0 = 0, w1 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float f = __fmul_rn((float)(hv[k] + excl), p.lut_scale);
+        f = floorf(fminf(fmaxf(f, 0.0f), 255.0f));
+        const uint32_t b = (uint32_t)(int)f;
+        if (k < 4) w0 |= b << (8 * k); else w1 |= b << (8 * (k - 4));
+    }
+    *reinterpret_cast<uint2*>(lut_out + 8 * lane) = make_uint2(w0, w1);
+}
+
+}  // namespace mie

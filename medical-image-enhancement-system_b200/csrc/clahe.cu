@@ -112,9 +112,9 @@ clahe_apply_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t
 // ---------------------------------------------------------------- host side
 static int clahe_common_checks(const void* src, int sd, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int gh,
                                int gw, int semantics, float lo, float hi, ClaheGeom* g) {
-    if (!src) return MIE_E_NULL;
-    if (!valid_dtype(sd)) return MIE_E_DTYPE;
     if (n < 0 || h <= 0 || w <= 0) return MIE_E_SHAPE;
+    if (n > 0 && !src) return MIE_E_NULL;
+    if (!valid_dtype(sd)) return MIE_E_DTYPE;
     if (ssh < w || (n > 1 && ssn < (int64_t)(h - 1) * ssh + w)) return MIE_E_STRIDE;
     if (semantics != MIE_CLAHE_KORNIA && semantics != MIE_CLAHE_OPENCV) return MIE_E_UNSUPPORTED;
     if (semantics == MIE_CLAHE_OPENCV && sd != MIE_U8) return MIE_E_UNSUPPORTED;  // 65536-bin mode: not built yet

@@ -48,20 +48,3 @@ int mie_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 }  // extern "C"
-
-// ---- temporary: entry points whose kernels land in later commits -------------------------------
-#ifndef MIE_HAVE_EQUALIZE
-extern "C" size_t mie_equalize_workspace_bytes(int64_t) { return 0; }
-extern "C" int mie_equalize(const void*, void*, int, int, int64_t, int, int, int64_t, int64_t, int64_t, int64_t, float,
-                            float, void*, size_t, void*) { return MIE_E_UNSUPPORTED; }
-#endif
-#ifndef MIE_HAVE_MEDIAN
-extern "C" int mie_median2d(const void*, void*, int, int64_t, int, int, int64_t, int64_t, int64_t, int64_t, int, int, int,
-                            void*) { return MIE_E_UNSUPPORTED; }
-extern "C" int mie_median3d(const void*, void*, int, int, int, int, int64_t, int64_t, int64_t, int64_t, const void*,
-                            const void*, int, void*) { return MIE_E_UNSUPPORTED; }
-#endif
-#ifndef MIE_HAVE_BILATERAL
-extern "C" int mie_bilateral(const void*, void*, int, int, int64_t, int, int, int64_t, int64_t, int64_t, int64_t,
-                             const float*, int, int, float, int, float, float, void*) { return MIE_E_UNSUPPORTED; }
-#endif

@@ -126,8 +126,8 @@ struct PlaneArgs {
 
 inline int check_planes(const void* src, const void* dst, int64_t n, int h, int w,
                         int64_t ssn, int64_t ssh, int64_t dsn, int64_t dsh, bool need_dst = true) {
-    if (!src || (need_dst && !dst)) return MIE_E_NULL;
     if (n < 0 || h <= 0 || w <= 0) return MIE_E_SHAPE;
+    if (n > 0 && (!src || (need_dst && !dst))) return MIE_E_NULL;  // empty batches carry null pointers
     if (ssh < w || (n > 1 && ssn < (int64_t)(h - 1) * ssh + w)) return MIE_E_STRIDE;
     if (need_dst && (dsh < w || (n > 1 && dsn < (int64_t)(h - 1) * dsh + w))) return MIE_E_STRIDE;
     return MIE_OK;

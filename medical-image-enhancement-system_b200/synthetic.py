@@ -22,7 +22,8 @@ def uniform(shape, dtype=np.uint16, seed: int = 0) -> np.ndarray:
 
 
 def constant(shape, dtype=np.uint16, value: int = 1000) -> np.ndarray:
-    return np.full(shape, value, dtype=dtype)
+    info = np.iinfo(dtype)
+    return np.full(shape, min(max(value, info.min), info.max), dtype=dtype)
 
 
 def _phantom_slice(rng, h, w, z=0.0):

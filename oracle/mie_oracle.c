@@ -382,3 +382,176 @@ int orc_clahe_apply_opencv_u8(const uint8_t* in, uint8_t* out, int64_t n, int h,
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------ median (pure selection)
+ * 2-D: kornia.filters.median_blur (zero padding; torch.median = lower median, the
+ * true median for odd windows) / skimage.filters.median 2-D ('nearest');
+ * SURVEY.md §8(a) A5.  3-D: skimage.filters.median -> scipy.ndimage.median_filter
+ * 3x3x3, rank 27//2 (site-packages/scipy/ndimage/_filters.py:1928-2028); A6.
+ * Samples are carried as double so one routine serves every dtype exactly.       */
+static int cmp_double(const void* a, const void* b) {
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+
+int orc_median2d(const double* in, double* out, int64_t n, int h, int w, int ky, int kx, int border) {
+    const int ry = ky / 2, rx = kx / 2, cnt = ky * kx;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < n; ++i) {
+        const double* img = in + (size_t)i * h * w;
+        double* o = out + (size_t)i * h * w;
+        double win[33 * 33];
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                int k = 0;
+                for (int dy = -ry; dy <= ry; ++dy) {
+                    int sy = border_index(y + dy, h, border);
+                    for (int dx = -rx; dx <= rx; ++dx) {
+                        int sx = border_index(x + dx, w, border);
+                        win[k++] = (sy < 0 || sx < 0) ? 0.0 : img[(size_t)sy * w + sx];
+                    }
+                }
+                qsort(win, cnt, sizeof(double), cmp_double);
+                o[(size_t)y * w + x] = win[cnt / 2];
+            }
+    }
+    return 0;
+}
+
+/* halo_lo / halo_hi: optional h*w planes standing in for z = -1 and z = d. */
+int orc_median3d(const double* in, double* out, int d, int h, int w, const double* halo_lo, const double* halo_hi,
+                 int border) {
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int z = 0; z < d; ++z) {
+        double win[27];
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                int k = 0;
+                for (int dz = -1; dz <= 1; ++dz) {
+                    int zz = z + dz;
+                    const double* plane;
+                    if (zz < 0) plane = halo_lo ? halo_lo : (border == B_REPLICATE ? in : NULL);
+                    else if (zz >= d) plane = halo_hi ? halo_hi : (border == B_REPLICATE ? in + (size_t)(d - 1) * h * w : NULL);
+                    else plane = in + (size_t)zz * h * w;
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        int sy = border_index(y + dy, h, border);
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            int sx = border_index(x + dx, w, border);
+                            win[k++] = (!plane || sy < 0 || sx < 0) ? 0.0 : plane[(size_t)sy * w + sx];
+                        }
+                    }
+                }
+                qsort(win, 27, sizeof(double), cmp_double);
+                out[((size_t)z * h + y) * w + x] = win[13];
+            }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ bilateral
+ * kornia.filters.bilateral_blur, single channel:
+ * w = space[dy,dx] * exp(-0.5/sigma_color^2 * (v - c)^2); out = sum(w v)/sum(w).
+ * exp is evaluated by mie_exp (below) — a fixed sequence of fp32 fma operations
+ * with < 2 ulp error, so that the CUDA kernel can reproduce it bit for bit.      */
+static inline float mie_exp(float a) {
+    a = fminf(fmaxf(a, -87.0f), 88.0f);
+    float n = rintf(a * 1.44269504088896341f);
+    float r = fmaf(n, -0.693145751953125f, a);      /* ln2 high part (exact in fp32) */
+    r = fmaf(n, -1.42860682030941723e-6f, r);       /* ln2 low part */
+    float p = 1.3888889225e-3f;                     /* 1/720 */
+    p = fmaf(p, r, 8.3333337680e-3f);               /* 1/120 */
+    p = fmaf(p, r, 4.1666667908e-2f);               /* 1/24 */
+    p = fmaf(p, r, 1.6666667163e-1f);               /* 1/6 */
+    p = fmaf(p, r, 0.5f);
+    p = fmaf(p, r, 1.0f);
+    p = fmaf(p, r, 1.0f);
+    union { int32_t i; float f; } s;
+    s.i = ((int32_t)n + 127) << 23;
+    return p * s.f;
+}
+
+void orc_exp(const float* in, float* out, int64_t count) {
+    for (int64_t i = 0; i < count; ++i) out[i] = mie_exp(in[i]);
+}
+
+MIE_CLONES
+int orc_bilateral(const float* in, float* out, int64_t n, int h, int w, const float* wspace, int ky, int kx,
+                  float sigma_color, int border) {
+    const int ry = ky / 2, rx = kx / 2;
+    const float coef = (float)(-0.5 / ((double)sigma_color * (double)sigma_color));
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < n; ++i) {
+        const float* img = in + (size_t)i * h * w;
+        float* o = out + (size_t)i * h * w;
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x) {
+                const float c = img[(size_t)y * w + x];
+                float num = 0.0f, den = 0.0f;
+                for (int dy = 0; dy < ky; ++dy) {
+                    int sy = border_index(y - ry + dy, h, border);
+                    for (int dx = 0; dx < kx; ++dx) {
+                        int sx = border_index(x - rx + dx, w, border);
+                        float v = (sy < 0 || sx < 0) ? 0.0f : img[(size_t)sy * w + sx];
+                        float dv = v - c;
+                        float wgt = wspace[dy * kx + dx] * mie_exp(coef * (dv * dv));
+                        num = fmaf(wgt, v, num);
+                        den = den + wgt;
+                    }
+                }
+                o[(size_t)y * w + x] = num / den;
+            }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------ global equalisation
+ * kornia.enhance.equalize -> _scale_channel, the
+ * torchvision rule (site-packages/torchvision/transforms/_functional_tensor.py:863-881):
+ * v = x*255; hist = histc(v, 256, 0, 255); step = (sum(nz) - nz[-1]) // 255;
+ * lut = [0, ((cumsum + step//2) // step)[:-1]] clamped; out = lut[trunc(v)] / 255,
+ * or v / 255 unchanged when step == 0.                                            */
+int orc_equalize(const float* in, float* out, int64_t n, int h, int w) {
+    const size_t px = (size_t)h * w;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < n; ++i) {
+        const float* img = in + i * px;
+        float* o = out + i * px;
+        int64_t hist[256];
+        memset(hist, 0, sizeof(hist));
+        for (size_t p = 0; p < px; ++p) {
+            float v = img[p] * 255.0f;
+            if (!(v >= 0.0f && v <= 255.0f)) continue; /* histc ignores out-of-range and NaN */
+            int b = (int)((v / 255.0f) * 256.0f);
+            if (b > 255) b = 255;
+            hist[b] += 1;
+        }
+        int64_t total = 0, last = 0;
+        for (int b = 0; b < 256; ++b) {
+            total += hist[b];
+            if (hist[b]) last = hist[b];
+        }
+        int64_t step = (total - last) / 255;
+        float lut[256];
+        if (step > 0) {
+            int64_t cum = 0;
+            lut[0] = 0.0f;
+            for (int b = 0; b < 255; ++b) {
+                cum += hist[b];
+                int64_t q = (cum + step / 2) / step;
+                lut[b + 1] = (float)(q > 255 ? 255 : q);
+            }
+        }
+        for (size_t p = 0; p < px; ++p) {
+            float v = img[p] * 255.0f;
+            float r;
+            if (step > 0) {
+                float c = fminf(fmaxf(v, 0.0f), 255.0f);
+                r = lut[(int)c];
+            } else {
+                r = v;
+            }
+            o[p] = r / 255.0f;
+        }
+    }
+    return 0;
+}

@@ -54,6 +54,11 @@ class _Sig:
     orc_clahe_hist_opencv_u8 = ([_p, _i64, _i, _i, _i, _i, _p], _i)
     orc_clahe_luts_from_hist_opencv = ([_p, _i64, _i, _i, _d, _p], _i)
     orc_clahe_apply_opencv_u8 = ([_p, _p, _i64, _i, _i, _i, _i, _p], _i)
+    orc_median2d = ([_p, _p, _i64, _i, _i, _i, _i, _i], _i)
+    orc_median3d = ([_p, _p, _i, _i, _i, _p, _p, _i], _i)
+    orc_exp = ([_p, _p, _i64], None)
+    orc_bilateral = ([_p, _p, _i64, _i, _i, _p, _i, _i, _f, _i], _i)
+    orc_equalize = ([_p, _p, _i64, _i, _i], _i)
 
 
 def _ptr(a: np.ndarray):
@@ -215,6 +220,55 @@ def opencv_clahe(img, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
     luts = opencv_clahe_luts(x, clip_limit, grid_size)
     out = np.empty_like(x)
     _check(lib().orc_clahe_apply_opencv_u8(_ptr(x), _ptr(out), n, h, w, gh, gw, _ptr(luts)))
+    return out
+
+
+# ------------------------------------------------------------------ median / bilateral / equalize
+def median_blur(a, kernel_size, border_type="constant") -> np.ndarray:
+    """kornia.filters.median_blur (zero padding) on (..., H, W); any dtype, same dtype out."""
+    a = np.ascontiguousarray(a)
+    x, n, h, w = _planes(a, np.float64)
+    ky, kx = _pair(kernel_size)
+    out = np.empty_like(x)
+    _check(lib().orc_median2d(_ptr(x), _ptr(out), n, h, w, ky, kx, BORDERS[border_type]))
+    return out.astype(a.dtype)
+
+
+def median3d(vol, mode="nearest", halo_lo=None, halo_hi=None) -> np.ndarray:
+    """skimage.filters.median / scipy.ndimage.median_filter 3x3x3 on a (D, H, W) volume."""
+    vol = np.ascontiguousarray(vol)
+    d, h, w = vol.shape
+    x = vol.astype(np.float64)
+    lo = None if halo_lo is None else np.ascontiguousarray(halo_lo, np.float64)
+    hi = None if halo_hi is None else np.ascontiguousarray(halo_hi, np.float64)
+    out = np.empty_like(x)
+    border = {"nearest": 2, "constant": 0}[mode]
+    _check(lib().orc_median3d(_ptr(x), _ptr(out), d, h, w, None if lo is None else _ptr(lo),
+                              None if hi is None else _ptr(hi), border))
+    return out.astype(vol.dtype)
+
+
+def mie_exp(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.float32)
+    out = np.empty_like(a)
+    lib().orc_exp(_ptr(a), _ptr(out), a.size)
+    return out
+
+
+def bilateral_blur(x01, kernel_size, sigma_color, sigma_space, border_type="reflect") -> np.ndarray:
+    x, n, h, w = _planes(x01, np.float32)
+    ky, kx = _pair(kernel_size)
+    sy, sx = _pair(sigma_space)
+    wsp = np.ascontiguousarray((gaussian_kernel1d(ky, sy)[:, None] * gaussian_kernel1d(kx, sx)[None, :]).astype(np.float32))
+    out = np.empty_like(x)
+    _check(lib().orc_bilateral(_ptr(x), _ptr(out), n, h, w, _ptr(wsp), ky, kx, float(sigma_color), BORDERS[border_type]))
+    return out
+
+
+def equalize(x01) -> np.ndarray:
+    x, n, h, w = _planes(x01, np.float32)
+    out = np.empty_like(x)
+    _check(lib().orc_equalize(_ptr(x), _ptr(out), n, h, w))
     return out
 
 

@@ -1,0 +1,187 @@
+"""GPU parity tests for median (2-D / 3-D), bilateral and global equalisation, and the committed
+golden vectors.  Integer / selection work is bit-exact; bilateral follows the oracle's fp32
+operation order (including its fixed-sequence exp) and is asserted bit-exact as well, with the
+north star's rel 1e-5 checked against the torch-CPU kornia twin (true exp)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def gpu(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def cpu(t):
+    return t.cpu().numpy()
+
+
+def rand(dtype, shape, seed):
+    rng = np.random.default_rng(seed)
+    if dtype == np.float32:
+        return rng.random(shape, dtype=np.float32)
+    info = np.iinfo(dtype)
+    return rng.integers(info.min, info.max + 1, shape).astype(dtype)
+
+
+# ---------------------------------------------------------------------------- median 2-D
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.int16, np.float32])
+@pytest.mark.parametrize("k", [3, 5, 7, (3, 5), (5, 3), (1, 3), 1])
+def test_median_blur_bit_exact(dev, dtype, k):
+    import mie_b200 as M
+    import oracle as O
+
+    for shape in [(2, 1, 70, 50), (1, 2, 33, 129), (1, 1, 5, 4)]:
+        x = rand(dtype, shape, 3)
+        if dtype != np.float32:
+            x[..., : shape[-2] // 2, :] //= 16  # many ties
+        for border in ("constant", "replicate"):
+            got = cpu(M.median_blur(gpu(x, dev), k, border_type=border))
+            assert np.array_equal(got, O.median_blur(x, k, border)), (shape, k, border)
+
+
+def test_median_blur_matches_scipy_and_cv2(dev):
+    cv2 = pytest.importorskip("cv2")
+    ndi = pytest.importorskip("scipy.ndimage")
+    import mie_b200 as M
+
+    x = rand(np.uint16, (300, 400), 4)
+    xt = gpu(x, dev)
+    assert np.array_equal(cpu(M.median_blur(xt, 3)), ndi.median_filter(x, size=3, mode="constant", cval=0))
+    assert np.array_equal(cpu(M.median_blur(xt, 5, border_type="replicate")), cv2.medianBlur(x, 5))
+    assert np.array_equal(cpu(M.median(xt)), ndi.median_filter(x, size=3, mode="nearest"))  # skimage default
+
+
+def test_median_unsupported_kernel(dev):
+    import mie_b200 as M
+
+    with pytest.raises(ValueError):
+        M.median_blur(gpu(np.zeros((8, 8), np.uint16), dev), 9)
+    with pytest.raises(ValueError):
+        M.median_blur(gpu(np.zeros((8, 8), np.uint16), dev), 4)
+
+
+# ---------------------------------------------------------------------------- median 3-D
+@pytest.mark.parametrize("dtype", [np.int16, np.uint16, np.uint8, np.float32])
+def test_median3d_bit_exact_against_oracle_and_scipy(dev, dtype):
+    ndi = pytest.importorskip("scipy.ndimage")
+    import mie_b200 as M
+    import oracle as O
+
+    for shape in [(12, 20, 24), (70, 33, 65), (1, 9, 9), (3, 8, 40)]:
+        vol = rand(dtype, shape, 6)
+        for mode in ("nearest", "constant"):
+            got = cpu(M.median(gpu(vol, dev), mode=mode))
+            assert np.array_equal(got, O.median3d(vol, mode)), (shape, mode)
+            if mode == "nearest":
+                assert np.array_equal(got, ndi.median_filter(vol, size=3, mode="nearest"))
+
+
+def test_median3d_slab_halos(dev):
+    """z-slabs with neighbour halo planes reproduce the unsharded volume bit for bit."""
+    import mie_b200 as M
+    from mie_b200 import synthetic
+
+    vol = synthetic.phantom_volume((40, 64, 96), np.int16, seed=1)
+    vt = gpu(vol, dev)
+    full = cpu(M.median(vt))
+    for nslab in (2, 4, 5):
+        bounds = np.linspace(0, 40, nslab + 1).astype(int)
+        parts = []
+        for i in range(nslab):
+            lo, hi = bounds[i], bounds[i + 1]
+            halo_lo = vt[lo - 1].contiguous() if lo > 0 else None
+            halo_hi = vt[hi].contiguous() if hi < 40 else None
+            parts.append(cpu(M.median(vt[lo:hi], halo_lo=halo_lo, halo_hi=halo_hi)))
+        assert np.array_equal(np.concatenate(parts), full), nslab
+
+
+# ---------------------------------------------------------------------------- bilateral
+@pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8])
+def test_bilateral_bit_exact_and_within_tolerance_of_true_exp(dev, dtype):
+    import kornia_twin as K
+    import mie_b200 as M
+    import oracle as O
+
+    for shape, k, sc, ss, border in [((2, 1, 70, 50), 9, 0.1, 1.5, "reflect"), ((1, 1, 33, 65), (5, 7), 0.2, (1.5, 1.2), "replicate"),
+                                     ((1, 1, 40, 40), 3, 0.05, 0.8, "constant"), ((1, 1, 64, 64), 15, 0.3, 3.0, "reflect")]:
+        x = rand(dtype, shape, 8)
+        x01 = O.to01(x)
+        ref = O.bilateral_blur(x01, k, sc, ss, border)
+        got = cpu(M.bilateral_blur(gpu(x, dev), k, sc, ss, border, out_dtype=torch.float32))
+        assert np.array_equal(got, ref), float(np.abs(got - ref).max())
+        twin = K.bilateral_blur(torch.from_numpy(x01), k, sc, ss, border).numpy()
+        assert (np.abs(got - twin) / np.maximum(np.abs(twin), 1e-6)).max() <= 1e-5
+        if dtype != np.float32:
+            q = cpu(M.bilateral_blur(gpu(x, dev), k, sc, ss, border))
+            assert np.array_equal(q, O.from01(ref, dtype))
+
+
+# ---------------------------------------------------------------------------- global equalisation
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.int16, np.float32])
+def test_equalize_bit_exact(dev, dtype):
+    import mie_b200 as M
+    import oracle as O
+
+    for shape in [(3, 1, 64, 80), (1, 2, 300, 500), (1, 1, 7, 5)]:
+        x = rand(dtype, shape, 10)
+        ref = O.equalize(O.to01(x))
+        got = cpu(M.equalize(gpu(x, dev), out_dtype=torch.float32))
+        assert np.array_equal(got, ref)
+        if dtype != np.float32:
+            assert np.array_equal(cpu(M.equalize(gpu(x, dev))), O.from01(ref, dtype))
+    # constant image: step == 0 -> returned unchanged
+    c = np.full((1, 1, 32, 32), 77, np.uint8)
+    assert np.array_equal(cpu(M.equalize(gpu(c, dev))), c)
+
+
+def test_equalize_matches_torchvision_uint8(dev):
+    tvf = pytest.importorskip("torchvision.transforms.v2.functional")
+    import mie_b200 as M
+
+    x = rand(np.uint8, (2, 3, 120, 90), 11)
+    ref = tvf.equalize(torch.from_numpy(x)).numpy()
+    assert np.array_equal(cpu(M.equalize(gpu(x, dev))), ref)
+
+
+# ---------------------------------------------------------------------------- golden vectors
+def test_golden_hashes_on_gpu(dev):
+    import make_golden as G
+    import mie_b200 as M
+
+    with open(os.path.join(GOLDEN, "golden.json")) as f:
+        want = json.load(f)
+    x = G.inputs()
+    p, f32, u8, u16 = gpu(x["phantom_u16"], dev), gpu(x["noise_f32"], dev), gpu(x["noise_u8"], dev), gpu(x["uniform_u16"], dev)
+    got = {
+        "chain_c2_phantom_u16": G.sha(cpu(M.enhance_chain(p))),
+        "chain_c2_uniform_u16": G.sha(cpu(M.enhance_chain(u16))),
+        "clahe_luts_phantom_u16_8x8_clip2": G.sha(cpu(M.clahe_luts(p, 2.0, (8, 8)))),
+        "clahe_phantom_u16_8x8_clip2": G.sha(cpu(M.equalize_clahe(p, 2.0, (8, 8)))),
+        "clahe_f32_4x6_clip2": G.sha(cpu(M.equalize_clahe(f32, 2.0, (4, 6)))),
+        "gauss_f32_k9_s1_reflect": G.sha(cpu(M.gaussian_blur2d(f32, 9, 1.0))),
+        "gauss_f32_k5_s1.2_replicate": G.sha(cpu(M.gaussian_blur2d(f32, 5, 1.2, "replicate"))),
+        "unsharp_f32_k9_s1_reflect": G.sha(cpu(M.unsharp_mask(f32, 9, 1.0))),
+        "opencv_clahe_u8_8x8_clip2": G.sha(cpu(M.equalize_clahe(u8, 2.0, (8, 8), semantics="opencv"))),
+        "median3x3_u16_zero": G.sha(cpu(M.median_blur(u16, 3))),
+        "median5x5_u16_zero": G.sha(cpu(M.median_blur(u16, 5))),
+        "median3d_i16_nearest": G.sha(cpu(M.median(gpu(x["phantom_i16_vol"], dev)))),
+        "bilateral_f32_k9_sc0.1_ss1.5": G.sha(cpu(M.bilateral_blur(f32, 9, 0.1, 1.5))),
+        "equalize_u8": G.sha(cpu(M.equalize(u8))),
+        "equalize_f32": G.sha(cpu(M.equalize(f32))),
+    }
+    assert got == want
+
+
+def test_committed_fixture(dev):
+    import mie_b200 as M
+
+    fx = np.load(os.path.join(GOLDEN, "chain_128_grid2.npz"))
+    cfg = M.ChainConfig(grid_size=(2, 2))
+    assert np.array_equal(cpu(M.enhance_chain(gpu(fx["input"], dev), cfg)), fx["output"])
