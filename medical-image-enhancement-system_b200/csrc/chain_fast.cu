@@ -5,29 +5,56 @@
 
 namespace mie {
 
+// 24 converted pixels x[0..23] = image columns c0-4 .. c0+19 of one row (16 outputs + halo 4);
+// columns outside the image (left edge: c0 == 0, right edge: c0 + 16 == w) are filled from the
+// registers already loaded, so edge tiles cost no extra loads.
+template <typename SrcT>
+__device__ __forceinline__ void load_row24(const SrcT* row, int c0, int w, int border, float* x) {
+    Fast<SrcT>::load8(row + c0, x + 4);
+    Fast<SrcT>::load8(row + c0 + 8, x + 12);
+    if (c0 != 0) {
+        Fast<SrcT>::load4(row + c0 - 4, x);
+    } else if (border == MIE_BORDER_REFLECT) {
+        x[0] = x[8]; x[1] = x[7]; x[2] = x[6]; x[3] = x[5];
+    } else {
+        const float e = border == MIE_BORDER_REPLICATE ? x[4] : 0.0f;
+        x[0] = e; x[1] = e; x[2] = e; x[3] = e;
+    }
+    if (c0 + 16 != w) {
+        Fast<SrcT>::load4(row + c0 + 16, x + 20);
+    } else if (border == MIE_BORDER_REFLECT) {
+        x[20] = x[18]; x[21] = x[17]; x[22] = x[16]; x[23] = x[15];
+    } else {
+        const float e = border == MIE_BORDER_REPLICATE ? x[19] : 0.0f;
+        x[20] = e; x[21] = e; x[22] = e; x[23] = e;
+    }
+}
+
+// s_mid row layout of the tuned chain_a kernel: the 16 column quads of a row are stored even quads
+// first (quad q at word 4*(q/2)), odd quads from word 48 (4*(12 + q/2)), rows 84 words apart.  With
+// it, the row pass (4 lanes of a row x 2 rows per quarter-warp, STS.128 each) and the column pass
+// (8 lanes of a row per quarter-warp, LDS.128 each) both touch 32 distinct banks.
+constexpr int kPMa = 84;
+__device__ __forceinline__ int quad_off(int q) { return 4 * ((q >> 1) + ((q & 1) ? 12 : 0)); }
+
 // ================================================================ chain_a (fast)
 // One block (9 warps) per CLAHE tile:
-//   row pass   : 72 rows x 8 segments; a thread loads 16 pixels of one row with
-//                64/128-bit loads, converts them, forms 8 horizontal sums and stores
-//                them to s_mid (conflict-free STS.128 order);
+//   row pass   : 72 rows x 4 segments = one item per thread; a thread loads 24 pixels of one row
+//                with 64/128-bit loads, converts them, forms 16 horizontal sums -> s_mid;
 //   col pass   : warps 0-7, 4 columns x 4 rows per thread out of s_mid;
 //   epilogue   : lookup index -> 32-bit stores into the index plane; histogram bin ->
-//                warp-voted adds into the warp's private histogram;
-//   LUT        : 256 threads fold the 8 private histograms, warp 8 clips / scans.
+//                ATOMS.POPC.INC into the block histogram;
+//   LUT        : warp 8 clips / redistributes / scans (8 bins per lane).
 template <typename SrcT, int R>
 __global__ void __launch_bounds__(kFastThreads)
 chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
     constexpr int ROWS = kTile + 2 * R;
-    // s_mid row layout: segment s (8 floats) is split — floats 0..3 at word 4s, floats 4..7 at word
-    // 48+4s — so that both the row pass (8 lanes of a row storing 16 B each) and the column pass
-    // (16 lanes of a row loading 16 B each) touch 32 distinct banks per quarter-warp.
-    constexpr int PM = 80, HI = 48;
-    __shared__ __align__(16) float s_mid[ROWS * PM];
-    __shared__ __align__(16) int s_hist[8 * kBins];
-    __shared__ __align__(16) int s_tot[kBins];
+    constexpr bool NN = !(sizeof(SrcT) == 4);  // integer pixels: blurred values are >= 0 and finite
+    __shared__ __align__(16) float s_mid[ROWS * kPMa];
+    __shared__ __align__(16) int s_hist[kBins + 8];  // [256] = dummy slot for ignored pixels
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 8 * kBins; i += kFastThreads) s_hist[i] = 0;
+    if (tid < kBins + 8) s_hist[tid] = 0;
 
     const int64_t tile = blockIdx.x;
     const int tx = (int)(tile % a.g.gw), ty = (int)((tile / a.g.gw) % a.g.gh);
@@ -37,50 +64,42 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
     const SrcT* plane = (const SrcT*)a.src + n * a.ssn;
 
     // ---- horizontal pass, straight from global memory
-    for (int i = tid; i < ROWS * 8; i += kFastThreads) {
-        const int s = i & 7, r = i >> 3;
+    for (int i = tid; i < ROWS * 4; i += kFastThreads) {
+        const int s = i & 3, r = i >> 2;
         const int sy = border_index(ty0 - R + r, h, a.border);
-        float x[16];
+        float x[24];
         if (sy < 0) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) x[k] = 0.0f;
+            for (int k = 0; k < 24; ++k) x[k] = 0.0f;
         } else {
-            const SrcT* row = plane + (int64_t)sy * a.ssh;
-            const int c0 = tx0 + 8 * s;  // first output column of this segment
-            const bool ledge = (c0 == 0), redge = (c0 + 8 == w);
-            if (!ledge && !redge) {
-                Fast<SrcT>::load16(row + c0 - 4, x);
-            } else {
+            load_row24<SrcT>(plane + (int64_t)sy * a.ssh, tx0 + 16 * s, w, a.border, x);
+        }
+        float* mrow = s_mid + r * kPMa + 8 * s;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int sx = border_index(c0 - 4 + k, w, a.border);
-                    x[k] = sx < 0 ? 0.0f : Fast<SrcT>::one(row[sx]);
-                }
+        for (int k = 0; k < 4; ++k) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float acc = __fmul_rn(wx.w[0], x[4 * k + j + 4 - R]);
+#pragma unroll
+                for (int t = 1; t <= 2 * R; ++t) acc = __fmaf_rn(wx.w[t], x[4 * k + j + 4 - R + t], acc);
+                o[j] = acc;
             }
+            // quad 4s+k: even quads at word 4*(2s + k/2), odd quads at 48 + 4*(2s + k/2)
+            *reinterpret_cast<float4*>(mrow + ((k & 1) ? 48 : 0) + 4 * (k >> 1)) = make_float4(o[0], o[1], o[2], o[3]);
         }
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float acc = __fmul_rn(wx.w[0], x[j + 4 - R]);
-#pragma unroll
-            for (int t = 1; t <= 2 * R; ++t) acc = __fmaf_rn(wx.w[t], x[j + 4 - R + t], acc);
-            o[j] = acc;
-        }
-        *reinterpret_cast<float4*>(s_mid + r * PM + 4 * s) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(s_mid + r * PM + HI + 4 * s) = make_float4(o[4], o[5], o[6], o[7]);
     }
     __syncthreads();
 
     // ---- vertical pass + epilogue (warps 0..7)
     if (warp < 8) {
         const int q = tid & 15, rb = tid >> 4;
-        const int qoff = (q & 1) ? HI + 4 * (q >> 1) : 4 * (q >> 1);
+        const int qoff = quad_off(q);
         float4 win[4 + 2 * R];
 #pragma unroll
         for (int k = 0; k < 4 + 2 * R; ++k)
-            win[k] = *reinterpret_cast<const float4*>(s_mid + (rb * 4 + k) * PM + qoff);
-        uint8_t* iplane = a.idx + n * (int64_t)h * w;
-        int* my_hist = s_hist + warp * kBins;
+            win[k] = *reinterpret_cast<const float4*>(s_mid + (rb * 4 + k) * kPMa + qoff);
+        uint8_t* ip = a.idx + n * (int64_t)h * w + (int64_t)(ty0 + rb * 4) * w + tx0 + q * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float g[4];
@@ -91,22 +110,15 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
                 g[0] = __fmaf_rn(wy.w[t], win[j + t].x, g[0]); g[1] = __fmaf_rn(wy.w[t], win[j + t].y, g[1]);
                 g[2] = __fmaf_rn(wy.w[t], win[j + t].z, g[2]); g[3] = __fmaf_rn(wy.w[t], win[j + t].w, g[3]);
             }
-            const uint32_t pack = fast_idx(g[0]) | (fast_idx(g[1]) << 8) | (fast_idx(g[2]) << 16) |
-                                  (fast_idx(g[3]) << 24);
-            *reinterpret_cast<uint32_t*>(iplane + (int64_t)(ty0 + rb * 4 + j) * w + tx0 + q * 4) = pack;
+            *reinterpret_cast<uint32_t*>(ip + (int64_t)j * w) =
+                pack_low_bytes(fast_idx_bits<NN>(g[0]), fast_idx_bits<NN>(g[1]), fast_idx_bits<NN>(g[2]),
+                               fast_idx_bits<NN>(g[3]));
 #pragma unroll
-            for (int k = 0; k < 4; ++k) hist_vote_add(my_hist, fast_bin(g[k]), lane);
+            for (int k = 0; k < 4; ++k) hist_add_nobranch(s_hist, fast_bin<NN>(g[k]));
         }
     }
     __syncthreads();
-    if (tid < kBins) {
-        int hv = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hv += s_hist[i * kBins + tid];
-        s_tot[tid] = hv;
-    }
-    __syncthreads();
-    if (warp == 8) warp_build_lut(s_tot, a.lp, a.luts + tile * kBins, lane);
+    if (warp == 8) warp_build_lut(s_hist, a.lp, a.luts + tile * kBins, lane);
 }
 
 // ================================================================ chain_b (fast)
@@ -116,6 +128,19 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
 //            cell (a,b) packed in one word; per-row / per-column weight tables;
 //   C pass : CLAHE output C for every haloed pixel -> s_in;
 //   row / col pass, epilogue: C + (C - blur(C)) -> quantise -> 64-bit stores.
+
+// CLAHE output of one pixel: e = packed (tl,tr,bl,br); bytes become floats by OR-ing them into the
+// mantissa of 2^23 (differences of two such floats are exact).
+__device__ __forceinline__ float clahe_px(uint32_t e, float wxv, float wyv) {
+    const float A = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7650));  // 2^23 + tl
+    const float B = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7651));  // 2^23 + tr
+    const float C = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7652));  // 2^23 + bl
+    const float D = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7653));  // 2^23 + br
+    const float t = __fmaf_rn(wxv, __fsub_rn(A, B), __fsub_rn(B, 8388608.0f));
+    const float b = __fmaf_rn(wxv, __fsub_rn(C, D), __fsub_rn(D, 8388608.0f));
+    return div255(__fmaf_rn(wyv, __fsub_rn(t, b), b));
+}
+
 template <typename DstT, int R>
 __global__ void __launch_bounds__(kFastThreads)
 chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
@@ -123,7 +148,7 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
     constexpr int PIN = TileSmem<R>::pin;
     __shared__ __align__(16) float s_in[E * PIN];
     __shared__ __align__(16) float s_mid[E * kPMid];
-    __shared__ uint32_t s_cell[4 * kBins];
+    __shared__ __align__(16) uint32_t s_cell[4 * kBins];
     __shared__ __align__(16) float s_wx[E + 8];
     __shared__ float s_wy[E];
     __shared__ int s_sy[E], s_sx[E + 8];
@@ -138,15 +163,11 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
     // ---- tables
     if (tid < kBins) {
         const uint8_t* nl = a.luts + n * (int64_t)gh * gw * kBins + tid;
-        // cell 0 = rows / columns before the tile centre, cell 1 = after it
-        const int j00 = ty == 0 ? 0 : ty - 1, j01 = ty;                      // a = 0: (top, bottom) LUT rows
-        const int j10 = ty, j11 = ty == gh - 1 ? gh - 1 : ty + 1;            // a = 1
-        const int i00 = tx == 0 ? 0 : tx - 1, i01 = tx;
-        const int i10 = tx, i11 = tx == gw - 1 ? gw - 1 : tx + 1;
-        const int jt[2] = {ty == 0 ? 0 : j00, ty == gh - 1 ? gh - 1 : j10};
-        const int jb[2] = {ty == 0 ? 0 : j01, j11};
-        const int il[2] = {tx == 0 ? 0 : i00, tx == gw - 1 ? gw - 1 : i10};
-        const int ir[2] = {tx == 0 ? 0 : i01, i11};
+        // cell 0 = source rows (columns) before the tile centre, cell 1 = after it
+        const int jt[2] = {ty == 0 ? 0 : ty - 1, ty};
+        const int jb[2] = {ty, ty == gh - 1 ? gh - 1 : ty + 1};
+        const int il[2] = {tx == 0 ? 0 : tx - 1, tx};
+        const int ir[2] = {tx, tx == gw - 1 ? gw - 1 : tx + 1};
 #pragma unroll
         for (int ca = 0; ca < 2; ++ca)
 #pragma unroll
@@ -157,7 +178,7 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
                 const uint32_t br = __ldg(nl + ((int64_t)jb[ca] * gw + ir[cb]) * kBins);
                 s_cell[(ca * 2 + cb) * kBins + tid] = tl | (tr << 8) | (bl << 16) | (br << 24);
             }
-    } else if (tid - kBins < 32) {
+    } else {
         // warp 8: per-row and per-column source coordinate + interpolation weight
         for (int k = tid - kBins; k < 2 * E; k += 32) {
             const bool is_row = k < E;
@@ -172,63 +193,72 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
     }
     __syncthreads();
 
-    // ---- CLAHE output of the haloed tile: item = (row r, 8-column chunk u), chunk u covers
-    //      tile columns 8u-R' .. 8u-R'+7 with the chunk grid anchored at column -4
+    // ---- CLAHE output of the haloed tile: item = (row r, 8-column chunk u)
     const uint8_t* iplane = a.idx + n * (int64_t)h * w;
-    constexpr int CH = (E + 7) / 8;  // chunks per row (9 for R=4 .. R=1: 66 -> 9)
+    constexpr int CH = (E + 7) / 8;
     for (int i = tid; i < E * CH; i += kFastThreads) {
         const int u = i % CH, r = i / CH;
         const int sy = s_sy[r];
-        const int c_first = 8 * u;              // first haloed column of the chunk (0-based in the E-wide row)
+        const int c_first = 8 * u;  // first haloed column of the chunk
         float cval[8];
-        if (sy < 0) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) cval[k] = 0.0f;
-        } else {
+        for (int k = 0; k < 8; ++k) cval[k] = 0.0f;
+        if (sy >= 0) {
             const float wyv = s_wy[r];
-            const int ca = (sy >= ty0 + kTile / 2) ? 2 : 0;
+            const int ca = (sy >= ty0 + kTile / 2) ? 2 * kBins : 0;
             const uint8_t* irow = iplane + (int64_t)sy * w;
-            const int gx0 = tx0 - R + c_first;  // image column of the chunk's first pixel
-            uint32_t id[8];
-            const bool interior = (gx0 >= 0) && (gx0 + 8 <= w) && ((gx0 & 3) == 0);
-            if (interior) {
-                const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
-                const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 + 4));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { id[k] = (w0 >> (8 * k)) & 0xFFu; id[4 + k] = (w1 >> (8 * k)) & 0xFFu; }
+            if (R == 4) {
+                // chunk = image columns gx0 .. gx0+7, gx0 = tx0 - 4 + 8u (4-byte aligned)
+                const int gx0 = tx0 - 4 + c_first;
+                uint32_t w0, w1;
+                bool z0 = false, z1 = false;
+                if (gx0 < 0) {  // columns -4..-1 mirror onto 4,3,2,1
+                    w1 = __ldg(reinterpret_cast<const uint32_t*>(irow));
+                    if (a.border == MIE_BORDER_REFLECT)
+                        w0 = __byte_perm(w1, __ldg(reinterpret_cast<const uint32_t*>(irow + 4)), 0x1234);
+                    else if (a.border == MIE_BORDER_REPLICATE) w0 = __byte_perm(w1, 0u, 0x0000);
+                    else { w0 = 0u; z0 = true; }
+                } else if (gx0 + 8 > w) {  // columns w..w+3 mirror onto w-2..w-5
+                    w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
+                    if (a.border == MIE_BORDER_REFLECT)
+                        w1 = __byte_perm(w0, __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 - 4)), 0x7012);
+                    else if (a.border == MIE_BORDER_REPLICATE) w1 = __byte_perm(w0, 0u, 0x3333);
+                    else { w1 = 0u; z1 = true; }
+                } else {
+                    w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
+                    w1 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 + 4));
+                }
+                // the cell column flips between haloed columns 35 and 36 (source column tx0+32)
+                const uint32_t* cellL = s_cell + ca + (c_first >= 36 ? kBins : 0);
+                const uint32_t* cellH = s_cell + ca + (c_first + 4 >= 36 ? kBins : 0);
+                const float4 wa = *reinterpret_cast<const float4*>(s_wx + c_first);
+                const float4 wb = *reinterpret_cast<const float4*>(s_wx + c_first + 4);
+                cval[0] = clahe_px(cellL[w0 & 0xFFu], wa.x, wyv);
+                cval[1] = clahe_px(cellL[(w0 >> 8) & 0xFFu], wa.y, wyv);
+                cval[2] = clahe_px(cellL[(w0 >> 16) & 0xFFu], wa.z, wyv);
+                cval[3] = clahe_px(cellL[w0 >> 24], wa.w, wyv);
+                cval[4] = clahe_px(cellH[w1 & 0xFFu], wb.x, wyv);
+                cval[5] = clahe_px(cellH[(w1 >> 8) & 0xFFu], wb.y, wyv);
+                cval[6] = clahe_px(cellH[(w1 >> 16) & 0xFFu], wb.z, wyv);
+                cval[7] = clahe_px(cellH[w1 >> 24], wb.w, wyv);
+                if (z0) { cval[0] = 0.f; cval[1] = 0.f; cval[2] = 0.f; cval[3] = 0.f; }
+                if (z1) { cval[4] = 0.f; cval[5] = 0.f; cval[6] = 0.f; cval[7] = 0.f; }
             } else {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int sx = (c_first + k < E) ? s_sx[c_first + k] : -1;
-                    id[k] = sx < 0 ? 0x100u : (uint32_t)irow[sx];
+                    const int c = c_first + k;
+                    const int sx = c < E ? s_sx[c] : -1;
+                    if (sx >= 0) {
+                        const int cb = (sx >= tx0 + kTile / 2) ? kBins : 0;
+                        cval[k] = clahe_px(s_cell[ca + cb + irow[sx]], s_wx[c], wyv);
+                    }
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int c = c_first + k;
-                float v = 0.0f;
-                if (id[k] < 0x100u && c < E) {
-                    const int sx = interior ? gx0 + k : s_sx[c];
-                    const int cb = (sx >= tx0 + kTile / 2) ? 1 : 0;
-                    const uint32_t e = s_cell[(ca + cb) * kBins + id[k]];
-                    const float A = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7650));  // 2^23 + tl
-                    const float B = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7651));  // 2^23 + tr
-                    const float C2 = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7652)); // 2^23 + bl
-                    const float D = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7653));  // 2^23 + br
-                    const float wxv = s_wx[c];
-                    const float t = __fmaf_rn(wxv, __fsub_rn(A, B), __fsub_rn(B, 8388608.0f));
-                    const float b = __fmaf_rn(wxv, __fsub_rn(C2, D), __fsub_rn(D, 8388608.0f));
-                    v = div255(__fmaf_rn(wyv, __fsub_rn(t, b), b));
-                }
-                cval[k] = v;
             }
         }
         float* dstp = s_in + r * PIN + c_first;
         if (c_first + 8 <= PIN) {
-            float4* q = reinterpret_cast<float4*>(dstp);
-            const float4 lo4 = make_float4(cval[0], cval[1], cval[2], cval[3]);
-            const float4 hi4 = make_float4(cval[4], cval[5], cval[6], cval[7]);
-            if (u & 4) { q[1] = hi4; q[0] = lo4; } else { q[0] = lo4; q[1] = hi4; }
+            *reinterpret_cast<float4*>(dstp) = make_float4(cval[0], cval[1], cval[2], cval[3]);
+            *reinterpret_cast<float4*>(dstp + 4) = make_float4(cval[4], cval[5], cval[6], cval[7]);
         } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
@@ -271,7 +301,7 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
 #pragma unroll
         for (int k = 0; k < 4 + 2 * R; ++k)
             win[k] = *reinterpret_cast<const float4*>(s_mid + (rb * 4 + k) * kPMid + q * 4);
-        DstT* oplane = (DstT*)a.dst + n * a.dsn;
+        DstT* op = (DstT*)a.dst + n * a.dsn + (int64_t)(ty0 + rb * 4) * a.dsh + tx0 + q * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float g[4];
@@ -282,12 +312,19 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
                 g[0] = __fmaf_rn(wy.w[t], win[j + t].x, g[0]); g[1] = __fmaf_rn(wy.w[t], win[j + t].y, g[1]);
                 g[2] = __fmaf_rn(wy.w[t], win[j + t].z, g[2]); g[3] = __fmaf_rn(wy.w[t], win[j + t].w, g[3]);
             }
-            const int r = rb * 4 + j;
-            const float* ctr = s_in + (r + R) * PIN + q * 4 + R;
+            const float* cp = s_in + (rb * 4 + j + R) * PIN + q * 4 + R;
+            float c[4];
+            if (R == 4) {
+                const float4 cv = *reinterpret_cast<const float4*>(cp);
+                c[0] = cv.x; c[1] = cv.y; c[2] = cv.z; c[3] = cv.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) c[k] = cp[k];
+            }
             float y[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(ctr[k], __fsub_rn(ctr[k], g[k]));
-            Fast<DstT>::store4(oplane + (int64_t)(ty0 + r) * a.dsh + tx0 + q * 4, y);
+            for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(c[k], __fsub_rn(c[k], g[k]));
+            Fast<DstT>::store4(op + (int64_t)j * a.dsh, y);
         }
     }
 }

@@ -12,10 +12,9 @@
 //   * floor()/trunc()/rint() by adding 2^23 in the matching rounding mode instead
 //     of F2I conversions (which run on the 16-lane conversion pipe);
 //   * x/255 as q0 = x*r; q = fma(fma(-255, q0, x), r, q0) (correctly rounded);
-//   * histogram votes: a warp peels off one distinct bin per iteration
-//     (shfl + ballot + popc) and a single lane adds the population count, so
-//     smooth (blurred) images cost ~1 shared-memory atomic per warp per distinct
-//     bin instead of 32 colliding ones;
+//   * histogram: one ATOMS.POPC.INC per pixel into a single block histogram — the
+//     hardware aggregates same-address lanes (measured: constant 1.53 cycles per warp
+//     instruction for 1..32-way collisions), so no software warp aggregation;
 //   * the clip / redistribute / scan -> LUT tail runs in one warp (8 bins per lane);
 //   * chain_b packs the four neighbouring LUTs of each interpolation cell into one
 //     32-bit word per grey level, so a pixel needs ONE shared-memory lookup.
@@ -60,6 +59,11 @@ int launch_chain_a_fast(const ChainAArgs& a, int src_dtype, const Taps& wx, cons
 int launch_chain_b_fast(const ChainBArgs& b, int dst_dtype, const Taps& wx, const Taps& wy, int R, int64_t n,
                         cudaStream_t st);
 
+// low bytes of four words -> one word (3 PRMT)
+__device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
 // ---------------------------------------------------------------- exact default-range pixel mapping
 template <typename T>
 struct Fast;
@@ -72,26 +76,27 @@ struct Fast<uint16_t> {
         return __fmaf_rn(t, kC, t);
     }
     static __device__ __forceinline__ float one(uint16_t v) { return from_bits(0x43000000u | v); }
-    // 16 consecutive pixels; p is 8-byte aligned and p+4 is 16-byte aligned
-    static __device__ __forceinline__ void load16(const uint16_t* p, float* x) {
-        const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + 4));
-        const uint2 c = __ldg(reinterpret_cast<const uint2*>(p + 12));
-        const uint32_t w[8] = {a.x, a.y, b.x, b.y, b.z, b.w, c.x, c.y};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            x[2 * i] = from_bits(__byte_perm(w[i], 0x43000000u, 0x7610));
-            x[2 * i + 1] = from_bits(__byte_perm(w[i], 0x43000000u, 0x7632));
-        }
+    static __device__ __forceinline__ void cvt2(uint32_t w, float* x) {
+        x[0] = from_bits(__byte_perm(w, 0x43000000u, 0x7610));
+        x[1] = from_bits(__byte_perm(w, 0x43000000u, 0x7632));
     }
-    static __device__ __forceinline__ uint32_t quant(float y) {  // rint(clamp(y,0,1)*65535)
+    static __device__ __forceinline__ void load4(const uint16_t* p, float* x) {  // p 8-byte aligned
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+        cvt2(a.x, x); cvt2(a.y, x + 2);
+    }
+    static __device__ __forceinline__ void load8(const uint16_t* p, float* x) {  // p 16-byte aligned
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p));
+        cvt2(b.x, x); cvt2(b.y, x + 2); cvt2(b.z, x + 4); cvt2(b.w, x + 6);
+    }
+    // rint(clamp(y,0,1)*65535) sits in the low 16 mantissa bits of the returned float's bit pattern
+    static __device__ __forceinline__ uint32_t quant(float y) {
         const float c = fminf(fmaxf(y, 0.0f), 1.0f);
-        return __float_as_uint(__fadd_rn(__fmul_rn(c, 65535.0f), 8388608.0f)) & 0xFFFFu;
+        return __float_as_uint(__fadd_rn(__fmul_rn(c, 65535.0f), 8388608.0f));
     }
     static __device__ __forceinline__ void store4(uint16_t* p, const float* y) {
         uint2 o;
-        o.x = quant(y[0]) | (quant(y[1]) << 16);
-        o.y = quant(y[2]) | (quant(y[3]) << 16);
+        o.x = __byte_perm(quant(y[0]), quant(y[1]), 0x5410);
+        o.y = __byte_perm(quant(y[2]), quant(y[3]), 0x5410);
         *reinterpret_cast<uint2*>(p) = o;
     }
 };
@@ -101,22 +106,19 @@ struct Fast<int16_t> {
     static __device__ __forceinline__ float one(int16_t v) {
         return Fast<uint16_t>::from_bits(0x43000000u | ((uint32_t)(uint16_t)v ^ 0x8000u));
     }
-    static __device__ __forceinline__ void load16(const int16_t* p, float* x) {
+    static __device__ __forceinline__ void load4(const int16_t* p, float* x) {
         const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
-        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p + 4));
-        const uint2 c = __ldg(reinterpret_cast<const uint2*>(p + 12));
-        const uint32_t w[8] = {a.x, a.y, b.x, b.y, b.z, b.w, c.x, c.y};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t u = w[i] ^ 0x80008000u;  // v + 32768 for both halves
-            x[2 * i] = Fast<uint16_t>::from_bits(__byte_perm(u, 0x43000000u, 0x7610));
-            x[2 * i + 1] = Fast<uint16_t>::from_bits(__byte_perm(u, 0x43000000u, 0x7632));
-        }
+        Fast<uint16_t>::cvt2(a.x ^ 0x80008000u, x); Fast<uint16_t>::cvt2(a.y ^ 0x80008000u, x + 2);  // v + 32768
+    }
+    static __device__ __forceinline__ void load8(const int16_t* p, float* x) {
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p));
+        Fast<uint16_t>::cvt2(b.x ^ 0x80008000u, x); Fast<uint16_t>::cvt2(b.y ^ 0x80008000u, x + 2);
+        Fast<uint16_t>::cvt2(b.z ^ 0x80008000u, x + 4); Fast<uint16_t>::cvt2(b.w ^ 0x80008000u, x + 6);
     }
     static __device__ __forceinline__ void store4(int16_t* p, const float* y) {
         uint2 o;
-        o.x = (Fast<uint16_t>::quant(y[0]) | (Fast<uint16_t>::quant(y[1]) << 16)) ^ 0x80008000u;
-        o.y = (Fast<uint16_t>::quant(y[2]) | (Fast<uint16_t>::quant(y[3]) << 16)) ^ 0x80008000u;
+        o.x = __byte_perm(Fast<uint16_t>::quant(y[0]), Fast<uint16_t>::quant(y[1]), 0x5410) ^ 0x80008000u;
+        o.y = __byte_perm(Fast<uint16_t>::quant(y[2]), Fast<uint16_t>::quant(y[3]), 0x5410) ^ 0x80008000u;
         *reinterpret_cast<uint2*>(p) = o;
     }
 };
@@ -129,38 +131,37 @@ struct Fast<uint8_t> {
         return __fmaf_rn(t, kC, t);
     }
     static __device__ __forceinline__ float one(uint8_t v) { return from_bits(0x47000000u | v); }
-    static __device__ __forceinline__ void load16(const uint8_t* p, float* x) {  // p 4-byte aligned, p+4 8-byte aligned
-        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(p));
-        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p + 4));
-        const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(p + 12));
-        const uint32_t w[4] = {a, b.x, b.y, c};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            x[4 * i] = from_bits(__byte_perm(w[i], 0x47000000u, 0x7650));
-            x[4 * i + 1] = from_bits(__byte_perm(w[i], 0x47000000u, 0x7651));
-            x[4 * i + 2] = from_bits(__byte_perm(w[i], 0x47000000u, 0x7652));
-            x[4 * i + 3] = from_bits(__byte_perm(w[i], 0x47000000u, 0x7653));
-        }
+    static __device__ __forceinline__ void cvt4(uint32_t w, float* x) {
+        x[0] = from_bits(__byte_perm(w, 0x47000000u, 0x7650));
+        x[1] = from_bits(__byte_perm(w, 0x47000000u, 0x7651));
+        x[2] = from_bits(__byte_perm(w, 0x47000000u, 0x7652));
+        x[3] = from_bits(__byte_perm(w, 0x47000000u, 0x7653));
     }
-    static __device__ __forceinline__ uint32_t quant(float y) {
+    static __device__ __forceinline__ void load4(const uint8_t* p, float* x) {  // p 4-byte aligned
+        cvt4(__ldg(reinterpret_cast<const uint32_t*>(p)), x);
+    }
+    static __device__ __forceinline__ void load8(const uint8_t* p, float* x) {  // p 8-byte aligned
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
+        cvt4(b.x, x); cvt4(b.y, x + 4);
+    }
+    static __device__ __forceinline__ uint32_t quant(float y) {  // value in the low byte of the bit pattern
         const float c = fminf(fmaxf(y, 0.0f), 1.0f);
-        return __float_as_uint(__fadd_rn(__fmul_rn(c, 255.0f), 8388608.0f)) & 0xFFu;
+        return __float_as_uint(__fadd_rn(__fmul_rn(c, 255.0f), 8388608.0f));
     }
     static __device__ __forceinline__ void store4(uint8_t* p, const float* y) {
-        *reinterpret_cast<uint32_t*>(p) = quant(y[0]) | (quant(y[1]) << 8) | (quant(y[2]) << 16) | (quant(y[3]) << 24);
+        *reinterpret_cast<uint32_t*>(p) = pack_low_bytes(quant(y[0]), quant(y[1]), quant(y[2]), quant(y[3]));
     }
 };
 
 template <>
 struct Fast<float> {
     static __device__ __forceinline__ float one(float v) { return v; }
-    static __device__ __forceinline__ void load16(const float* p, float* x) {
-        const float4* q = reinterpret_cast<const float4*>(p);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 v = __ldg(q + i);
-            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-        }
+    static __device__ __forceinline__ void load4(const float* p, float* x) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+    }
+    static __device__ __forceinline__ void load8(const float* p, float* x) {
+        load4(p, x); load4(p + 4, x + 4);
     }
     static __device__ __forceinline__ void store4(float* p, const float* y) {
         *reinterpret_cast<float4*>(p) = make_float4(y[0], y[1], y[2], y[3]);
@@ -168,15 +169,24 @@ struct Fast<float> {
 };
 
 // ---------------------------------------------------------------- index rules without F2I
-// floor(g*256) and trunc(clamp(g*255)): add 2^23 rounding toward -inf and read the
-// mantissa.  Same values as kornia_bin / kornia_idx (clahe.cuh).
-__device__ __forceinline__ int fast_bin(float g) {  // -1 = not counted (outside [0,1] or NaN)
-    const int n = (int)(__float_as_uint(__fmaf_rd(g, 256.0f, 8388608.0f)) - 0x4B000000u);
-    return (g >= 0.0f && g <= 1.0f) ? min(n, 255) : -1;
+// floor(g*256) and trunc(clamp(g*255)): add 2^23 rounding toward -inf and read the mantissa.
+// Same values as kornia_bin / kornia_idx (clahe.cuh).
+constexpr int kDummyBin = 256;  // histogram slot that swallows pixels torch.histc would ignore
+// Word offset into a 257-entry histogram: min(floor(g*256), 255), or kDummyBin outside [0,1] / NaN.
+// NONNEG: the caller guarantees g >= 0 and not NaN (Gaussian of normalised integer pixels).
+template <bool NONNEG>
+__device__ __forceinline__ int fast_bin(float g) {
+    float f = fminf(__fmaf_rd(g, 256.0f, 8388608.0f), 8388608.0f + 255.0f);
+    const bool ok = NONNEG ? (g <= 1.0f) : (g >= 0.0f && g <= 1.0f);
+    f = ok ? f : 8388608.0f + (float)kDummyBin;
+    return (int)(__float_as_uint(f) - 0x4B000000u);
 }
-__device__ __forceinline__ uint32_t fast_idx(float g) {
-    const float f = fminf(fmaxf(__fmul_rn(g, 255.0f), 0.0f), 255.0f);
-    return __float_as_uint(__fadd_rd(f, 8388608.0f)) & 0xFFu;
+// Bit pattern whose low byte is trunc(clamp(g*255, 0, 255)) (NaN -> 0).
+template <bool NONNEG>
+__device__ __forceinline__ uint32_t fast_idx_bits(float g) {
+    float f = fminf(__fmul_rn(g, 255.0f), 255.0f);
+    if (!NONNEG) f = fmaxf(f, 0.0f);
+    return __float_as_uint(__fadd_rd(f, 8388608.0f));
 }
 
 // x / 255, correctly rounded (Markstein: y = RN(1/b), q0 = RN(a*y), r = a - b*q0 exact, RN(q0 + r*y)).
@@ -186,17 +196,17 @@ __device__ __forceinline__ float div255(float x) {
     return __fmaf_rn(__fmaf_rn(-255.0f, q0, x), r, q0);
 }
 
-// One warp adds `bin` (or nothing when bin < 0) of each lane to its private histogram.
-__device__ __forceinline__ void hist_vote_add(int* s_h, int bin, int lane) {
-    unsigned rem = __ballot_sync(0xffffffffu, bin >= 0);
-    while (rem) {
-        const int leader = __ffs(rem) - 1;
-        const int b0 = __shfl_sync(0xffffffffu, bin, leader);
-        const unsigned m = __ballot_sync(0xffffffffu, bin == b0);
-        if (lane == leader) atomicAdd(&s_h[b0], __popc(m));
-        rem &= ~m;
-    }
+// Histogram increment.  atomicAdd(p, 1) with an unused result compiles to ATOMS.POPC.INC.32, which
+// aggregates same-address lanes in hardware: measured on B200 at 1.53 cycles per warp instruction
+// per SM for every same-address multiplicity from 1 to 32 (profiles/microbench/hist_prims_b200_r1.log),
+// whereas software aggregation costs far more issue slots (MATCH.ANY: 64 cycles for 32 distinct
+// values; a shfl/ballot/popc peel loop: ~14 instructions per distinct bin).  So constant images
+// ("air") and noise cost the same, and no per-warp sub-histograms are needed.
+__device__ __forceinline__ void hist_add(int* s_h, int bin) {
+    if (bin >= 0) atomicAdd(&s_h[bin], 1);
 }
+// Branch-free form for histograms with a dummy slot (bin from fast_bin, always in range).
+__device__ __forceinline__ void hist_add_nobranch(int* s_h, int bin) { atomicAdd(&s_h[bin], 1); }
 
 // Clip / redistribute / cumulate -> 256 LUT bytes, computed by ONE warp from the
 // block-total histogram in shared memory (lane L owns bins 8L..8L+7).

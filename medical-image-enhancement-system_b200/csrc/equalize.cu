@@ -44,7 +44,7 @@ equalize_hist_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, int
             const int x = x0 + lane;
             int bin = -1;
             if (x < w) bin = eq_bin(__fmul_rn(Px<SrcT>::to01(row[x], lo, rg), 255.0f));
-            hist_vote_add(s_hist + warp * kBins, bin, lane);
+            hist_add(s_hist + warp * kBins, bin);
         }
     }
     __syncthreads();
