@@ -121,11 +121,26 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
     if (warp == 8) warp_build_lut(s_hist, a.lp, a.luts + tile * kBins, lane);
 }
 
-// ================================================================ chain_b (fast)
-// One block per 64x64 output tile (aligned with the CLAHE tile grid, so the haloed
-// 72x72 region touches exactly 2x2 interpolation cells):
-//   tables : s_cell[a][b][grey] = the four neighbouring LUT entries (tl,tr,bl,br) of
-//            cell (a,b) packed in one word; per-row / per-column weight tables;
+// ================================================================ cell tables
+// Interpolation cell (cy, cx), cy in [0, gh], cx in [0, gw], is the region between the centres of
+// tiles (cy-1, cx-1) .. (cy, cx) (clamped at the image border).  For every grey level the four
+// neighbouring LUT entries (tl, tr, bl, br) are packed into one 32-bit word, so that chain_b needs a
+// single shared-memory lookup per pixel.  1 KB per cell; a tiny launch between chain_a and chain_b.
+__global__ void __launch_bounds__(256)
+chain_pack_cells_kernel(const uint8_t* __restrict__ luts, uint32_t* __restrict__ cells, int gh, int gw) {
+    const int cx = blockIdx.x, cy = blockIdx.y;
+    const int64_t n = blockIdx.z;
+    const int jt = max(cy - 1, 0), jb = min(cy, gh - 1), il = max(cx - 1, 0), ir = min(cx, gw - 1);
+    const uint8_t* nl = luts + n * (int64_t)gh * gw * kBins + threadIdx.x;
+    const uint32_t tl = nl[(jt * gw + il) * kBins], tr = nl[(jt * gw + ir) * kBins];
+    const uint32_t bl = nl[(jb * gw + il) * kBins], br = nl[(jb * gw + ir) * kBins];
+    cells[((n * (gh + 1) + cy) * (int64_t)(gw + 1) + cx) * kBins + threadIdx.x] = tl | (tr << 8) | (bl << 16) | (br << 24);
+}
+
+// ================================================================ chain_b (fast, 9-tap unsharp)
+// One block per 64x64 output tile (aligned with the CLAHE tile grid, so the haloed 72x72 region
+// touches exactly 2x2 interpolation cells):
+//   tables : the block's four 1 KB cell tables -> shared memory (one 16-byte copy per thread);
 //   C pass : CLAHE output C for every haloed pixel -> s_in;
 //   row / col pass, epilogue: C + (C - blur(C)) -> quantise -> 64-bit stores.
 
@@ -141,17 +156,21 @@ __device__ __forceinline__ float clahe_px(uint32_t e, float wxv, float wyv) {
     return div255(__fmaf_rn(wyv, __fsub_rn(t, b), b));
 }
 
-template <typename DstT, int R>
+// Interpolation weight of the upper / left tile for haloed index k (tile position p = k - 4):
+// kornia_axis() of any pixel at that position, identical for every interior tile; in the border
+// half-tiles both neighbours are the same tile, so the value there is irrelevant.
+struct AxisWeights {
+    float w[kTile + 8];
+};
+
+template <typename DstT>
 __global__ void __launch_bounds__(kFastThreads)
-chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
-    constexpr int E = kTile + 2 * R;
-    constexpr int PIN = TileSmem<R>::pin;
+chain_b_fast_kernel(ChainBArgs a, const uint32_t* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy) {
+    constexpr int R = 4, E = kTile + 2 * R, PIN = TileSmem<R>::pin;
     __shared__ __align__(16) float s_in[E * PIN];
     __shared__ __align__(16) float s_mid[E * kPMid];
     __shared__ __align__(16) uint32_t s_cell[4 * kBins];
-    __shared__ __align__(16) float s_wx[E + 8];
-    __shared__ float s_wy[E];
-    __shared__ int s_sy[E], s_sx[E + 8];
+    __shared__ __align__(16) float s_w[E];
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -160,137 +179,91 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
     const int tx0 = tx * kTile, ty0 = ty * kTile;
     const int h = a.g.h, w = a.g.w, gh = a.g.gh, gw = a.g.gw;
 
-    // ---- tables
-    if (tid < kBins) {
-        const uint8_t* nl = a.luts + n * (int64_t)gh * gw * kBins + tid;
-        // cell 0 = source rows (columns) before the tile centre, cell 1 = after it
-        const int jt[2] = {ty == 0 ? 0 : ty - 1, ty};
-        const int jb[2] = {ty, ty == gh - 1 ? gh - 1 : ty + 1};
-        const int il[2] = {tx == 0 ? 0 : tx - 1, tx};
-        const int ir[2] = {tx, tx == gw - 1 ? gw - 1 : tx + 1};
-#pragma unroll
-        for (int ca = 0; ca < 2; ++ca)
-#pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                const uint32_t tl = __ldg(nl + ((int64_t)jt[ca] * gw + il[cb]) * kBins);
-                const uint32_t tr = __ldg(nl + ((int64_t)jt[ca] * gw + ir[cb]) * kBins);
-                const uint32_t bl = __ldg(nl + ((int64_t)jb[ca] * gw + il[cb]) * kBins);
-                const uint32_t br = __ldg(nl + ((int64_t)jb[ca] * gw + ir[cb]) * kBins);
-                s_cell[(ca * 2 + cb) * kBins + tid] = tl | (tr << 8) | (bl << 16) | (br << 24);
-            }
-    } else {
-        // warp 8: per-row and per-column source coordinate + interpolation weight
-        for (int k = tid - kBins; k < 2 * E; k += 32) {
-            const bool is_row = k < E;
-            const int kk = is_row ? k : k - E;
-            const int len = is_row ? h : w;
-            const int src = border_index((is_row ? ty0 : tx0) - R + kk, len, a.border);
-            int j0, j1;
-            float wgt = 0.0f;
-            if (src >= 0) kornia_axis(src, kTile, is_row ? gh : gw, j0, j1, wgt);
-            if (is_row) { s_sy[kk] = src; s_wy[kk] = wgt; } else { s_sx[kk] = src; s_wx[kk] = wgt; }
-        }
+    // ---- tables: cell (a, b) of this tile = global cell (ty + a, tx + b)
+    if (tid < 256) {
+        const int c = tid >> 6, part = tid & 63;
+        const uint4* src = reinterpret_cast<const uint4*>(
+            cells + ((n * (gh + 1) + ty + (c >> 1)) * (int64_t)(gw + 1) + tx + (c & 1)) * kBins);
+        reinterpret_cast<uint4*>(s_cell)[tid] = __ldg(src + part);
+    } else if (tid - 256 < E / 4) {
+        const int k = (tid - 256) * 4;
+        *reinterpret_cast<float4*>(s_w + k) = make_float4(aw.w[k], aw.w[k + 1], aw.w[k + 2], aw.w[k + 3]);
     }
     __syncthreads();
 
-    // ---- CLAHE output of the haloed tile: item = (row r, 8-column chunk u)
+    // ---- CLAHE output of the haloed tile: item = (row r, 8-column chunk u); chunk u = image
+    //      columns gx0 .. gx0+7 with gx0 = tx0 - 4 + 8u (4-byte aligned)
     const uint8_t* iplane = a.idx + n * (int64_t)h * w;
-    constexpr int CH = (E + 7) / 8;
-    for (int i = tid; i < E * CH; i += kFastThreads) {
-        const int u = i % CH, r = i / CH;
-        const int sy = s_sy[r];
-        const int c_first = 8 * u;  // first haloed column of the chunk
-        float cval[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) cval[k] = 0.0f;
+    for (int i = tid; i < E * 9; i += kFastThreads) {
+        const int u = i % 9, r = i / 9;
+        const int sy = border_index(ty0 - R + r, h, a.border);
+        float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
         if (sy >= 0) {
-            const float wyv = s_wy[r];
-            const int ca = (sy >= ty0 + kTile / 2) ? 2 * kBins : 0;
+            const float wyv = s_w[r];
+            const uint32_t* cell = s_cell + ((sy >= ty0 + kTile / 2) ? 2 * kBins : 0);
             const uint8_t* irow = iplane + (int64_t)sy * w;
-            if (R == 4) {
-                // chunk = image columns gx0 .. gx0+7, gx0 = tx0 - 4 + 8u (4-byte aligned)
-                const int gx0 = tx0 - 4 + c_first;
-                uint32_t w0, w1;
-                bool z0 = false, z1 = false;
-                if (gx0 < 0) {  // columns -4..-1 mirror onto 4,3,2,1
-                    w1 = __ldg(reinterpret_cast<const uint32_t*>(irow));
-                    if (a.border == MIE_BORDER_REFLECT)
-                        w0 = __byte_perm(w1, __ldg(reinterpret_cast<const uint32_t*>(irow + 4)), 0x1234);
-                    else if (a.border == MIE_BORDER_REPLICATE) w0 = __byte_perm(w1, 0u, 0x0000);
-                    else { w0 = 0u; z0 = true; }
-                } else if (gx0 + 8 > w) {  // columns w..w+3 mirror onto w-2..w-5
-                    w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
-                    if (a.border == MIE_BORDER_REFLECT)
-                        w1 = __byte_perm(w0, __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 - 4)), 0x7012);
-                    else if (a.border == MIE_BORDER_REPLICATE) w1 = __byte_perm(w0, 0u, 0x3333);
-                    else { w1 = 0u; z1 = true; }
-                } else {
-                    w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
-                    w1 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 + 4));
-                }
-                // the cell column flips between haloed columns 35 and 36 (source column tx0+32)
-                const uint32_t* cellL = s_cell + ca + (c_first >= 36 ? kBins : 0);
-                const uint32_t* cellH = s_cell + ca + (c_first + 4 >= 36 ? kBins : 0);
-                const float4 wa = *reinterpret_cast<const float4*>(s_wx + c_first);
-                const float4 wb = *reinterpret_cast<const float4*>(s_wx + c_first + 4);
-                cval[0] = clahe_px(cellL[w0 & 0xFFu], wa.x, wyv);
-                cval[1] = clahe_px(cellL[(w0 >> 8) & 0xFFu], wa.y, wyv);
-                cval[2] = clahe_px(cellL[(w0 >> 16) & 0xFFu], wa.z, wyv);
-                cval[3] = clahe_px(cellL[w0 >> 24], wa.w, wyv);
-                cval[4] = clahe_px(cellH[w1 & 0xFFu], wb.x, wyv);
-                cval[5] = clahe_px(cellH[(w1 >> 8) & 0xFFu], wb.y, wyv);
-                cval[6] = clahe_px(cellH[(w1 >> 16) & 0xFFu], wb.z, wyv);
-                cval[7] = clahe_px(cellH[w1 >> 24], wb.w, wyv);
-                if (z0) { cval[0] = 0.f; cval[1] = 0.f; cval[2] = 0.f; cval[3] = 0.f; }
-                if (z1) { cval[4] = 0.f; cval[5] = 0.f; cval[6] = 0.f; cval[7] = 0.f; }
+            const int gx0 = tx0 - 4 + 8 * u;
+            uint32_t w0, w1;
+            bool z0 = false, z1 = false;
+            if (gx0 < 0) {  // columns -4..-1 mirror onto 4,3,2,1
+                w1 = __ldg(reinterpret_cast<const uint32_t*>(irow));
+                if (a.border == MIE_BORDER_REFLECT)
+                    w0 = __byte_perm(w1, __ldg(reinterpret_cast<const uint32_t*>(irow + 4)), 0x1234);
+                else if (a.border == MIE_BORDER_REPLICATE) w0 = __byte_perm(w1, 0u, 0x0000);
+                else { w0 = 0u; z0 = true; }
+            } else if (gx0 + 8 > w) {  // columns w..w+3 mirror onto w-2..w-5
+                w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
+                if (a.border == MIE_BORDER_REFLECT)
+                    w1 = __byte_perm(w0, __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 - 4)), 0x7012);
+                else if (a.border == MIE_BORDER_REPLICATE) w1 = __byte_perm(w0, 0u, 0x3333);
+                else { w1 = 0u; z1 = true; }
             } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int c = c_first + k;
-                    const int sx = c < E ? s_sx[c] : -1;
-                    if (sx >= 0) {
-                        const int cb = (sx >= tx0 + kTile / 2) ? kBins : 0;
-                        cval[k] = clahe_px(s_cell[ca + cb + irow[sx]], s_wx[c], wyv);
-                    }
-                }
+                w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
+                w1 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 + 4));
             }
+            // the cell column flips between haloed columns 35 and 36 (source column tx0 + 32)
+            const uint32_t* cellL = cell + (u >= 5 ? kBins : 0);
+            const uint32_t* cellH = cell + (u >= 4 ? kBins : 0);
+            const float4 wa = *reinterpret_cast<const float4*>(s_w + 8 * u);
+            const float4 wb = *reinterpret_cast<const float4*>(s_w + 8 * u + 4);
+            lo4.x = clahe_px(cellL[__byte_perm(w0, 0u, 0x4440)], wa.x, wyv);
+            lo4.y = clahe_px(cellL[__byte_perm(w0, 0u, 0x4441)], wa.y, wyv);
+            lo4.z = clahe_px(cellL[__byte_perm(w0, 0u, 0x4442)], wa.z, wyv);
+            lo4.w = clahe_px(cellL[__byte_perm(w0, 0u, 0x4443)], wa.w, wyv);
+            hi4.x = clahe_px(cellH[__byte_perm(w1, 0u, 0x4440)], wb.x, wyv);
+            hi4.y = clahe_px(cellH[__byte_perm(w1, 0u, 0x4441)], wb.y, wyv);
+            hi4.z = clahe_px(cellH[__byte_perm(w1, 0u, 0x4442)], wb.z, wyv);
+            hi4.w = clahe_px(cellH[__byte_perm(w1, 0u, 0x4443)], wb.w, wyv);
+            if (z0) lo4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (z1) hi4 = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float* dstp = s_in + r * PIN + c_first;
-        if (c_first + 8 <= PIN) {
-            *reinterpret_cast<float4*>(dstp) = make_float4(cval[0], cval[1], cval[2], cval[3]);
-            *reinterpret_cast<float4*>(dstp + 4) = make_float4(cval[4], cval[5], cval[6], cval[7]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (c_first + k < PIN) dstp[k] = cval[k];
-        }
+        float* dstp = s_in + r * PIN + 8 * u;
+        *reinterpret_cast<float4*>(dstp) = lo4;
+        *reinterpret_cast<float4*>(dstp + 4) = hi4;
     }
     __syncthreads();
 
     // ---- horizontal pass out of s_in (lanes on consecutive rows: conflict-free LDS.128 / STS.128)
-    {
-        constexpr int NV = (8 + 2 * R + 3) / 4;
-        for (int i = tid; i < E * 8; i += kFastThreads) {
-            const int r = i % E, s = i / E;
-            const float4* p = reinterpret_cast<const float4*>(s_in + r * PIN + s * 8);
-            float win[NV * 4];
+    for (int i = tid; i < E * 8; i += kFastThreads) {
+        const int r = i % E, s = i / E;
+        const float4* p = reinterpret_cast<const float4*>(s_in + r * PIN + s * 8);
+        float win[16];
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                const float4 t = p[v];
-                win[4 * v] = t.x; win[4 * v + 1] = t.y; win[4 * v + 2] = t.z; win[4 * v + 3] = t.w;
-            }
-            float o[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float acc = __fmul_rn(wx.w[0], win[j]);
-#pragma unroll
-                for (int t = 1; t <= 2 * R; ++t) acc = __fmaf_rn(wx.w[t], win[j + t], acc);
-                o[j] = acc;
-            }
-            float4* q = reinterpret_cast<float4*>(s_mid + r * kPMid + s * 8);
-            q[0] = make_float4(o[0], o[1], o[2], o[3]);
-            q[1] = make_float4(o[4], o[5], o[6], o[7]);
+        for (int v = 0; v < 4; ++v) {
+            const float4 t = p[v];
+            win[4 * v] = t.x; win[4 * v + 1] = t.y; win[4 * v + 2] = t.z; win[4 * v + 3] = t.w;
         }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float acc = __fmul_rn(wx.w[0], win[j]);
+#pragma unroll
+            for (int t = 1; t <= 2 * R; ++t) acc = __fmaf_rn(wx.w[t], win[j + t], acc);
+            o[j] = acc;
+        }
+        float4* q = reinterpret_cast<float4*>(s_mid + r * kPMid + s * 8);
+        q[0] = make_float4(o[0], o[1], o[2], o[3]);
+        q[1] = make_float4(o[4], o[5], o[6], o[7]);
     }
     __syncthreads();
 
@@ -302,6 +275,7 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
         for (int k = 0; k < 4 + 2 * R; ++k)
             win[k] = *reinterpret_cast<const float4*>(s_mid + (rb * 4 + k) * kPMid + q * 4);
         DstT* op = (DstT*)a.dst + n * a.dsn + (int64_t)(ty0 + rb * 4) * a.dsh + tx0 + q * 4;
+        const float* cp = s_in + (rb * 4 + R) * PIN + q * 4 + R;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float g[4];
@@ -312,18 +286,10 @@ chain_b_fast_kernel(ChainBArgs a, Taps wx, Taps wy) {
                 g[0] = __fmaf_rn(wy.w[t], win[j + t].x, g[0]); g[1] = __fmaf_rn(wy.w[t], win[j + t].y, g[1]);
                 g[2] = __fmaf_rn(wy.w[t], win[j + t].z, g[2]); g[3] = __fmaf_rn(wy.w[t], win[j + t].w, g[3]);
             }
-            const float* cp = s_in + (rb * 4 + j + R) * PIN + q * 4 + R;
-            float c[4];
-            if (R == 4) {
-                const float4 cv = *reinterpret_cast<const float4*>(cp);
-                c[0] = cv.x; c[1] = cv.y; c[2] = cv.z; c[3] = cv.w;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) c[k] = cp[k];
-            }
+            const float4 c = *reinterpret_cast<const float4*>(cp + j * PIN);
             float y[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(c[k], __fsub_rn(c[k], g[k]));
+            y[0] = __fadd_rn(c.x, __fsub_rn(c.x, g[0])); y[1] = __fadd_rn(c.y, __fsub_rn(c.y, g[1]));
+            y[2] = __fadd_rn(c.z, __fsub_rn(c.z, g[2])); y[3] = __fadd_rn(c.w, __fsub_rn(c.w, g[3]));
             Fast<DstT>::store4(op + (int64_t)j * a.dsh, y);
         }
     }
@@ -370,21 +336,32 @@ int launch_chain_a_fast(const ChainAArgs& a, int sd, const Taps& wx, const Taps&
     return MIE_OK;
 }
 
+size_t chain_cells_bytes(int64_t n, int gh, int gw) { return (size_t)n * (gh + 1) * (gw + 1) * kBins * 4; }
+
 template <typename DstT>
-static int launch_b_t(const ChainBArgs& b, const Taps& wx, const Taps& wy, int R, unsigned blocks, cudaStream_t st) {
-    switch (R) {
-        case 1: chain_b_fast_kernel<DstT, 1><<<blocks, kFastThreads, 0, st>>>(b, wx, wy); break;
-        case 2: chain_b_fast_kernel<DstT, 2><<<blocks, kFastThreads, 0, st>>>(b, wx, wy); break;
-        case 3: chain_b_fast_kernel<DstT, 3><<<blocks, kFastThreads, 0, st>>>(b, wx, wy); break;
-        default: chain_b_fast_kernel<DstT, 4><<<blocks, kFastThreads, 0, st>>>(b, wx, wy); break;
-    }
+static int launch_b_t(const ChainBArgs& b, const uint32_t* cells, const AxisWeights& aw, const Taps& wx,
+                      const Taps& wy, unsigned blocks, cudaStream_t st) {
+    chain_b_fast_kernel<DstT><<<blocks, kFastThreads, 0, st>>>(b, cells, aw, wx, wy);
     return check_launch();
 }
 
-int launch_chain_b_fast(const ChainBArgs& b, int dd, const Taps& wx, const Taps& wy, int R, int64_t n,
+// Runs the cell-packing launch and the tuned chain_b (9-tap unsharp only).  `cells` must hold
+// chain_cells_bytes(n, gh, gw) bytes.
+int launch_chain_b_fast(const ChainBArgs& b, int dd, uint32_t* cells, const Taps& wx, const Taps& wy, int64_t n,
                         cudaStream_t st) {
+    if (n > 65535) return MIE_E_SHAPE;
+    dim3 pgrid((unsigned)(b.g.gw + 1), (unsigned)(b.g.gh + 1), (unsigned)n);
+    chain_pack_cells_kernel<<<pgrid, 256, 0, st>>>(b.luts, cells, b.g.gh, b.g.gw);
+    int rc = check_launch();
+    if (rc) return rc;
+    AxisWeights aw;
+    for (int k = 0; k < kTile + 8; ++k) {
+        const int p = k - 4;                              // position relative to the tile origin
+        const int r = p < kTile / 2 ? p + kTile / 2 : p - kTile / 2;  // offset from the previous tile centre
+        aw.w[k] = (float)(kTile - 1 - r) / (float)(kTile - 1);
+    }
     const unsigned blocks = (unsigned)(n * b.tiles_x * b.tiles_y);
-    MIE_DISPATCH_SRC(dd, return launch_b_t<SrcT>(b, wx, wy, R, blocks, st));
+    MIE_DISPATCH_SRC(dd, return launch_b_t<SrcT>(b, cells, aw, wx, wy, blocks, st));
     return MIE_OK;
 }
 
