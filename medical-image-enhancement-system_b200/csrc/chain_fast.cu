@@ -103,13 +103,7 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float g[4];
-            g[0] = __fmul_rn(wy.w[0], win[j].x); g[1] = __fmul_rn(wy.w[0], win[j].y);
-            g[2] = __fmul_rn(wy.w[0], win[j].z); g[3] = __fmul_rn(wy.w[0], win[j].w);
-#pragma unroll
-            for (int t = 1; t <= 2 * R; ++t) {
-                g[0] = __fmaf_rn(wy.w[t], win[j + t].x, g[0]); g[1] = __fmaf_rn(wy.w[t], win[j + t].y, g[1]);
-                g[2] = __fmaf_rn(wy.w[t], win[j + t].z, g[2]); g[3] = __fmaf_rn(wy.w[t], win[j + t].w, g[3]);
-            }
+            col4_f32x2<R>(win, j, wy, g);
             *reinterpret_cast<uint32_t*>(ip + (int64_t)j * w) =
                 pack_low_bytes(fast_idx_bits<NN>(g[0]), fast_idx_bits<NN>(g[1]), fast_idx_bits<NN>(g[2]),
                                fast_idx_bits<NN>(g[3]));
@@ -279,13 +273,7 @@ chain_b_fast_kernel(ChainBArgs a, const uint32_t* __restrict__ cells, AxisWeight
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float g[4];
-            g[0] = __fmul_rn(wy.w[0], win[j].x); g[1] = __fmul_rn(wy.w[0], win[j].y);
-            g[2] = __fmul_rn(wy.w[0], win[j].z); g[3] = __fmul_rn(wy.w[0], win[j].w);
-#pragma unroll
-            for (int t = 1; t <= 2 * R; ++t) {
-                g[0] = __fmaf_rn(wy.w[t], win[j + t].x, g[0]); g[1] = __fmaf_rn(wy.w[t], win[j + t].y, g[1]);
-                g[2] = __fmaf_rn(wy.w[t], win[j + t].z, g[2]); g[3] = __fmaf_rn(wy.w[t], win[j + t].w, g[3]);
-            }
+            col4_f32x2<R>(win, j, wy, g);
             const float4 c = *reinterpret_cast<const float4*>(cp + j * PIN);
             float y[4];
             y[0] = __fadd_rn(c.x, __fsub_rn(c.x, g[0])); y[1] = __fadd_rn(c.y, __fsub_rn(c.y, g[1]));

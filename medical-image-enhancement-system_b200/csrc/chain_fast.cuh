@@ -190,6 +190,22 @@ __device__ __forceinline__ uint32_t fast_idx_bits(float g) {
     return __float_as_uint(__fadd_rd(f, 8388608.0f));
 }
 
+// Vertical correlation of 4 adjacent columns with packed fma.rn.f32x2 (same per-lane rounding as
+// four scalar fmas; one issue slot per two results).  win[k] = row k of the window, result row j.
+template <int R>
+__device__ __forceinline__ void col4_f32x2(const float4* win, int j, const Taps& wy, float* g) {
+    const float2 w0 = make_float2(wy.w[0], wy.w[0]);
+    float2 a = __fmul2_rn(w0, make_float2(win[j].x, win[j].y));
+    float2 b = __fmul2_rn(w0, make_float2(win[j].z, win[j].w));
+#pragma unroll
+    for (int t = 1; t <= 2 * R; ++t) {
+        const float2 wt = make_float2(wy.w[t], wy.w[t]);
+        a = __ffma2_rn(wt, make_float2(win[j + t].x, win[j + t].y), a);
+        b = __ffma2_rn(wt, make_float2(win[j + t].z, win[j + t].w), b);
+    }
+    g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
+}
+
 // x / 255, correctly rounded (Markstein: y = RN(1/b), q0 = RN(a*y), r = a - b*q0 exact, RN(q0 + r*y)).
 __device__ __forceinline__ float div255(float x) {
     constexpr float r = 0.003921568859368563f;

@@ -1,0 +1,66 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): the NCCL z-halo path of BASELINE.json
+config 3 and the slice-sharded chain reproduce the 1-GPU results bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import mie_b200 as M
+    from mie_b200 import synthetic
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    try:
+        vol = synthetic.phantom_volume((37, 128, 192), np.int16, seed=5)  # ragged split on purpose
+        z0, z1 = M.shard_range(vol.shape[0], world, rank)
+        slab = torch.from_numpy(vol[z0:z1].copy()).to(dev)
+        out = M.median3d_clahe_slab(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0))
+        np.save(os.path.join(out_dir, f"vol{rank}.npy"), out.cpu().numpy())
+        x = synthetic.phantom((10, 1, 256, 256), np.uint16, seed=6)
+        s0, s1 = M.shard_range(10, world, rank)
+        y = M.enhance_chain(torch.from_numpy(x[s0:s1].copy()).to(dev), M.ChainConfig(grid_size=(4, 4)))
+        np.save(os.path.join(out_dir, f"chain{rank}.npy"), y.cpu().numpy())
+        torch.cuda.synchronize()
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_results_equal_single_gpu(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import mie_b200 as M
+    from mie_b200 import synthetic
+
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    dev = torch.device("cuda:0")
+    vol = synthetic.phantom_volume((37, 128, 192), np.int16, seed=5)
+    ref = M.median3d_clahe_slab(torch.from_numpy(vol).to(dev), 2.0, (2, 3), value_range=(-1024.0, 3071.0)).cpu().numpy()
+    got = np.concatenate([np.load(tmp_path / f"vol{r}.npy") for r in range(world)])
+    assert np.array_equal(got, ref)
+    x = synthetic.phantom((10, 1, 256, 256), np.uint16, seed=6)
+    refc = M.enhance_chain(torch.from_numpy(x).to(dev), M.ChainConfig(grid_size=(4, 4))).cpu().numpy()
+    gotc = np.concatenate([np.load(tmp_path / f"chain{r}.npy") for r in range(world)])
+    assert np.array_equal(gotc, refc)
