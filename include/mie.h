@@ -180,7 +180,10 @@ int mie_bilateral(const void* src, void* dst, int src_dtype, int dst_dtype,
  * bench.py to time each kernel with CUDA events; MIE_E_UNSUPPORTED when the
  * geometry takes the unfused path).                                               */
 enum mie_chain_stages { MIE_CHAIN_STAGE_A = 1, MIE_CHAIN_STAGE_B = 2, MIE_CHAIN_ALL = 3 };
-/* 1 if (h, w, grid, kernel sizes) run on the fused two-launch path, else 0. */
+/* Which path (h, w, grid, kernel sizes) takes: 0 = stages run unfused (4 launches), 1 = generic
+ * fused kernels (2 launches), 2 = tuned fused kernels for 64x64-pixel tiles and a 9-tap unsharp
+ * (3 launches: chain_a, cell-table packing, chain_b; needs 16-byte aligned rows and the dtype's
+ * default value range, otherwise 1 applies). */
 int mie_chain_is_fused(int h, int w, int gh, int gw, int kgx, int kgy, int kux, int kuy);
 size_t mie_chain_workspace_bytes(int64_t n, int h, int w, int gh, int gw);
 int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int dst_dtype,

@@ -234,7 +234,10 @@ int mie_chain_is_fused(int h, int w, int gh, int gw, int kgx, int kgy, int kux, 
     ClaheGeom g;
     int cap = 0;
     if (make_clahe_geom(h, w, gh, gw, MIE_CLAHE_KORNIA, &g)) return 0;
-    return fused_ok(g, kgx, kgy, kux, kuy, &cap) ? 1 : 0;
+    if (!fused_ok(g, kgx, kgy, kux, kuy, &cap)) return 0;
+    // 2: tuned kernels (chain_a, cell packing, chain_b = 3 launches) when the buffers are 16-byte
+    // aligned and the integer range is the dtype default; 1: generic fused kernels (2 launches)
+    return (g.th == kTile && g.tw == kTile && kux == 9) ? 2 : 1;
 }
 
 size_t mie_chain_workspace_bytes(int64_t n, int h, int w, int gh, int gw) {

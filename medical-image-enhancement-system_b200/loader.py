@@ -1,0 +1,104 @@
+"""Slice / volume batching loader (named in the north star as a subsystem that
+changes): host-resident slice stacks are streamed through the GPU kernels in chunks, with the
+host->device copy of chunk k+1, the kernels of chunk k and the device->host copy of chunk k-1
+running concurrently on three CUDA streams (PCIe is full duplex, so a step costs about
+max(H2D, D2H) instead of their sum plus the kernels).
+
+    pipe = HostSlicePipeline(device, (512, 512), torch.uint16, chunk=32)
+    pipe.run(x_host_pinned, y_host_pinned)          # enhance_chain on every slice
+
+Pinned host memory is required for the copies to be asynchronous; `pin()` is a helper.
+Integer <-> [0,1] normalisation policy (value_range / HU window) travels in ChainConfig.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+
+from .chain import ChainConfig, chain_workspace_bytes, enhance_chain
+
+__all__ = ["HostSlicePipeline", "pin", "enhance_chain_host"]
+
+
+def pin(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_pinned() else t.contiguous().pin_memory()
+
+
+class HostSlicePipeline:
+    """Triple-buffered host -> device -> host pipeline over the leading (slice) dimension.
+
+    `fn(x_dev, out_dev, workspace)` enqueues the device work of one chunk on the current stream;
+    the default runs the fused Gaussian -> CLAHE -> unsharp chain.
+    """
+
+    def __init__(self, device, slice_shape, dtype, chunk: int = 32, depth: int = 3,
+                 config: ChainConfig = ChainConfig(), fn: Optional[Callable] = None, out_dtype=None):
+        self.device = torch.device(device)
+        self.h, self.w = int(slice_shape[-2]), int(slice_shape[-1])
+        self.chunk, self.depth, self.config = int(chunk), int(depth), config
+        self.dtype = dtype
+        self.out_dtype = dtype if out_dtype is None else out_dtype
+        self.fn = fn
+        with torch.cuda.device(self.device):
+            self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream() for _ in range(3))
+            shape = (self.chunk, 1, self.h, self.w)
+            self.x = [torch.empty(shape, dtype=dtype, device=self.device) for _ in range(depth)]
+            self.y = [torch.empty(shape, dtype=self.out_dtype, device=self.device) for _ in range(depth)]
+            ws = chain_workspace_bytes(self.chunk, self.h, self.w, config.grid_size)
+            self.ws = [torch.empty(max(ws, 1), dtype=torch.uint8, device=self.device) for _ in range(depth)]
+            self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_comp = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.launches_per_chunk = 3
+
+    def _device_work(self, x, y, ws):
+        if self.fn is not None:
+            self.fn(x, y, ws)
+        else:
+            enhance_chain(x, self.config, out=y, workspace=ws)
+
+    def run(self, src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+        """src, dst: host tensors (N, H, W) or (N, 1, H, W), ideally pinned.  Returns dst.  The call
+        returns after the last device->host copy has been enqueued AND completed."""
+        n = src.shape[0]
+        s = src.reshape(n, 1, self.h, self.w)
+        d = dst.reshape(n, 1, self.h, self.w)
+        caller = torch.cuda.current_stream(self.device)
+        for st in (self.s_in, self.s_comp, self.s_out):
+            st.wait_stream(caller)
+        used = [False] * self.depth
+        for i, z0 in enumerate(range(0, n, self.chunk)):
+            z1 = min(z0 + self.chunk, n)
+            m, k = z1 - z0, i % self.depth
+            with torch.cuda.stream(self.s_in):
+                if used[k]:
+                    self.s_in.wait_event(self.ev_comp[k])    # kernels of the previous user of x[k] are done
+                self.x[k][:m].copy_(s[z0:z1], non_blocking=True)
+                self.ev_in[k].record(self.s_in)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(self.ev_in[k])
+                if used[k]:
+                    self.s_comp.wait_event(self.ev_out[k])   # previous contents of y[k] have left the device
+                self._device_work(self.x[k][:m], self.y[k][:m], self.ws[k])
+                self.ev_comp[k].record(self.s_comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_comp[k])
+                d[z0:z1].copy_(self.y[k][:m], non_blocking=True)
+                self.ev_out[k].record(self.s_out)
+            used[k] = True
+        caller.wait_stream(self.s_out)
+        self.s_out.synchronize()
+        return dst
+
+
+def enhance_chain_host(src: torch.Tensor, config: ChainConfig = ChainConfig(), *, out: torch.Tensor = None,
+                       device="cuda", chunk: int = 32) -> torch.Tensor:
+    """One-call convenience: enhance a host-resident slice stack (N, H, W) / (N, 1, H, W) on `device`."""
+    if src.is_cuda:
+        raise ValueError("enhance_chain_host takes host tensors; use enhance_chain for device tensors")
+    src = pin(src)
+    if out is None:
+        out = torch.empty_like(src).pin_memory()
+    pipe = HostSlicePipeline(device, src.shape[-2:], src.dtype, chunk=min(chunk, max(int(src.shape[0]), 1)), config=config)
+    return pipe.run(src, out)

@@ -35,8 +35,8 @@ def shard_range(total: int, world_size: int, rank: int):
 
 
 def _wire(t: torch.Tensor) -> torch.Tensor:
-    """uint16 has no NCCL / gloo datatype: ship the same bits as int16."""
-    return t.view(torch.int16) if t.dtype == torch.uint16 else t
+    """16-bit integer planes have no NCCL process-group datatype: ship the same bytes as uint8."""
+    return t.view(torch.uint8)
 
 
 class _HaloExchange:
