@@ -46,13 +46,14 @@ def enhance_chain(input: torch.Tensor, config: ChainConfig = ChainConfig(), *, o
     """
     cfg = config
     _check_clahe_args(cfg.clip_limit, cfg.grid_size)
-    require_cuda(input)
     gky, gkx = _pair_int(cfg.denoise_kernel_size, "denoise_kernel_size")
     uky, ukx = _pair_int(cfg.sharpen_kernel_size, "sharpen_kernel_size")
     _check_kernel(gky, gkx)
     _check_kernel(uky, ukx)
     gsy, gsx = _pair_float(cfg.denoise_sigma, "denoise_sigma")
     usy, usx = _pair_float(cfg.sharpen_sigma, "sharpen_sigma")
+    _border(cfg.border_type)
+    require_cuda(input)
     x, n, h, w = as_planes(input)
     lo, hi = value_range_of(x, cfg.value_range)
     if out is None:

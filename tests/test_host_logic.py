@@ -1,0 +1,122 @@
+"""CPU checks of the arithmetic identities the tuned kernels rely on (csrc/chain_fast.cuh) and of host-side
+helpers.  fp32 fma is emulated in float64, which is exact here: every product / sum involved fits in 53 bits
+before the single rounding to fp32."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def fma32(a, b, c):
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def test_u16_to_unit_without_divide_is_exact_for_all_codes():
+    v = np.arange(65536, dtype=np.uint32)
+    bits = (np.uint32(0x43000000) | v).astype(np.uint32)           # OR v into the mantissa of 128.0f
+    t = (bits.view(np.float32) - np.float32(128.0)).astype(np.float32)   # v * 2^-16, exact
+    assert np.array_equal(t.astype(np.float64), v / 65536.0)
+    c = np.float32(1.5259021893143654e-05)                          # RN(1/65535)
+    assert c == np.float32(1.0 / 65535.0)
+    x = fma32(t, c, t)
+    assert np.array_equal(x, v.astype(np.float32) / np.float32(65535.0))
+
+
+def test_i16_and_u8_variants():
+    s = np.arange(-32768, 32768, dtype=np.int32)
+    u = (s.astype(np.uint32) & 0xFFFF) ^ 0x8000                      # v + 32768
+    t = ((np.uint32(0x43000000) | u).astype(np.uint32).view(np.float32) - np.float32(128.0)).astype(np.float32)
+    x = fma32(t, np.float32(1.0 / 65535.0), t)
+    assert np.array_equal(x, (s.astype(np.float32) + np.float32(32768.0)) / np.float32(65535.0))
+    b = np.arange(256, dtype=np.uint32)
+    t8 = ((np.uint32(0x47000000) | b).astype(np.uint32).view(np.float32) - np.float32(32768.0)).astype(np.float32)
+    x8 = fma32(t8, np.float32(0.003921568859368563), t8)
+    assert np.array_equal(x8, b.astype(np.float32) / np.float32(255.0))
+
+
+def test_markstein_division_by_255_is_correctly_rounded():
+    rng = np.random.default_rng(0)
+    o = np.concatenate([(rng.random(4_000_000) * 255).astype(np.float32), np.arange(256, dtype=np.float32),
+                        np.float32([1e-6, 254.99998, 255.0, 0.0])])
+    r = np.float32(0.003921568859368563)
+    q0 = (o * r).astype(np.float32)
+    q = fma32(fma32(np.float32(-255.0), q0, o), r, q0)
+    assert np.array_equal(q, (o / np.float32(255.0)).astype(np.float32))
+
+
+def test_magic_number_floor_trunc_rint():
+    rng = np.random.default_rng(1)
+    g = np.concatenate([rng.random(1_000_000, dtype=np.float32), np.float32([0.0, 1.0, 0.5, 255 / 256.0])])
+    magic = np.float32(8388608.0)
+    # floor(g*256): the fma is exact before its round-down, so floor of the exact product
+    n = np.floor(g.astype(np.float64) * 256.0 + float(magic)).astype(np.int64) - 0x800000
+    assert np.array_equal(np.minimum(n, 255), np.minimum(np.floor(g * np.float32(256.0)), 255).astype(np.int64))
+    # trunc(fl(g*255)): round the product to fp32 first, then add 2^23 rounding down
+    f = (g * np.float32(255.0)).astype(np.float32)
+    idx = np.floor(f.astype(np.float64) + float(magic)).astype(np.int64) - 0x800000
+    assert np.array_equal(idx, f.astype(np.int64))
+    # rint(c*65535) by adding 2^23 in round-to-nearest-even
+    p = (g * np.float32(65535.0)).astype(np.float32)
+    q = (p + magic).astype(np.float32).view(np.uint32) & 0xFFFF
+    assert np.array_equal(q.astype(np.int64), np.rint(p).astype(np.int64))
+
+
+def test_axis_weight_table_matches_kornia_axis():
+    """The per-position weight table of chain_b (csrc/chain_fast.cu: launch_chain_b_fast) equals
+    (T-1-r)/(T-1) of the oracle's kornia_axis for every interior tile position."""
+    T = 64
+    for k in range(T + 8):
+        p = k - 4
+        r = p + T // 2 if p < T // 2 else p - T // 2
+        w = np.float32(T - 1 - r) / np.float32(T - 1)
+        for ty0 in (64, 192):                       # interior tiles of a 512-row image
+            y = ty0 + p
+            rel = y - T // 2
+            j0 = rel // T
+            assert rel - j0 * T == r
+            assert w == np.float32(T - 1 - (rel - j0 * T)) / np.float32(T - 1)
+
+
+def test_gaussian_kernel_host_function_matches_oracle():
+    import mie_b200 as M
+    import oracle as O
+
+    for k, s in [(9, 1.0), (7, 1.0), (5, 1.2), (33, 5.0), (4, 1.0), (1, 1.0)]:
+        a, b = M.get_gaussian_kernel1d(k, s), O.gaussian_kernel1d(k, s)
+        assert a.dtype == np.float32 and np.array_equal(a, b)
+        assert abs(float(a.astype(np.float64).sum()) - 1.0) < 1e-6
+
+
+def test_committed_fixture_matches_oracle():
+    import oracle as O
+
+    fx = np.load(os.path.join(GOLDEN, "chain_128_grid2.npz"))
+    out, st = O.chain_gauss_clahe_unsharp(fx["input"], grid_size=(2, 2), return_stages=True)
+    assert np.array_equal(out, fx["output"]) and np.array_equal(st["luts"], fx["luts"])
+
+
+def test_synthetic_phantom_properties():
+    from mie_b200 import synthetic
+
+    p = synthetic.phantom((4, 1, 512, 512), np.uint16, seed=0)
+    assert p.dtype == np.uint16 and p.max() <= 4095
+    assert (p == 0).mean() >= 0.40                      # >= 40 % air, exactly zero
+    v = synthetic.phantom_volume((16, 64, 64), np.int16, seed=0)
+    assert v.min() == -1024 and v.max() <= 3071
+    assert np.array_equal(synthetic.phantom((2, 1, 64, 64), np.uint16, seed=3), synthetic.phantom((2, 1, 64, 64), np.uint16, seed=3))
+
+
+def test_chain_config_validation_without_gpu():
+    import torch
+
+    import mie_b200 as M
+
+    x = torch.zeros(1, 1, 64, 64, dtype=torch.uint16)
+    with pytest.raises(TypeError):
+        M.enhance_chain(x, M.ChainConfig(clip_limit=2))
+    with pytest.raises(ValueError):
+        M.enhance_chain(x, M.ChainConfig(denoise_kernel_size=8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        M.enhance_chain(x)
