@@ -314,11 +314,11 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
         }
         if (!(stages & MIE_CHAIN_STAGE_B)) return MIE_OK;
         if (kux == 9) {
-            // packed cell tables live behind the index plane (always inside the workspace bound:
-            // (gh+1)(gw+1) KB <= 3 bytes per pixel for 64x64-pixel tiles)
+            // cell tables live behind the index plane (always inside the workspace bound:
+            // 2 (gh+1)(gw+1) KB <= 3 bytes per pixel for 64x64-pixel tiles)
             size_t off = ((size_t)n * gh * gw * kBins + (size_t)n * h * w + 255) & ~(size_t)255;
             if (off + chain_cells_bytes(n, gh, gw) > workspace_bytes) return MIE_E_WORKSPACE;
-            return launch_chain_b_fast(b, dst_dtype, (uint32_t*)((uint8_t*)workspace + off), tux, tuy, n, st);
+            return launch_chain_b_fast(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st);
         }
         stages = MIE_CHAIN_STAGE_B;  // other unsharp sizes: generic chain_b on the same index plane / LUTs
     }

@@ -1,6 +1,8 @@
 // chain_fast.cu — tuned kernels of the fused Gaussian -> CLAHE -> unsharp chain for
 // 64x64-pixel CLAHE tiles (see chain_fast.cuh for the instruction-level tricks and
 // chain.cu for the algorithm and the generic kernels these two must equal bit for bit).
+#include <cuda_fp16.h>
+
 #include "chain_fast.cuh"
 
 namespace mie {
@@ -117,18 +119,25 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
 
 // ================================================================ cell tables
 // Interpolation cell (cy, cx), cy in [0, gh], cx in [0, gw], is the region between the centres of
-// tiles (cy-1, cx-1) .. (cy, cx) (clamped at the image border).  For every grey level the four
-// neighbouring LUT entries (tl, tr, bl, br) are packed into one 32-bit word, so that chain_b needs a
-// single shared-memory lookup per pixel.  1 KB per cell; a tiny launch between chain_a and chain_b.
+// tiles (cy-1, cx-1) .. (cy, cx) (clamped at the image border).  For every grey level the cell table
+// holds what the blend needs, ready to use: (tl - tr, tr, bl - br, br) as four fp16 values (integers
+// of magnitude <= 255 are exact in fp16), 8 bytes per grey level, 2 KB per cell.  chain_b then needs
+// ONE 64-bit shared-memory load per pixel and no integer unpacking.  A tiny launch between chain_a
+// and chain_b.
 __global__ void __launch_bounds__(256)
-chain_pack_cells_kernel(const uint8_t* __restrict__ luts, uint32_t* __restrict__ cells, int gh, int gw) {
+chain_pack_cells_kernel(const uint8_t* __restrict__ luts, uint2* __restrict__ cells, int gh, int gw) {
     const int cx = blockIdx.x, cy = blockIdx.y;
     const int64_t n = blockIdx.z;
     const int jt = max(cy - 1, 0), jb = min(cy, gh - 1), il = max(cx - 1, 0), ir = min(cx, gw - 1);
     const uint8_t* nl = luts + n * (int64_t)gh * gw * kBins + threadIdx.x;
-    const uint32_t tl = nl[(jt * gw + il) * kBins], tr = nl[(jt * gw + ir) * kBins];
-    const uint32_t bl = nl[(jb * gw + il) * kBins], br = nl[(jb * gw + ir) * kBins];
-    cells[((n * (gh + 1) + cy) * (int64_t)(gw + 1) + cx) * kBins + threadIdx.x] = tl | (tr << 8) | (bl << 16) | (br << 24);
+    const int tl = nl[(jt * gw + il) * kBins], tr = nl[(jt * gw + ir) * kBins];
+    const int bl = nl[(jb * gw + il) * kBins], br = nl[(jb * gw + ir) * kBins];
+    const __half2 top = __floats2half2_rn((float)(tl - tr), (float)tr);
+    const __half2 bot = __floats2half2_rn((float)(bl - br), (float)br);
+    uint2 e;
+    e.x = *reinterpret_cast<const uint32_t*>(&top);
+    e.y = *reinterpret_cast<const uint32_t*>(&bot);
+    cells[((n * (gh + 1) + cy) * (int64_t)(gw + 1) + cx) * kBins + threadIdx.x] = e;
 }
 
 // ================================================================ chain_b (fast, 9-tap unsharp)
@@ -138,15 +147,13 @@ chain_pack_cells_kernel(const uint8_t* __restrict__ luts, uint32_t* __restrict__
 //   C pass : CLAHE output C for every haloed pixel -> s_in;
 //   row / col pass, epilogue: C + (C - blur(C)) -> quantise -> 64-bit stores.
 
-// CLAHE output of one pixel: e = packed (tl,tr,bl,br); bytes become floats by OR-ing them into the
-// mantissa of 2^23 (differences of two such floats are exact).
-__device__ __forceinline__ float clahe_px(uint32_t e, float wxv, float wyv) {
-    const float A = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7650));  // 2^23 + tl
-    const float B = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7651));  // 2^23 + tr
-    const float C = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7652));  // 2^23 + bl
-    const float D = __uint_as_float(__byte_perm(e, 0x4B000000u, 0x7653));  // 2^23 + br
-    const float t = __fmaf_rn(wxv, __fsub_rn(A, B), __fsub_rn(B, 8388608.0f));
-    const float b = __fmaf_rn(wxv, __fsub_rn(C, D), __fsub_rn(D, 8388608.0f));
+// CLAHE output of one pixel from its cell-table entry e = fp16 (tl - tr, tr | bl - br, br):
+// t = tr + wx (tl - tr); b = br + wx (bl - br); out = (b + wy (t - b)) / 255, one fma per lerp.
+__device__ __forceinline__ float clahe_px(uint2 e, float wxv, float wyv) {
+    const float2 top = __half22float2(*reinterpret_cast<const __half2*>(&e.x));
+    const float2 bot = __half22float2(*reinterpret_cast<const __half2*>(&e.y));
+    const float t = __fmaf_rn(wxv, top.x, top.y);
+    const float b = __fmaf_rn(wxv, bot.x, bot.y);
     return div255(__fmaf_rn(wyv, __fsub_rn(t, b), b));
 }
 
@@ -159,12 +166,14 @@ struct AxisWeights {
 
 template <typename DstT>
 __global__ void __launch_bounds__(kFastThreads)
-chain_b_fast_kernel(ChainBArgs a, const uint32_t* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy) {
+chain_b_fast_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy) {
     constexpr int R = 4, E = kTile + 2 * R, PIN = TileSmem<R>::pin;
-    __shared__ __align__(16) float s_in[E * PIN];
-    __shared__ __align__(16) float s_mid[E * kPMid];
-    __shared__ __align__(16) uint32_t s_cell[4 * kBins];
-    __shared__ __align__(16) float s_w[E];
+    extern __shared__ __align__(16) float smem[];
+    float* s_in = smem;                                        // E x PIN
+    float* s_mid = s_in + E * PIN;                             // E x kPMid (written after the C pass)
+    uint2* s_cell = reinterpret_cast<uint2*>(s_mid);           // 4 cells x 256 entries: dead once the C pass
+                                                               // is over, so it shares s_mid's storage
+    float* s_w = s_mid + E * kPMid;                            // E weights
 
     const int tid = threadIdx.x;
     const int64_t tile = blockIdx.x;
@@ -175,65 +184,81 @@ chain_b_fast_kernel(ChainBArgs a, const uint32_t* __restrict__ cells, AxisWeight
 
     // ---- tables: cell (a, b) of this tile = global cell (ty + a, tx + b)
     if (tid < 256) {
-        const int c = tid >> 6, part = tid & 63;
+        const int c = tid >> 6, part = tid & 63;  // 64 threads x 2 x 16 B per 2 KB cell table
         const uint4* src = reinterpret_cast<const uint4*>(
             cells + ((n * (gh + 1) + ty + (c >> 1)) * (int64_t)(gw + 1) + tx + (c & 1)) * kBins);
-        reinterpret_cast<uint4*>(s_cell)[tid] = __ldg(src + part);
+        uint4* dst4 = reinterpret_cast<uint4*>(s_cell + c * kBins);
+        dst4[part] = __ldg(src + part);
+        dst4[part + 64] = __ldg(src + part + 64);
     } else if (tid - 256 < E / 4) {
         const int k = (tid - 256) * 4;
         *reinterpret_cast<float4*>(s_w + k) = make_float4(aw.w[k], aw.w[k + 1], aw.w[k + 2], aw.w[k + 3]);
     }
+    // ---- CLAHE output of the haloed tile: item = (row r, 8-column chunk u); chunk u = image
+    //      columns gx0 .. gx0+7 with gx0 = tx0 - 4 + 8u (4-byte aligned).  The index words of the
+    //      next item are fetched while the current one is computed (and the first fetch overlaps the
+    //      table loads above), which hides the global-load latency of this pass.
+    const uint8_t* iplane = a.idx + n * (int64_t)h * w;
+    struct IdxChunk { uint32_t w0, w1; int sy; bool z0, z1; };
+    auto fetch = [&](int i) {
+        IdxChunk c;
+        const int u = i % 9, r = i / 9;
+        c.sy = border_index(ty0 - R + r, h, a.border);
+        c.w0 = c.w1 = 0u; c.z0 = c.z1 = false;
+        if (c.sy >= 0) {
+            const uint8_t* irow = iplane + (int64_t)c.sy * w;
+            const int gx0 = tx0 - 4 + 8 * u;
+            if (gx0 < 0) {  // columns -4..-1 mirror onto 4,3,2,1
+                c.w1 = __ldg(reinterpret_cast<const uint32_t*>(irow));
+                if (a.border == MIE_BORDER_REFLECT)
+                    c.w0 = __byte_perm(c.w1, __ldg(reinterpret_cast<const uint32_t*>(irow + 4)), 0x1234);
+                else if (a.border == MIE_BORDER_REPLICATE) c.w0 = __byte_perm(c.w1, 0u, 0x0000);
+                else c.z0 = true;
+            } else if (gx0 + 8 > w) {  // columns w..w+3 mirror onto w-2..w-5
+                c.w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
+                if (a.border == MIE_BORDER_REFLECT)
+                    c.w1 = __byte_perm(c.w0, __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 - 4)), 0x7012);
+                else if (a.border == MIE_BORDER_REPLICATE) c.w1 = __byte_perm(c.w0, 0u, 0x3333);
+                else c.z1 = true;
+            } else {
+                c.w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
+                c.w1 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 + 4));
+            }
+        }
+        return c;
+    };
+    IdxChunk cur = fetch(tid);
     __syncthreads();
 
-    // ---- CLAHE output of the haloed tile: item = (row r, 8-column chunk u); chunk u = image
-    //      columns gx0 .. gx0+7 with gx0 = tx0 - 4 + 8u (4-byte aligned)
-    const uint8_t* iplane = a.idx + n * (int64_t)h * w;
     for (int i = tid; i < E * 9; i += kFastThreads) {
+        IdxChunk nxt = cur;
+        if (i + kFastThreads < E * 9) nxt = fetch(i + kFastThreads);
         const int u = i % 9, r = i / 9;
-        const int sy = border_index(ty0 - R + r, h, a.border);
         float4 lo4 = make_float4(0.f, 0.f, 0.f, 0.f), hi4 = lo4;
-        if (sy >= 0) {
+        if (cur.sy >= 0) {
             const float wyv = s_w[r];
-            const uint32_t* cell = s_cell + ((sy >= ty0 + kTile / 2) ? 2 * kBins : 0);
-            const uint8_t* irow = iplane + (int64_t)sy * w;
-            const int gx0 = tx0 - 4 + 8 * u;
-            uint32_t w0, w1;
-            bool z0 = false, z1 = false;
-            if (gx0 < 0) {  // columns -4..-1 mirror onto 4,3,2,1
-                w1 = __ldg(reinterpret_cast<const uint32_t*>(irow));
-                if (a.border == MIE_BORDER_REFLECT)
-                    w0 = __byte_perm(w1, __ldg(reinterpret_cast<const uint32_t*>(irow + 4)), 0x1234);
-                else if (a.border == MIE_BORDER_REPLICATE) w0 = __byte_perm(w1, 0u, 0x0000);
-                else { w0 = 0u; z0 = true; }
-            } else if (gx0 + 8 > w) {  // columns w..w+3 mirror onto w-2..w-5
-                w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
-                if (a.border == MIE_BORDER_REFLECT)
-                    w1 = __byte_perm(w0, __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 - 4)), 0x7012);
-                else if (a.border == MIE_BORDER_REPLICATE) w1 = __byte_perm(w0, 0u, 0x3333);
-                else { w1 = 0u; z1 = true; }
-            } else {
-                w0 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0));
-                w1 = __ldg(reinterpret_cast<const uint32_t*>(irow + gx0 + 4));
-            }
-            // the cell column flips between haloed columns 35 and 36 (source column tx0 + 32)
-            const uint32_t* cellL = cell + (u >= 5 ? kBins : 0);
-            const uint32_t* cellH = cell + (u >= 4 ? kBins : 0);
+            // cell number (row cell * 2 + column cell) goes into byte 1 of the table index; the
+            // column cell flips between haloed columns 35 and 36 (source column tx0 + 32)
+            const uint32_t ca = (cur.sy >= ty0 + kTile / 2) ? 2u : 0u;
+            const uint32_t cL = ca + (u >= 5 ? 1u : 0u), cH = ca + (u >= 4 ? 1u : 0u);
+            const uint32_t w0 = cur.w0, w1 = cur.w1;
             const float4 wa = *reinterpret_cast<const float4*>(s_w + 8 * u);
             const float4 wb = *reinterpret_cast<const float4*>(s_w + 8 * u + 4);
-            lo4.x = clahe_px(cellL[__byte_perm(w0, 0u, 0x4440)], wa.x, wyv);
-            lo4.y = clahe_px(cellL[__byte_perm(w0, 0u, 0x4441)], wa.y, wyv);
-            lo4.z = clahe_px(cellL[__byte_perm(w0, 0u, 0x4442)], wa.z, wyv);
-            lo4.w = clahe_px(cellL[__byte_perm(w0, 0u, 0x4443)], wa.w, wyv);
-            hi4.x = clahe_px(cellH[__byte_perm(w1, 0u, 0x4440)], wb.x, wyv);
-            hi4.y = clahe_px(cellH[__byte_perm(w1, 0u, 0x4441)], wb.y, wyv);
-            hi4.z = clahe_px(cellH[__byte_perm(w1, 0u, 0x4442)], wb.z, wyv);
-            hi4.w = clahe_px(cellH[__byte_perm(w1, 0u, 0x4443)], wb.w, wyv);
-            if (z0) lo4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (z1) hi4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            lo4.x = clahe_px(s_cell[__byte_perm(w0, cL, 0x7640)], wa.x, wyv);
+            lo4.y = clahe_px(s_cell[__byte_perm(w0, cL, 0x7641)], wa.y, wyv);
+            lo4.z = clahe_px(s_cell[__byte_perm(w0, cL, 0x7642)], wa.z, wyv);
+            lo4.w = clahe_px(s_cell[__byte_perm(w0, cL, 0x7643)], wa.w, wyv);
+            hi4.x = clahe_px(s_cell[__byte_perm(w1, cH, 0x7640)], wb.x, wyv);
+            hi4.y = clahe_px(s_cell[__byte_perm(w1, cH, 0x7641)], wb.y, wyv);
+            hi4.z = clahe_px(s_cell[__byte_perm(w1, cH, 0x7642)], wb.z, wyv);
+            hi4.w = clahe_px(s_cell[__byte_perm(w1, cH, 0x7643)], wb.w, wyv);
+            if (cur.z0) lo4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (cur.z1) hi4 = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float* dstp = s_in + r * PIN + 8 * u;
         *reinterpret_cast<float4*>(dstp) = lo4;
         *reinterpret_cast<float4*>(dstp + 4) = hi4;
+        cur = nxt;
     }
     __syncthreads();
 
@@ -324,20 +349,25 @@ int launch_chain_a_fast(const ChainAArgs& a, int sd, const Taps& wx, const Taps&
     return MIE_OK;
 }
 
-size_t chain_cells_bytes(int64_t n, int gh, int gw) { return (size_t)n * (gh + 1) * (gw + 1) * kBins * 4; }
+size_t chain_cells_bytes(int64_t n, int gh, int gw) { return (size_t)n * (gh + 1) * (gw + 1) * kBins * 8; }
 
 template <typename DstT>
-static int launch_b_t(const ChainBArgs& b, const uint32_t* cells, const AxisWeights& aw, const Taps& wx,
+static int launch_b_t(const ChainBArgs& b, const uint2* cells, const AxisWeights& aw, const Taps& wx,
                       const Taps& wy, unsigned blocks, cudaStream_t st) {
-    chain_b_fast_kernel<DstT><<<blocks, kFastThreads, 0, st>>>(b, cells, aw, wx, wy);
+    constexpr int E = kTile + 8;
+    constexpr size_t smem = (size_t)(E * TileSmem<4>::pin + E * kPMid + E) * 4;
+    static_assert(E * kPMid * 4 >= 4 * kBins * 8, "cell tables must fit in the s_mid region");
+    MIE_ENSURE_SMEM((chain_b_fast_kernel<DstT>), smem);
+    chain_b_fast_kernel<DstT><<<blocks, kFastThreads, smem, st>>>(b, cells, aw, wx, wy);
     return check_launch();
 }
 
 // Runs the cell-packing launch and the tuned chain_b (9-tap unsharp only).  `cells` must hold
 // chain_cells_bytes(n, gh, gw) bytes.
-int launch_chain_b_fast(const ChainBArgs& b, int dd, uint32_t* cells, const Taps& wx, const Taps& wy, int64_t n,
+int launch_chain_b_fast(const ChainBArgs& b, int dd, void* cells_raw, const Taps& wx, const Taps& wy, int64_t n,
                         cudaStream_t st) {
     if (n > 65535) return MIE_E_SHAPE;
+    uint2* cells = (uint2*)cells_raw;
     dim3 pgrid((unsigned)(b.g.gw + 1), (unsigned)(b.g.gh + 1), (unsigned)n);
     chain_pack_cells_kernel<<<pgrid, 256, 0, st>>>(b.luts, cells, b.g.gh, b.g.gw);
     int rc = check_launch();

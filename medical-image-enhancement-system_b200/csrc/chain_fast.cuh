@@ -57,7 +57,7 @@ bool fast_chain_ok(const ClaheGeom& g, int src_dtype, int dst_dtype, const void*
 int launch_chain_a_fast(const ChainAArgs& a, int src_dtype, const Taps& wx, const Taps& wy, int R, int64_t n,
                         cudaStream_t st);
 size_t chain_cells_bytes(int64_t n, int gh, int gw);
-int launch_chain_b_fast(const ChainBArgs& b, int dst_dtype, uint32_t* cells, const Taps& wx, const Taps& wy,
+int launch_chain_b_fast(const ChainBArgs& b, int dst_dtype, void* cells, const Taps& wx, const Taps& wy,
                         int64_t n, cudaStream_t st);
 
 // low bytes of four words -> one word (3 PRMT)
