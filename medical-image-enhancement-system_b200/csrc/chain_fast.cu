@@ -1,43 +1,9 @@
 // chain_fast.cu — tuned kernels of the fused Gaussian -> CLAHE -> unsharp chain for
 // 64x64-pixel CLAHE tiles (see chain_fast.cuh for the instruction-level tricks and
 // chain.cu for the algorithm and the generic kernels these two must equal bit for bit).
-#include <cuda_fp16.h>
-
 #include "chain_fast.cuh"
 
 namespace mie {
-
-// 24 converted pixels x[0..23] = image columns c0-4 .. c0+19 of one row (16 outputs + halo 4);
-// columns outside the image (left edge: c0 == 0, right edge: c0 + 16 == w) are filled from the
-// registers already loaded, so edge tiles cost no extra loads.
-template <typename SrcT>
-__device__ __forceinline__ void load_row24(const SrcT* row, int c0, int w, int border, float* x) {
-    Fast<SrcT>::load8(row + c0, x + 4);
-    Fast<SrcT>::load8(row + c0 + 8, x + 12);
-    if (c0 != 0) {
-        Fast<SrcT>::load4(row + c0 - 4, x);
-    } else if (border == MIE_BORDER_REFLECT) {
-        x[0] = x[8]; x[1] = x[7]; x[2] = x[6]; x[3] = x[5];
-    } else {
-        const float e = border == MIE_BORDER_REPLICATE ? x[4] : 0.0f;
-        x[0] = e; x[1] = e; x[2] = e; x[3] = e;
-    }
-    if (c0 + 16 != w) {
-        Fast<SrcT>::load4(row + c0 + 16, x + 20);
-    } else if (border == MIE_BORDER_REFLECT) {
-        x[20] = x[18]; x[21] = x[17]; x[22] = x[16]; x[23] = x[15];
-    } else {
-        const float e = border == MIE_BORDER_REPLICATE ? x[19] : 0.0f;
-        x[20] = e; x[21] = e; x[22] = e; x[23] = e;
-    }
-}
-
-// s_mid row layout of the tuned chain_a kernel: the 16 column quads of a row are stored even quads
-// first (quad q at word 4*(q/2)), odd quads from word 48 (4*(12 + q/2)), rows 84 words apart.  With
-// it, the row pass (4 lanes of a row x 2 rows per quarter-warp, STS.128 each) and the column pass
-// (8 lanes of a row per quarter-warp, LDS.128 each) both touch 32 distinct banks.
-constexpr int kPMa = 84;
-__device__ __forceinline__ int quad_off(int q) { return 4 * ((q >> 1) + ((q & 1) ? 12 : 0)); }
 
 // ================================================================ chain_a (fast)
 // One block (9 warps) per CLAHE tile:
@@ -146,23 +112,6 @@ chain_pack_cells_kernel(const uint8_t* __restrict__ luts, uint2* __restrict__ ce
 //   tables : the block's four 1 KB cell tables -> shared memory (one 16-byte copy per thread);
 //   C pass : CLAHE output C for every haloed pixel -> s_in;
 //   row / col pass, epilogue: C + (C - blur(C)) -> quantise -> 64-bit stores.
-
-// CLAHE output of one pixel from its cell-table entry e = fp16 (tl - tr, tr | bl - br, br):
-// t = tr + wx (tl - tr); b = br + wx (bl - br); out = (b + wy (t - b)) / 255, one fma per lerp.
-__device__ __forceinline__ float clahe_px(uint2 e, float wxv, float wyv) {
-    const float2 top = __half22float2(*reinterpret_cast<const __half2*>(&e.x));
-    const float2 bot = __half22float2(*reinterpret_cast<const __half2*>(&e.y));
-    const float t = __fmaf_rn(wxv, top.x, top.y);
-    const float b = __fmaf_rn(wxv, bot.x, bot.y);
-    return div255(__fmaf_rn(wyv, __fsub_rn(t, b), b));
-}
-
-// Interpolation weight of the upper / left tile for haloed index k (tile position p = k - 4):
-// kornia_axis() of any pixel at that position, identical for every interior tile; in the border
-// half-tiles both neighbours are the same tile, so the value there is irrelevant.
-struct AxisWeights {
-    float w[kTile + 8];
-};
 
 template <typename DstT>
 __global__ void __launch_bounds__(kFastThreads)
@@ -349,6 +298,13 @@ int launch_chain_a_fast(const ChainAArgs& a, int sd, const Taps& wx, const Taps&
     return MIE_OK;
 }
 
+int launch_pack_cells(const uint8_t* luts, void* cells, int64_t n, int gh, int gw, cudaStream_t st) {
+    if (n > 65535) return MIE_E_SHAPE;
+    dim3 pgrid((unsigned)(gw + 1), (unsigned)(gh + 1), (unsigned)n);
+    chain_pack_cells_kernel<<<pgrid, 256, 0, st>>>(luts, (uint2*)cells, gh, gw);
+    return check_launch();
+}
+
 size_t chain_cells_bytes(int64_t n, int gh, int gw) { return (size_t)n * (gh + 1) * (gw + 1) * kBins * 8; }
 
 template <typename DstT>
@@ -366,11 +322,8 @@ static int launch_b_t(const ChainBArgs& b, const uint2* cells, const AxisWeights
 // chain_cells_bytes(n, gh, gw) bytes.
 int launch_chain_b_fast(const ChainBArgs& b, int dd, void* cells_raw, const Taps& wx, const Taps& wy, int64_t n,
                         cudaStream_t st) {
-    if (n > 65535) return MIE_E_SHAPE;
     uint2* cells = (uint2*)cells_raw;
-    dim3 pgrid((unsigned)(b.g.gw + 1), (unsigned)(b.g.gh + 1), (unsigned)n);
-    chain_pack_cells_kernel<<<pgrid, 256, 0, st>>>(b.luts, cells, b.g.gh, b.g.gw);
-    int rc = check_launch();
+    int rc = launch_pack_cells(b.luts, cells, n, b.g.gh, b.g.gw, st);
     if (rc) return rc;
     AxisWeights aw;
     for (int k = 0; k < kTile + 8; ++k) {

@@ -20,6 +20,8 @@
 //     32-bit word per grey level, so a pixel needs ONE shared-memory lookup.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "clahe.cuh"
 #include "stencil.cuh"
 
@@ -57,6 +59,8 @@ bool fast_chain_ok(const ClaheGeom& g, int src_dtype, int dst_dtype, const void*
 int launch_chain_a_fast(const ChainAArgs& a, int src_dtype, const Taps& wx, const Taps& wy, int R, int64_t n,
                         cudaStream_t st);
 size_t chain_cells_bytes(int64_t n, int gh, int gw);
+// cells[n][gh+1][gw+1][256] (8 bytes each) from luts[n][gh][gw][256]; see chain_fast.cu
+int launch_pack_cells(const uint8_t* luts, void* cells, int64_t n, int gh, int gw, cudaStream_t st);
 int launch_chain_b_fast(const ChainBArgs& b, int dst_dtype, void* cells, const Taps& wx, const Taps& wy,
                         int64_t n, cudaStream_t st);
 
@@ -263,5 +267,54 @@ __device__ __forceinline__ void warp_build_lut(const int* s_tot, const LutParams
     }
     *reinterpret_cast<uint2*>(lut_out + 8 * lane) = make_uint2(w0, w1);
 }
+
+// 24 converted pixels x[0..23] = image columns c0-4 .. c0+19 of one row (16 outputs + halo 4);
+// columns outside the image (left edge: c0 == 0, right edge: c0 + 16 == w) are filled from the
+// registers already loaded, so edge tiles cost no extra loads.
+template <typename SrcT>
+__device__ __forceinline__ void load_row24(const SrcT* row, int c0, int w, int border, float* x) {
+    Fast<SrcT>::load8(row + c0, x + 4);
+    Fast<SrcT>::load8(row + c0 + 8, x + 12);
+    if (c0 != 0) {
+        Fast<SrcT>::load4(row + c0 - 4, x);
+    } else if (border == MIE_BORDER_REFLECT) {
+        x[0] = x[8]; x[1] = x[7]; x[2] = x[6]; x[3] = x[5];
+    } else {
+        const float e = border == MIE_BORDER_REPLICATE ? x[4] : 0.0f;
+        x[0] = e; x[1] = e; x[2] = e; x[3] = e;
+    }
+    if (c0 + 16 != w) {
+        Fast<SrcT>::load4(row + c0 + 16, x + 20);
+    } else if (border == MIE_BORDER_REFLECT) {
+        x[20] = x[18]; x[21] = x[17]; x[22] = x[16]; x[23] = x[15];
+    } else {
+        const float e = border == MIE_BORDER_REPLICATE ? x[19] : 0.0f;
+        x[20] = e; x[21] = e; x[22] = e; x[23] = e;
+    }
+}
+
+// s_mid row layout of the tuned chain_a kernel: the 16 column quads of a row are stored even quads
+// first (quad q at word 4*(q/2)), odd quads from word 48 (4*(12 + q/2)), rows 84 words apart.  With
+// it, the row pass (4 lanes of a row x 2 rows per quarter-warp, STS.128 each) and the column pass
+// (8 lanes of a row per quarter-warp, LDS.128 each) both touch 32 distinct banks.
+constexpr int kPMa = 84;
+__device__ __forceinline__ int quad_off(int q) { return 4 * ((q >> 1) + ((q & 1) ? 12 : 0)); }
+
+// CLAHE output of one pixel from its cell-table entry e = fp16 (tl - tr, tr | bl - br, br):
+// t = tr + wx (tl - tr); b = br + wx (bl - br); out = (b + wy (t - b)) / 255, one fma per lerp.
+__device__ __forceinline__ float clahe_px(uint2 e, float wxv, float wyv) {
+    const float2 top = __half22float2(*reinterpret_cast<const __half2*>(&e.x));
+    const float2 bot = __half22float2(*reinterpret_cast<const __half2*>(&e.y));
+    const float t = __fmaf_rn(wxv, top.x, top.y);
+    const float b = __fmaf_rn(wxv, bot.x, bot.y);
+    return div255(__fmaf_rn(wyv, __fsub_rn(t, b), b));
+}
+
+// Interpolation weight of the upper / left tile for haloed index k (tile position p = k - 4):
+// kornia_axis() of any pixel at that position, identical for every interior tile; in the border
+// half-tiles both neighbours are the same tile, so the value there is irrelevant.
+struct AxisWeights {
+    float w[kTile + 8];
+};
 
 }  // namespace mie
