@@ -14,6 +14,8 @@
 // intermediates bit for bit (same operation order; tests/test_chain_gpu.py).
 // Shapes the fused kernels do not cover (CLAHE padding needed, tiles > 64 px,
 // non-square or > 9-tap kernels) run those three stages unfused.
+#include <cstdlib>
+
 #include "chain_fast.cuh"
 
 namespace mie {
@@ -220,6 +222,13 @@ static int launch_b(const ChainBArgs& a, const Taps& wx, const Taps& wy, int64_t
     return check_launch();
 }
 
+// Test / benchmark hook: 1 = keep the tiled tuned kernels even where the marching kernels apply
+// (MIE_CHAIN_NO_MARCH=1 in the environment; read once).
+static const bool g_disable_march = [] {
+    const char* e = getenv("MIE_CHAIN_NO_MARCH");
+    return e && e[0] == '1';
+}();
+
 static void fill_taps(Taps& t, const float* w, int k) {
     for (int i = 0; i < MIE_MAX_TAPS; ++i) t.w[i] = i < k ? w[i] : 0.f;
 }
@@ -308,8 +317,10 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     b.lo = lo; b.rg = hi - lo;
     if (n * (int64_t)b.tiles_x * b.tiles_y > 2147483647LL) return MIE_E_SHAPE;
     if (fast) {
+        const bool march = march_chain_ok(g, kgx, kux) && !g_disable_march;
         if (stages & MIE_CHAIN_STAGE_A) {
-            rc = launch_chain_a_fast(a, src_dtype, tgx, tgy, kgx / 2, n, st);
+            rc = march ? launch_chain_a_march(a, src_dtype, tgx, tgy, n, st)
+                       : launch_chain_a_fast(a, src_dtype, tgx, tgy, kgx / 2, n, st);
             if (rc) return rc;
         }
         if (!(stages & MIE_CHAIN_STAGE_B)) return MIE_OK;
@@ -318,7 +329,8 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
             // 2 (gh+1)(gw+1) KB <= 3 bytes per pixel for 64x64-pixel tiles)
             size_t off = ((size_t)n * gh * gw * kBins + (size_t)n * h * w + 255) & ~(size_t)255;
             if (off + chain_cells_bytes(n, gh, gw) > workspace_bytes) return MIE_E_WORKSPACE;
-            return launch_chain_b_fast(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st);
+            return march ? launch_chain_b_march(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st)
+                         : launch_chain_b_fast(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st);
         }
         stages = MIE_CHAIN_STAGE_B;  // other unsharp sizes: generic chain_b on the same index plane / LUTs
     }

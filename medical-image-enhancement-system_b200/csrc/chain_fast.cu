@@ -86,8 +86,8 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
 // ================================================================ cell tables
 // Interpolation cell (cy, cx), cy in [0, gh], cx in [0, gw], is the region between the centres of
 // tiles (cy-1, cx-1) .. (cy, cx) (clamped at the image border).  For every grey level the cell table
-// holds what the blend needs, ready to use: (tl - tr, tr, bl - br, br) as four fp16 values (integers
-// of magnitude <= 255 are exact in fp16), 8 bytes per grey level, 2 KB per cell.  chain_b then needs
+// holds what the blend needs, ready to use: (tl - tr, tr, bl - br, br) as four half-width floats (see
+// cell_word), 8 bytes per grey level, 2 KB per cell.  chain_b then needs
 // ONE 64-bit shared-memory load per pixel and no integer unpacking.  A tiny launch between chain_a
 // and chain_b.
 __global__ void __launch_bounds__(256)
@@ -98,11 +98,9 @@ chain_pack_cells_kernel(const uint8_t* __restrict__ luts, uint2* __restrict__ ce
     const uint8_t* nl = luts + n * (int64_t)gh * gw * kBins + threadIdx.x;
     const int tl = nl[(jt * gw + il) * kBins], tr = nl[(jt * gw + ir) * kBins];
     const int bl = nl[(jb * gw + il) * kBins], br = nl[(jb * gw + ir) * kBins];
-    const __half2 top = __floats2half2_rn((float)(tl - tr), (float)tr);
-    const __half2 bot = __floats2half2_rn((float)(bl - br), (float)br);
     uint2 e;
-    e.x = *reinterpret_cast<const uint32_t*>(&top);
-    e.y = *reinterpret_cast<const uint32_t*>(&bot);
+    e.x = cell_word(tl - tr, tr);
+    e.y = cell_word(bl - br, br);
     cells[((n * (gh + 1) + cy) * (int64_t)(gw + 1) + cx) * kBins + threadIdx.x] = e;
 }
 
@@ -326,11 +324,7 @@ int launch_chain_b_fast(const ChainBArgs& b, int dd, void* cells_raw, const Taps
     int rc = launch_pack_cells(b.luts, cells, n, b.g.gh, b.g.gw, st);
     if (rc) return rc;
     AxisWeights aw;
-    for (int k = 0; k < kTile + 8; ++k) {
-        const int p = k - 4;                              // position relative to the tile origin
-        const int r = p < kTile / 2 ? p + kTile / 2 : p - kTile / 2;  // offset from the previous tile centre
-        aw.w[k] = (float)(kTile - 1 - r) / (float)(kTile - 1);
-    }
+    fill_axis_weights(aw);
     const unsigned blocks = (unsigned)(n * b.tiles_x * b.tiles_y);
     MIE_DISPATCH_SRC(dd, return launch_b_t<SrcT>(b, cells, aw, wx, wy, blocks, st));
     return MIE_OK;

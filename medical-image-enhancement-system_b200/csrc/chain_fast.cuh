@@ -89,6 +89,11 @@ struct Fast<uint16_t> {
         const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
         cvt2(a.x, x); cvt2(a.y, x + 2);
     }
+    // split form of load4 (the marching kernels issue the load rows ahead of the conversion)
+    typedef uint2 raw4;
+    static __device__ __forceinline__ raw4 ldg4(const uint16_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+    static __device__ __forceinline__ raw4 zero4() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ void cvt_raw4(raw4 a, float* x) { cvt2(a.x, x); cvt2(a.y, x + 2); }
     static __device__ __forceinline__ void load8(const uint16_t* p, float* x) {  // p 16-byte aligned
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(p));
         cvt2(b.x, x); cvt2(b.y, x + 2); cvt2(b.z, x + 4); cvt2(b.w, x + 6);
@@ -114,6 +119,12 @@ struct Fast<int16_t> {
     static __device__ __forceinline__ void load4(const int16_t* p, float* x) {
         const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
         Fast<uint16_t>::cvt2(a.x ^ 0x80008000u, x); Fast<uint16_t>::cvt2(a.y ^ 0x80008000u, x + 2);  // v + 32768
+    }
+    typedef uint2 raw4;
+    static __device__ __forceinline__ raw4 ldg4(const int16_t* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+    static __device__ __forceinline__ raw4 zero4() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ void cvt_raw4(raw4 a, float* x) {
+        Fast<uint16_t>::cvt2(a.x ^ 0x80008000u, x); Fast<uint16_t>::cvt2(a.y ^ 0x80008000u, x + 2);
     }
     static __device__ __forceinline__ void load8(const int16_t* p, float* x) {
         const uint4 b = __ldg(reinterpret_cast<const uint4*>(p));
@@ -145,6 +156,10 @@ struct Fast<uint8_t> {
     static __device__ __forceinline__ void load4(const uint8_t* p, float* x) {  // p 4-byte aligned
         cvt4(__ldg(reinterpret_cast<const uint32_t*>(p)), x);
     }
+    typedef uint32_t raw4;
+    static __device__ __forceinline__ raw4 ldg4(const uint8_t* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+    static __device__ __forceinline__ raw4 zero4() { return 0u; }
+    static __device__ __forceinline__ void cvt_raw4(raw4 a, float* x) { cvt4(a, x); }
     static __device__ __forceinline__ void load8(const uint8_t* p, float* x) {  // p 8-byte aligned
         const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
         cvt4(b.x, x); cvt4(b.y, x + 4);
@@ -168,6 +183,10 @@ struct Fast<float> {
     static __device__ __forceinline__ void load8(const float* p, float* x) {
         load4(p, x); load4(p + 4, x + 4);
     }
+    typedef float4 raw4;
+    static __device__ __forceinline__ raw4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    static __device__ __forceinline__ raw4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ void cvt_raw4(raw4 v, float* x) { x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
     static __device__ __forceinline__ void store4(float* p, const float* y) {
         *reinterpret_cast<float4*>(p) = make_float4(y[0], y[1], y[2], y[3]);
     }
@@ -229,14 +248,35 @@ __device__ __forceinline__ void hist_add(int* s_h, int bin) {
 // Branch-free form for histograms with a dummy slot (bin from fast_bin, always in range).
 __device__ __forceinline__ void hist_add_nobranch(int* s_h, int bin) { atomicAdd(&s_h[bin], 1); }
 
+// Histogram increment for values proven to lie in [0, 1] (integer pixels blurred with weights whose
+// fp32 sum, accumulated in kernel order, does not exceed 1: gauss_of_ones_le1 on the host).  Then
+// floor(g*256) is in [0, 256] with 256 <=> g == 1.0, which torch.histc counts in the last bin: slot 256
+// is merged into bin 255 when the LUT is built (warp_build_lut<true>).  Three instructions per pixel:
+// FFMA.RM (mantissa of g*256 + 2^23 rounded down = the bin), LEA (bin*4 + base) and ATOMS.POPC.INC.
+// hist_base32 = shared-window address of slot 0 minus 4 * 0x4B000000 (mod 2^32).
+__device__ __forceinline__ uint32_t hist_base32(const int* s_h) {
+    return (uint32_t)__cvta_generic_to_shared(s_h) - (0x4B000000u << 2);
+}
+__device__ __forceinline__ void hist_add_le1(uint32_t base32, float g) {
+    const uint32_t addr = base32 + (__float_as_uint(__fmaf_rd(g, 256.0f, 8388608.0f)) << 2);
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+// Bit pattern whose low byte is trunc(g*255) for g in [0, 1].
+__device__ __forceinline__ uint32_t fast_idx_bits_le1(float g) {
+    return __float_as_uint(__fadd_rd(__fmul_rn(g, 255.0f), 8388608.0f));
+}
+
 // Clip / redistribute / cumulate -> 256 LUT bytes, computed by ONE warp from the
 // block-total histogram in shared memory (lane L owns bins 8L..8L+7).
+// MERGE256: slot 256 holds pixels whose value is exactly 1.0 (see hist_add_le1) and belongs to bin 255.
+template <bool MERGE256 = false>
 __device__ __forceinline__ void warp_build_lut(const int* s_tot, const LutParams& p, uint8_t* lut_out, int lane) {
     int hv[8];
     {
         const int4 a = *reinterpret_cast<const int4*>(s_tot + 8 * lane);
         const int4 b = *reinterpret_cast<const int4*>(s_tot + 8 * lane + 4);
         hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
+        if (MERGE256 && lane == 31) hv[7] += s_tot[256];
     }
     if (p.clip > 0) {
         int local = 0;
@@ -300,13 +340,20 @@ __device__ __forceinline__ void load_row24(const SrcT* row, int c0, int w, int b
 constexpr int kPMa = 84;
 __device__ __forceinline__ int quad_off(int q) { return 4 * ((q >> 1) + ((q & 1) ? 12 : 0)); }
 
-// CLAHE output of one pixel from its cell-table entry e = fp16 (tl - tr, tr | bl - br, br):
+// Cell-table entry: four integers of magnitude <= 255 stored as the UPPER 16 bits of their fp32
+// encodings (exact: 8 significant bits), e.x = hi16(tl - tr) | hi16(tr) << 16, e.y the same for the
+// bottom pair.  Decoding is one PRMT / LOP3 per value on the integer pipe (an fp16 table would cost
+// one HADD2.F32 per value on the FMA pipe, which is the busier one).
+__device__ __forceinline__ uint32_t cell_word(int diff, int base) {
+    return (__float_as_uint((float)diff) >> 16) | (__float_as_uint((float)base) & 0xFFFF0000u);
+}
+// CLAHE output of one pixel from its cell-table entry:
 // t = tr + wx (tl - tr); b = br + wx (bl - br); out = (b + wy (t - b)) / 255, one fma per lerp.
 __device__ __forceinline__ float clahe_px(uint2 e, float wxv, float wyv) {
-    const float2 top = __half22float2(*reinterpret_cast<const __half2*>(&e.x));
-    const float2 bot = __half22float2(*reinterpret_cast<const __half2*>(&e.y));
-    const float t = __fmaf_rn(wxv, top.x, top.y);
-    const float b = __fmaf_rn(wxv, bot.x, bot.y);
+    const float dt = __uint_as_float(__byte_perm(e.x, 0u, 0x1044)), tr = __uint_as_float(e.x & 0xFFFF0000u);
+    const float db = __uint_as_float(__byte_perm(e.y, 0u, 0x1044)), br = __uint_as_float(e.y & 0xFFFF0000u);
+    const float t = __fmaf_rn(wxv, dt, tr);
+    const float b = __fmaf_rn(wxv, db, br);
     return div255(__fmaf_rn(wyv, __fsub_rn(t, b), b));
 }
 
@@ -316,5 +363,19 @@ __device__ __forceinline__ float clahe_px(uint2 e, float wxv, float wyv) {
 struct AxisWeights {
     float w[kTile + 8];
 };
+inline void fill_axis_weights(AxisWeights& aw) {
+    for (int k = 0; k < kTile + 8; ++k) {
+        const int p = k - 4;                                          // position relative to the tile origin
+        const int r = p < kTile / 2 ? p + kTile / 2 : p - kTile / 2;  // offset from the previous tile centre
+        aw.w[k] = (float)(kTile - 1 - r) / (float)(kTile - 1);
+    }
+}
+
+// Marching kernels (chain_march.cu): full-width 64-row bands, 9-tap Gaussians, W % 128 == 0, W <= 1024.
+bool march_chain_ok(const ClaheGeom& g, int kg, int ku);
+int launch_chain_a_march(const ChainAArgs& a, int src_dtype, const Taps& wx, const Taps& wy, int64_t n,
+                         cudaStream_t st);
+int launch_chain_b_march(const ChainBArgs& b, int dst_dtype, void* cells, const Taps& wx, const Taps& wy, int64_t n,
+                         cudaStream_t st);
 
 }  // namespace mie

@@ -1,0 +1,371 @@
+// chain_march.cu — "marching" kernels of the fused Gaussian -> CLAHE -> unsharp chain for the
+// headline geometry (BASELINE.json config 2: 64x64-pixel CLAHE tiles, 9-tap Gaussians, image width a
+// multiple of 128 and <= 1024).  Same arithmetic, bit for bit, as chain.cu / chain_fast.cu and
+// oracle/mie_oracle.c; what changes is the schedule:
+//
+//   * one block owns a full-width band of 64 rows (one row of CLAHE tiles) and walks down its
+//     64 + 8 source rows; thread t owns image columns 4t .. 4t+3 for the whole walk;
+//   * a row is converted (chain_a) / CLAHE-blended (chain_b) exactly once per band and exchanged
+//     through a small ring of row buffers in shared memory — one STS.128 and three LDS.128 per
+//     thread and row; the image-border halo comes from two warp shuffles, not from extra loads;
+//   * the vertical pass never touches shared memory: the last nine horizontally filtered rows of the
+//     thread's four columns live in registers (the walk is unrolled by nine so that the ring is
+//     addressed statically) and feed packed fma.rn.f32x2;
+//   * nothing is computed for a horizontal halo, and only 8 of 72 rows are vertical halo, so the
+//     per-pixel work is 1.125x the arithmetic minimum (the tiled kernels: 1.27x-1.7x), and the
+//     shared-memory traffic drops from ~45 to ~24 bytes per pixel;
+//   * global loads (4 pixels / 4 index bytes per thread and row) are issued two rows ahead.
+#include "chain_fast.cuh"
+
+namespace mie {
+
+constexpr int kMR = 4;                    // 9-tap kernels
+constexpr int kMRows = kTile + 2 * kMR;   // source rows per band
+constexpr int kMRing = 2 * kMR + 1;       // register ring depth == unroll factor
+constexpr int kHistPitch = 264;           // 257 slots (256 = ignored pixels), padded to a multiple of 8
+
+// Source row of band row r (|overshoot| <= 6 < h, so one reflection suffices): branch-free, on the
+// uniform datapath.  -1 = outside the image with a constant border.
+template <int BORDER>
+__device__ __forceinline__ int march_src_row(int r, int h) {
+    if (BORDER == MIE_BORDER_REFLECT) {
+        const int m = abs(r);
+        return min(m, 2 * (h - 1) - m);
+    }
+    if (BORDER == MIE_BORDER_REPLICATE) return min(max(r, 0), h - 1);
+    return (unsigned)r < (unsigned)h ? r : -1;
+}
+
+// Image-border halo of a row buffer: rowbuf[0..3] (left) and [4+W .. 4+W+3] (right) from the four
+// pixels of the first / last thread and one value of their neighbour lane.
+template <int BORDER>
+__device__ __forceinline__ void march_halo(float* rowbuf, const float* x, int W, bool first_warp, bool last_warp,
+                                           int tid, int T) {
+    if (first_warp) {
+        float nb = 0.f;
+        if (BORDER == MIE_BORDER_REFLECT) nb = __shfl_down_sync(0xffffffffu, x[0], 1);  // column 4 -> thread 0
+        if (tid == 0) {
+            float4 hl;
+            if (BORDER == MIE_BORDER_REFLECT) hl = make_float4(nb, x[3], x[2], x[1]);
+            else if (BORDER == MIE_BORDER_REPLICATE) hl = make_float4(x[0], x[0], x[0], x[0]);
+            else hl = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(rowbuf) = hl;
+        }
+    }
+    if (last_warp) {
+        float nb = 0.f;
+        if (BORDER == MIE_BORDER_REFLECT) nb = __shfl_up_sync(0xffffffffu, x[3], 1);  // column W-5 -> last thread
+        if (tid == T - 1) {
+            float4 hr;
+            if (BORDER == MIE_BORDER_REFLECT) hr = make_float4(x[2], x[1], x[0], nb);
+            else if (BORDER == MIE_BORDER_REPLICATE) hr = make_float4(x[3], x[3], x[3], x[3]);
+            else hr = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(rowbuf + 4 + W) = hr;
+        }
+    }
+}
+
+// Horizontal 9-tap pass for the thread's four columns out of the row buffer (columns 4t-4 .. 4t+7).
+__device__ __forceinline__ void march_row_pass(const float* rowbuf, int tid, const Taps& wx, float2& m01, float2& m23) {
+    const float4* p = reinterpret_cast<const float4*>(rowbuf + 4 * tid);
+    const float4 a = p[0], b = p[1], c = p[2];
+    const float win[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float acc = __fmul_rn(wx.w[0], win[j]);
+#pragma unroll
+        for (int t = 1; t <= 2 * kMR; ++t) acc = __fmaf_rn(wx.w[t], win[j + t], acc);
+        o[j] = acc;
+    }
+    m01 = make_float2(o[0], o[1]);
+    m23 = make_float2(o[2], o[3]);
+}
+
+// Vertical 9-tap pass out of the register ring; OLDEST = ring slot of the topmost tap (a constant
+// after unrolling, so the ring stays in registers).
+__device__ __forceinline__ void march_col_pass(const float2 (&ring)[kMRing][2], const int OLDEST, const Taps& wy,
+                                               float* g) {
+    const float2 w0 = make_float2(wy.w[0], wy.w[0]);
+    float2 a = __fmul2_rn(w0, ring[OLDEST][0]);
+    float2 b = __fmul2_rn(w0, ring[OLDEST][1]);
+#pragma unroll
+    for (int t = 1; t <= 2 * kMR; ++t) {
+        const float2 wt = make_float2(wy.w[t], wy.w[t]);
+        a = __ffma2_rn(wt, ring[(OLDEST + t) % kMRing][0], a);
+        b = __ffma2_rn(wt, ring[(OLDEST + t) % kMRing][1], b);
+    }
+    g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
+}
+
+struct TrueC { static constexpr bool value = true; };
+struct FalseC { static constexpr bool value = false; };
+
+// ================================================================ chain_a (marching)
+// grid = n * gh blocks of W/4 threads.  Per source row: load (two rows ahead) -> convert -> row
+// buffer -> horizontal pass -> register ring -> vertical pass -> lookup index (32-bit store into the
+// index plane) and histogram bin (ATOMS.POPC.INC into the thread's tile histogram).  After the walk
+// each warp turns tile histograms into LUTs.  The first nine rows (which emit one output row) are a
+// separate copy of the loop body, so the steady state carries no "is there an output yet" test.
+// LE1: the host has proven that every blurred value lies in [0, 1] (integer pixels and
+// gauss_of_ones_le1), which removes the range tests from the index / bin rules.
+template <typename SrcT, int BORDER, bool LE1>
+__global__ void __launch_bounds__(256)
+chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
+    typedef typename Fast<SrcT>::raw4 raw4;
+    constexpr bool NN = !(sizeof(SrcT) == 4);
+    static_assert(!LE1 || NN, "LE1 needs integer pixels");
+    extern __shared__ __align__(16) float smem[];
+    const int W = a.g.w, T = blockDim.x, pitch = W + 8, gw = a.g.gw, h = a.g.h;
+    float* s_row = smem;                                       // 3 x pitch
+    int* s_hist = reinterpret_cast<int*>(smem + 3 * pitch);    // gw x kHistPitch
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    for (int i = tid; i < gw * kHistPitch; i += T) s_hist[i] = 0;
+
+    const int ty = (int)(blockIdx.x % a.g.gh);
+    const int64_t n = blockIdx.x / a.g.gh;
+    const int ty0 = ty * kTile;
+    const SrcT* plane = (const SrcT*)a.src + n * a.ssn + 4 * tid;
+    const int ssh = (int)a.ssh;
+    int* my_hist = s_hist + (tid >> 4) * kHistPitch;
+    const uint32_t my_hist32 = hist_base32(my_hist);
+    uint8_t* ip = a.idx + (n * h + ty0) * (int64_t)W + 4 * tid;
+    const bool first_warp = warp == 0, last_warp = warp == nwarps - 1;
+
+    // rows kMRows, kMRows+1 are fetched but never used (they exist or mirror onto existing rows)
+    auto fetch = [&](int s) -> raw4 {
+        const int sy = march_src_row<BORDER>(ty0 - kMR + s, h);
+        if (BORDER == MIE_BORDER_CONSTANT && sy < 0) return Fast<SrcT>::zero4();
+        return Fast<SrcT>::ldg4(plane + (unsigned)(sy * ssh));
+    };
+    raw4 raw[3];
+    raw[0] = fetch(0);
+    raw[1] = fetch(1);
+    float2 ring[kMRing][2];
+    float* const my_buf = s_row + 4 + 4 * tid;
+
+    auto nine = [&](auto first_c, const int s0) {
+        constexpr bool FIRST = decltype(first_c)::value;
+#pragma unroll
+        for (int u = 0; u < kMRing; ++u) {
+            const int s = s0 + u;
+            raw[(u + 2) % 3] = fetch(s + 2);
+            float x[4];
+            Fast<SrcT>::cvt_raw4(raw[u % 3], x);
+            if (BORDER == MIE_BORDER_CONSTANT && (unsigned)(ty0 - kMR + s) >= (unsigned)h) {
+                x[0] = x[1] = x[2] = x[3] = 0.0f;
+            }
+            float* rowbuf = s_row + (u % 3) * pitch;
+            *reinterpret_cast<float4*>(my_buf + (u % 3) * pitch) = make_float4(x[0], x[1], x[2], x[3]);
+            march_halo<BORDER>(rowbuf, x, W, first_warp, last_warp, tid, T);
+            __syncthreads();
+            march_row_pass(rowbuf, tid, wx, ring[u][0], ring[u][1]);
+            if (!FIRST || u == kMRing - 1) {
+                float g[4];
+                march_col_pass(ring, (u + 1) % kMRing, wy, g);
+                if (LE1) {
+                    *reinterpret_cast<uint32_t*>(ip) =
+                        pack_low_bytes(fast_idx_bits_le1(g[0]), fast_idx_bits_le1(g[1]), fast_idx_bits_le1(g[2]),
+                                       fast_idx_bits_le1(g[3]));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hist_add_le1(my_hist32, g[k]);
+                } else {
+                    *reinterpret_cast<uint32_t*>(ip) =
+                        pack_low_bytes(fast_idx_bits<NN>(g[0]), fast_idx_bits<NN>(g[1]), fast_idx_bits<NN>(g[2]),
+                                       fast_idx_bits<NN>(g[3]));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) hist_add_nobranch(my_hist, fast_bin<NN>(g[k]));
+                }
+                ip += W;
+            }
+        }
+    };
+    nine(TrueC(), 0);
+    for (int s0 = kMRing; s0 < kMRows; s0 += kMRing) nine(FalseC(), s0);
+
+    __syncthreads();
+    uint8_t* luts = a.luts + (n * a.g.gh + ty) * (int64_t)gw * kBins;
+    for (int t = warp; t < gw; t += nwarps)
+        warp_build_lut<LE1>(s_hist + t * kHistPitch, a.lp, luts + t * kBins, lane);
+}
+
+// ================================================================ chain_b (marching, 9-tap unsharp)
+// grid = n * gh blocks of W/4 threads.  The band's 72 source rows lie in two rows of interpolation
+// cells; their 2 (gw+1) cell tables (2 KB each, contiguous in the workspace) are staged in shared
+// memory once.  Per source row: index bytes (two rows ahead) -> one 64-bit table lookup per pixel ->
+// CLAHE output C -> row buffer -> horizontal pass -> register ring -> vertical pass ->
+// C + (C - blur(C)) -> quantise -> one 64-bit store per thread.  The C values of the last nine rows
+// stay in the row-buffer ring, which is where the epilogue re-reads its centre pixels.
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+template <typename DstT, int BORDER>
+__global__ void __launch_bounds__(256)
+chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy) {
+    extern __shared__ __align__(16) float smem[];
+    const int W = a.g.w, T = blockDim.x, pitch = W + 8, gw = a.g.gw, gh = a.g.gh, h = a.g.h;
+    uint2* s_tab = reinterpret_cast<uint2*>(smem);       // 2 x (gw+1) x 256 entries
+    float* s_row = smem + 2 * (gw + 1) * kBins * 2;      // kMRing x pitch
+
+    const int tid = threadIdx.x, warp = tid >> 5, nwarps = T >> 5;
+    const int ty = (int)(blockIdx.x % gh);
+    const int64_t n = blockIdx.x / gh;
+    const int ty0 = ty * kTile;
+    const bool first_warp = warp == 0, last_warp = warp == nwarps - 1;
+
+    const uint8_t* iplane = a.idx + n * (int64_t)h * W + 4 * tid;
+    auto fetch = [&](int s) -> uint32_t {
+        const int sy = march_src_row<BORDER>(ty0 - kMR + s, h);
+        if (BORDER == MIE_BORDER_CONSTANT && sy < 0) return 0u;
+        return __ldg(reinterpret_cast<const uint32_t*>(iplane + (unsigned)(sy * W)));
+    };
+    uint32_t raw[3];
+    raw[0] = fetch(0);
+    raw[1] = fetch(1);
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(cells + (n * (gh + 1) + ty) * (int64_t)(gw + 1) * kBins);
+        uint4* dst4 = reinterpret_cast<uint4*>(s_tab);
+        const int total = 2 * (gw + 1) * kBins / 2;  // 16-byte pieces
+        for (int i = tid; i < total; i += T) dst4[i] = __ldg(src + i);
+    }
+    // cells of this thread's columns: column cell (4t + 32) / 64; row cell 0 (rows above the tile
+    // centre line ty0 + 32) or 1.  Shared-window byte addresses, so a lookup is LEA + LDS.64.
+    const uint32_t tb0 = (uint32_t)__cvta_generic_to_shared(s_tab + ((tid + 8) >> 4) * kBins);
+    const uint32_t tb_step = (uint32_t)((gw + 1) * kBins * 8);
+    float wxv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wxv[k] = aw.w[4 + ((4 * tid + k) & (kTile - 1))];
+    DstT* op = (DstT*)a.dst + n * a.dsn + (int64_t)ty0 * a.dsh + 4 * tid;
+    const int dsh = (int)a.dsh;
+    float2 ring[kMRing][2];
+    float* const my_buf = s_row + 4 + 4 * tid;
+    __syncthreads();  // tables staged
+
+    auto nine = [&](auto first_c, const int s0) {
+        constexpr bool FIRST = decltype(first_c)::value;
+        // Row cell: source rows at or below the tile centre line ty0 + 32 use the lower cell row.  Band
+        // row s maps to source row ty0 - 4 + s (or its mirror image, which lies in the same cell row), so
+        // the switch happens at s = 36 — a multiple of nine, i.e. between two calls of this lambda.
+        static_assert((kTile / 2 + kMR) % kMRing == 0, "cell-row switch must fall on a ring boundary");
+        const uint32_t tb = tb0 + (s0 >= kTile / 2 + kMR ? tb_step : 0u);
+#pragma unroll
+        for (int u = 0; u < kMRing; ++u) {
+            const int s = s0 + u;
+            raw[(u + 2) % 3] = fetch(s + 2);
+            const float wyv = aw.w[s];
+            const uint32_t iw = raw[u % 3];
+            float x[4];
+            x[0] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4440) << 3)), wxv[0], wyv);
+            x[1] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4441) << 3)), wxv[1], wyv);
+            x[2] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4442) << 3)), wxv[2], wyv);
+            x[3] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4443) << 3)), wxv[3], wyv);
+            if (BORDER == MIE_BORDER_CONSTANT && (unsigned)(ty0 - kMR + s) >= (unsigned)h) {
+                x[0] = x[1] = x[2] = x[3] = 0.0f;
+            }
+            float* rowbuf = s_row + u * pitch;
+            *reinterpret_cast<float4*>(my_buf + u * pitch) = make_float4(x[0], x[1], x[2], x[3]);
+            march_halo<BORDER>(rowbuf, x, W, first_warp, last_warp, tid, T);
+            __syncthreads();
+            march_row_pass(rowbuf, tid, wx, ring[u][0], ring[u][1]);
+            if (!FIRST || u == kMRing - 1) {
+                float g[4];
+                march_col_pass(ring, (u + 1) % kMRing, wy, g);
+                const float4 c = *reinterpret_cast<const float4*>(my_buf + ((u + 5) % kMRing) * pitch);
+                float y[4];
+                y[0] = __fadd_rn(c.x, __fsub_rn(c.x, g[0])); y[1] = __fadd_rn(c.y, __fsub_rn(c.y, g[1]));
+                y[2] = __fadd_rn(c.z, __fsub_rn(c.z, g[2])); y[3] = __fadd_rn(c.w, __fsub_rn(c.w, g[3]));
+                Fast<DstT>::store4(op, y);
+                op += dsh;
+            }
+        }
+    };
+    nine(TrueC(), 0);
+    for (int s0 = kMRing; s0 < kMRows; s0 += kMRing) nine(FalseC(), s0);
+}
+
+// ================================================================ host side
+bool march_chain_ok(const ClaheGeom& g, int kg, int ku) {
+    if (kg != 9 || ku != 9) return false;
+    if (g.th != kTile || g.tw != kTile || g.hp != g.h || g.wp != g.w) return false;
+    if (g.w % 128 != 0 || g.w > 1024) return false;
+    return true;
+}
+
+static size_t march_a_smem(const ClaheGeom& g) { return (size_t)(3 * (g.w + 8) + g.gw * kHistPitch) * 4; }
+static size_t march_b_smem(const ClaheGeom& g) {
+    return (size_t)(2 * (g.gw + 1) * kBins * 2 + kMRing * (g.w + 8)) * 4;
+}
+
+// Blur of an all-ones image in the kernels' operation order.  Every fma is monotone in its data
+// operands (the weights are >= 0), so for pixels in [0, 1] no blurred value exceeds this one.
+static bool gauss_of_ones_le1(const Taps& wx, const Taps& wy) {
+    for (int t = 0; t < 2 * kMR + 1; ++t)
+        if (!(wx.w[t] >= 0.0f) || !(wy.w[t] >= 0.0f)) return false;
+    float r = wx.w[0] * 1.0f;
+    for (int t = 1; t < 2 * kMR + 1; ++t) r = fmaf(wx.w[t], 1.0f, r);
+    float c = wy.w[0] * r;
+    for (int t = 1; t < 2 * kMR + 1; ++t) c = fmaf(wy.w[t], r, c);
+    return r <= 1.0f && c <= 1.0f;
+}
+
+template <typename SrcT, int BORDER, bool LE1>
+static int launch_a_march_tbl(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st) {
+    MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1>), 64 * 1024);
+    chain_a_march_kernel<SrcT, BORDER, LE1><<<blocks, a.g.w / 4, march_a_smem(a.g), st>>>(a, wx, wy);
+    return check_launch();
+}
+template <typename SrcT, int BORDER>
+static int launch_a_march_tb(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st) {
+    if constexpr (sizeof(SrcT) != 4) {
+        if (gauss_of_ones_le1(wx, wy)) return launch_a_march_tbl<SrcT, BORDER, true>(a, wx, wy, blocks, st);
+    }
+    return launch_a_march_tbl<SrcT, BORDER, false>(a, wx, wy, blocks, st);
+}
+template <typename SrcT>
+static int launch_a_march_t(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st) {
+    switch (a.border) {
+        case MIE_BORDER_REFLECT: return launch_a_march_tb<SrcT, MIE_BORDER_REFLECT>(a, wx, wy, blocks, st);
+        case MIE_BORDER_REPLICATE: return launch_a_march_tb<SrcT, MIE_BORDER_REPLICATE>(a, wx, wy, blocks, st);
+        default: return launch_a_march_tb<SrcT, MIE_BORDER_CONSTANT>(a, wx, wy, blocks, st);
+    }
+}
+
+int launch_chain_a_march(const ChainAArgs& a, int sd, const Taps& wx, const Taps& wy, int64_t n, cudaStream_t st) {
+    const unsigned blocks = (unsigned)(n * a.g.gh);
+    MIE_DISPATCH_SRC(sd, return launch_a_march_t<SrcT>(a, wx, wy, blocks, st));
+    return MIE_OK;
+}
+
+template <typename DstT, int BORDER>
+static int launch_b_march_tb(const ChainBArgs& b, const uint2* cells, const AxisWeights& aw, const Taps& wx,
+                             const Taps& wy, unsigned blocks, cudaStream_t st) {
+    MIE_ENSURE_SMEM((chain_b_march_kernel<DstT, BORDER>), 128 * 1024);
+    chain_b_march_kernel<DstT, BORDER><<<blocks, b.g.w / 4, march_b_smem(b.g), st>>>(b, cells, aw, wx, wy);
+    return check_launch();
+}
+template <typename DstT>
+static int launch_b_march_t(const ChainBArgs& b, const uint2* cells, const AxisWeights& aw, const Taps& wx,
+                            const Taps& wy, unsigned blocks, cudaStream_t st) {
+    switch (b.border) {
+        case MIE_BORDER_REFLECT: return launch_b_march_tb<DstT, MIE_BORDER_REFLECT>(b, cells, aw, wx, wy, blocks, st);
+        case MIE_BORDER_REPLICATE: return launch_b_march_tb<DstT, MIE_BORDER_REPLICATE>(b, cells, aw, wx, wy, blocks, st);
+        default: return launch_b_march_tb<DstT, MIE_BORDER_CONSTANT>(b, cells, aw, wx, wy, blocks, st);
+    }
+}
+
+int launch_chain_b_march(const ChainBArgs& b, int dd, void* cells_raw, const Taps& wx, const Taps& wy, int64_t n,
+                         cudaStream_t st) {
+    int rc = launch_pack_cells(b.luts, cells_raw, n, b.g.gh, b.g.gw, st);
+    if (rc) return rc;
+    AxisWeights aw;
+    fill_axis_weights(aw);
+    const unsigned blocks = (unsigned)(n * b.g.gh);
+    MIE_DISPATCH_SRC(dd, return launch_b_march_t<SrcT>(b, (const uint2*)cells_raw, aw, wx, wy, blocks, st));
+    return MIE_OK;
+}
+
+}  // namespace mie
