@@ -92,16 +92,24 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
 // and chain_b.
 __global__ void __launch_bounds__(256)
 chain_pack_cells_kernel(const uint8_t* __restrict__ luts, uint2* __restrict__ cells, int gh, int gw) {
-    const int cx = blockIdx.x, cy = blockIdx.y;
-    const int64_t n = blockIdx.z;
-    const int jt = max(cy - 1, 0), jb = min(cy, gh - 1), il = max(cx - 1, 0), ir = min(cx, gw - 1);
-    const uint8_t* nl = luts + n * (int64_t)gh * gw * kBins + threadIdx.x;
-    const int tl = nl[(jt * gw + il) * kBins], tr = nl[(jt * gw + ir) * kBins];
-    const int bl = nl[(jb * gw + il) * kBins], br = nl[(jb * gw + ir) * kBins];
-    uint2 e;
-    e.x = cell_word(tl - tr, tr);
-    e.y = cell_word(bl - br, br);
-    cells[((n * (gh + 1) + cy) * (int64_t)(gw + 1) + cx) * kBins + threadIdx.x] = e;
+    // one block per (image, cell row); thread = grey level; walks the gw + 1 cells of the row, carrying
+    // the right-hand LUT entries of one cell over as the left-hand entries of the next
+    const int cy = blockIdx.x;
+    const int64_t n = blockIdx.y;
+    const int jt = max(cy - 1, 0), jb = min(cy, gh - 1);
+    const uint8_t* top = luts + (n * gh + jt) * (int64_t)gw * kBins + threadIdx.x;
+    const uint8_t* bot = luts + (n * gh + jb) * (int64_t)gw * kBins + threadIdx.x;
+    uint2* out = cells + (n * (gh + 1) + cy) * (int64_t)(gw + 1) * kBins + threadIdx.x;
+    int tl = top[0], bl = bot[0];
+    for (int cx = 0; cx <= gw; ++cx) {
+        const int ir = min(cx, gw - 1);
+        const int tr = top[ir * kBins], br = bot[ir * kBins];
+        uint2 e;
+        e.x = cell_word(tl - tr, tr);
+        e.y = cell_word(bl - br, br);
+        out[cx * kBins] = e;
+        tl = tr; bl = br;
+    }
 }
 
 // ================================================================ chain_b (fast, 9-tap unsharp)
@@ -298,7 +306,7 @@ int launch_chain_a_fast(const ChainAArgs& a, int sd, const Taps& wx, const Taps&
 
 int launch_pack_cells(const uint8_t* luts, void* cells, int64_t n, int gh, int gw, cudaStream_t st) {
     if (n > 65535) return MIE_E_SHAPE;
-    dim3 pgrid((unsigned)(gw + 1), (unsigned)(gh + 1), (unsigned)n);
+    dim3 pgrid((unsigned)(gh + 1), (unsigned)n);
     chain_pack_cells_kernel<<<pgrid, 256, 0, st>>>(luts, (uint2*)cells, gh, gw);
     return check_launch();
 }

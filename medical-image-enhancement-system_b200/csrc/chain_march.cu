@@ -22,9 +22,13 @@ namespace mie {
 constexpr int kMR = 4;                    // 9-tap kernels
 constexpr int kMRows = kTile + 2 * kMR;   // source rows per band
 constexpr int kMRing = 2 * kMR + 1;       // register ring depth == unroll factor
+constexpr int kMBatch = 3;                // global loads are issued three rows at a time, 3..5 rows ahead of
+                                          // their use: a batch shares one scoreboard, so a consumer never
+                                          // waits on a load younger than its own (measured: issuing one load
+                                          // per row made every ninth consumer wait for the newest load)
 constexpr int kHistPitch = 264;           // 257 slots (256 = ignored pixels), padded to a multiple of 8
 
-// Source row of band row r (|overshoot| <= 6 < h, so one reflection suffices): branch-free, on the
+// Source row of band row r (|overshoot| <= 4 + 2 * kMBatch < h, so one reflection suffices): branch-free, on the
 // uniform datapath.  -1 = outside the image with a constant border.
 template <int BORDER>
 __device__ __forceinline__ int march_src_row(int r, int h) {
@@ -133,15 +137,15 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
     uint8_t* ip = a.idx + (n * h + ty0) * (int64_t)W + 4 * tid;
     const bool first_warp = warp == 0, last_warp = warp == nwarps - 1;
 
-    // rows kMRows, kMRows+1 are fetched but never used (they exist or mirror onto existing rows)
+    // rows kMRows .. kMRows+2*kMBatch-1 are fetched but never used (they exist or mirror onto existing rows)
     auto fetch = [&](int s) -> raw4 {
         const int sy = march_src_row<BORDER>(ty0 - kMR + s, h);
         if (BORDER == MIE_BORDER_CONSTANT && sy < 0) return Fast<SrcT>::zero4();
         return Fast<SrcT>::ldg4(plane + (unsigned)(sy * ssh));
     };
-    raw4 raw[3];
-    raw[0] = fetch(0);
-    raw[1] = fetch(1);
+    raw4 raw[kMRing];
+#pragma unroll
+    for (int s = 0; s < kMBatch; ++s) raw[s] = fetch(s);
     float2 ring[kMRing][2];
     float* const my_buf = s_row + 4 + 4 * tid;
 
@@ -150,9 +154,12 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
 #pragma unroll
         for (int u = 0; u < kMRing; ++u) {
             const int s = s0 + u;
-            raw[(u + 2) % 3] = fetch(s + 2);
             float x[4];
-            Fast<SrcT>::cvt_raw4(raw[u % 3], x);
+            Fast<SrcT>::cvt_raw4(raw[u], x);
+            if (u % kMBatch == 0) {
+#pragma unroll
+                for (int j = 0; j < kMBatch; ++j) raw[(u + kMBatch + j) % kMRing] = fetch(s + kMBatch + j);
+            }
             if (BORDER == MIE_BORDER_CONSTANT && (unsigned)(ty0 - kMR + s) >= (unsigned)h) {
                 x[0] = x[1] = x[2] = x[3] = 0.0f;
             }
@@ -223,9 +230,9 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
         if (BORDER == MIE_BORDER_CONSTANT && sy < 0) return 0u;
         return __ldg(reinterpret_cast<const uint32_t*>(iplane + (unsigned)(sy * W)));
     };
-    uint32_t raw[3];
-    raw[0] = fetch(0);
-    raw[1] = fetch(1);
+    uint32_t raw[kMRing];
+#pragma unroll
+    for (int s = 0; s < kMBatch; ++s) raw[s] = fetch(s);
     {
         const uint4* src = reinterpret_cast<const uint4*>(cells + (n * (gh + 1) + ty) * (int64_t)(gw + 1) * kBins);
         uint4* dst4 = reinterpret_cast<uint4*>(s_tab);
@@ -255,9 +262,12 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
 #pragma unroll
         for (int u = 0; u < kMRing; ++u) {
             const int s = s0 + u;
-            raw[(u + 2) % 3] = fetch(s + 2);
             const float wyv = aw.w[s];
-            const uint32_t iw = raw[u % 3];
+            const uint32_t iw = raw[u];
+            if (u % kMBatch == 0) {
+#pragma unroll
+                for (int j = 0; j < kMBatch; ++j) raw[(u + kMBatch + j) % kMRing] = fetch(s + kMBatch + j);
+            }
             float x[4];
             x[0] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4440) << 3)), wxv[0], wyv);
             x[1] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4441) << 3)), wxv[1], wyv);
