@@ -208,13 +208,17 @@ def run_ours(args):
     x = x_host.to(dev, non_blocking=True)
     y = torch.empty_like(x)
     cfg = mie_b200.ChainConfig()
-    ws = torch.empty(mie_b200.chain_workspace_bytes(BATCH, H, W, cfg.grid_size), dtype=torch.uint8, device=dev)
     path = int(mie_b200._lib().mie_chain_is_fused(H, W, 8, 8, 9, 9, 9, 9))
     fused = path > 0
     launches_per_step = {0: 4, 1: 2, 2: 3}[path]  # tuned path: chain_a, cell packing, chain_b
 
+    # steady state = fixed device buffers: the three launches of a step are captured once into a CUDA
+    # graph (mie_b200.ChainPlan) and replayed, so the timed region holds no per-call Python work
+    plan = mie_b200.ChainPlan(x, cfg, out=y)
+    ws = plan.workspace
+
     def step():
-        mie_b200.enhance_chain(x, cfg, out=y, workspace=ws)
+        plan.replay()
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -241,14 +245,15 @@ def run_ours(args):
     kern = {}
     if fused:
         for name, mask in (("chain_a_kernel", 1), ("chain_b_kernel", 2)):
+            g = mie_b200.ChainPlan(x, cfg, out=y, workspace=ws, stages=mask)
             for _ in range(3):
-                mie_b200.enhance_chain(x, cfg, out=y, workspace=ws, stages=mask)
+                g.replay()
             torch.cuda.synchronize()
             reps = max(args.steps, 10)
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             for _ in range(reps):
-                mie_b200.enhance_chain(x, cfg, out=y, workspace=ws, stages=mask)
+                g.replay()
             a1.record()
             torch.cuda.synchronize()
             kern[name] = a0.elapsed_time(a1) / reps

@@ -317,7 +317,8 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     b.lo = lo; b.rg = hi - lo;
     if (n * (int64_t)b.tiles_x * b.tiles_y > 2147483647LL) return MIE_E_SHAPE;
     if (fast) {
-        const bool march = march_chain_ok(g, kgx, kux) && !g_disable_march;
+        const bool march = march_chain_ok(g, kgx, kux) && !g_disable_march &&
+                           (int64_t)h * src_stride_h * 4 < (1LL << 31);  // 32-bit source-row offsets
         if (stages & MIE_CHAIN_STAGE_A) {
             rc = march ? launch_chain_a_march(a, src_dtype, tgx, tgy, n, st)
                        : launch_chain_a_fast(a, src_dtype, tgx, tgy, kgx / 2, n, st);

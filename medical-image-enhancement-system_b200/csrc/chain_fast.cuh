@@ -229,6 +229,30 @@ __device__ __forceinline__ void col4_f32x2(const float4* win, int j, const Taps&
     g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
 }
 
+// Packed f32x2 values held as ONE 64-bit register pair.  The CUDA float2 intrinsics re-pack their
+// operands at every call; when the two halves come from different producers (the marching kernels'
+// register ring) ptxas then copies them into an aligned pair at every use.  Packing once and keeping
+// the 64-bit value costs the two copies once.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // x / 255, correctly rounded (Markstein: y = RN(1/b), q0 = RN(a*y), r = a - b*q0 exact, RN(q0 + r*y)).
 __device__ __forceinline__ float div255(float x) {
     constexpr float r = 0.003921568859368563f;

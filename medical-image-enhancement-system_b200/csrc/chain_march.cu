@@ -4,32 +4,37 @@
 // oracle/mie_oracle.c; what changes is the schedule:
 //
 //   * one block owns a full-width band of 64 rows (one row of CLAHE tiles) and walks down its
-//     64 + 8 source rows; thread t owns image columns 4t .. 4t+3 for the whole walk;
+//     64 + 8 source rows TWO ROWS PER STEP; thread t owns image columns 4t .. 4t+3 for the whole walk;
 //   * a row is converted (chain_a) / CLAHE-blended (chain_b) exactly once per band and exchanged
-//     through a small ring of row buffers in shared memory — one STS.128 and three LDS.128 per
-//     thread and row; the image-border halo comes from two warp shuffles, not from extra loads;
-//   * the vertical pass never touches shared memory: the last nine horizontally filtered rows of the
-//     thread's four columns live in registers (the walk is unrolled by nine so that the ring is
-//     addressed statically) and feed packed fma.rn.f32x2;
-//   * nothing is computed for a horizontal halo, and only 8 of 72 rows are vertical halo, so the
-//     per-pixel work is 1.125x the arithmetic minimum (the tiled kernels: 1.27x-1.7x), and the
-//     shared-memory traffic drops from ~45 to ~24 bytes per pixel;
-//   * global loads (4 pixels / 4 index bytes per thread and row) are issued two rows ahead.
+//     through a small ring of row-pair buffers in shared memory in which the two rows of a pair are
+//     interleaved per column — so the horizontal pass reads ready-made (row s, row s+1) operand pairs
+//     and runs on packed fma.rn.f32x2 (one issue slot per two results);
+//   * the vertical pass never touches shared memory: the horizontally filtered rows of the thread's
+//     four columns live in a register ring (16 slots, ten of them live; the walk is unrolled by eight
+//     row pairs so that the ring is addressed statically) and feed packed fma.rn.f32x2 on column pairs;
+//   * nothing is computed for a horizontal halo (the image-border halo is four warp shuffles per row
+//     pair), and only 8 of 72 rows are vertical halo: per-pixel work is 1.125x the arithmetic minimum;
+//   * global loads (4 pixels / 4 index bytes per thread and row) are issued four rows at a time, four
+//     to seven rows ahead of their use; source-row offsets (mirrored at the image border) come from a
+//     small shared-memory table instead of per-row index arithmetic.
+#include <cstdlib>
+
 #include "chain_fast.cuh"
 
 namespace mie {
 
-constexpr int kMR = 4;                    // 9-tap kernels
-constexpr int kMRows = kTile + 2 * kMR;   // source rows per band
-constexpr int kMRing = 2 * kMR + 1;       // register ring depth == unroll factor
-constexpr int kMBatch = 3;                // global loads are issued three rows at a time, 3..5 rows ahead of
-                                          // their use: a batch shares one scoreboard, so a consumer never
-                                          // waits on a load younger than its own (measured: issuing one load
-                                          // per row made every ninth consumer wait for the newest load)
-constexpr int kHistPitch = 264;           // 257 slots (256 = ignored pixels), padded to a multiple of 8
+constexpr int kMR = 4;                     // 9-tap kernels
+constexpr int kMRows = kTile + 2 * kMR;    // 72 source rows per band
+constexpr int kMPairs = kMRows / 2;        // 36 row pairs
+constexpr int kMPro = kMR;                 // prologue: 4 row pairs (8 rows) that produce no output
+constexpr int kMRing = 16;                 // register-ring slots (row s lives in slot s % 16)
+constexpr int kMUnroll = kMRing / 2;       // main loop: 8 row pairs per iteration
+constexpr int kMOffRows = kMRows + 8;      // rows covered by the source-offset table (incl. over-fetch)
+constexpr int kHistPitch = 264;            // 257 slots (256 = value 1.0 / ignored pixels), padded
+static_assert((kMPairs - kMPro) % kMUnroll == 0, "main loop must tile the band");
 
-// Source row of band row r (|overshoot| <= 4 + 2 * kMBatch < h, so one reflection suffices): branch-free, on the
-// uniform datapath.  -1 = outside the image with a constant border.
+// Source row of band row r (|overshoot| <= 4 + 8 < h, so one reflection suffices).
+// -1 = outside the image with a constant border.
 template <int BORDER>
 __device__ __forceinline__ int march_src_row(int r, int h) {
     if (BORDER == MIE_BORDER_REFLECT) {
@@ -40,157 +45,297 @@ __device__ __forceinline__ int march_src_row(int r, int h) {
     return (unsigned)r < (unsigned)h ? r : -1;
 }
 
-// Image-border halo of a row buffer: rowbuf[0..3] (left) and [4+W .. 4+W+3] (right) from the four
-// pixels of the first / last thread and one value of their neighbour lane.
+// ---------------------------------------------------------------- row-pair buffers
+// One buffer holds two image rows (s, s+1) of W + 8 haloed columns as "quads": quad q = haloed
+// columns 4q .. 4q+3 (q = 0: left halo, q = t + 1: thread t, q = T + 1: right halo).  Region A holds
+// the first two columns of every quad, region B the last two, each as (row s, row s+1) pairs:
+//     A[4q .. 4q+3] = (x0[c], x1[c], x0[c+1], x1[c+1]),   B[4q .. 4q+3] = (x0[c+2], x1[c+2], x0[c+3], x1[c+3])
+// Every access below is a 16-byte access with a 16-byte thread stride: conflict-free.
+__device__ __forceinline__ int pairbuf_floats(int T) { return 8 * (T + 2); }
+
 template <int BORDER>
-__device__ __forceinline__ void march_halo(float* rowbuf, const float* x, int W, bool first_warp, bool last_warp,
-                                           int tid, int T) {
-    if (first_warp) {
-        float nb = 0.f;
-        if (BORDER == MIE_BORDER_REFLECT) nb = __shfl_down_sync(0xffffffffu, x[0], 1);  // column 4 -> thread 0
+__device__ __forceinline__ void pair_store(float* buf, int T, int tid, bool first_warp, bool last_warp,
+                                           const float* x0, const float* x1) {
+    float* A = buf;
+    float* B = buf + 4 * (T + 2);
+    *reinterpret_cast<float4*>(A + 4 * (tid + 1)) = make_float4(x0[0], x1[0], x0[1], x1[1]);
+    *reinterpret_cast<float4*>(B + 4 * (tid + 1)) = make_float4(x0[2], x1[2], x0[3], x1[3]);
+    if (first_warp) {  // columns -4..-1 mirror onto 4, 3, 2, 1
+        float n0 = 0.f, n1 = 0.f;
+        if (BORDER == MIE_BORDER_REFLECT) {
+            n0 = __shfl_down_sync(0xffffffffu, x0[0], 1);
+            n1 = __shfl_down_sync(0xffffffffu, x1[0], 1);
+        }
         if (tid == 0) {
-            float4 hl;
-            if (BORDER == MIE_BORDER_REFLECT) hl = make_float4(nb, x[3], x[2], x[1]);
-            else if (BORDER == MIE_BORDER_REPLICATE) hl = make_float4(x[0], x[0], x[0], x[0]);
-            else hl = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(rowbuf) = hl;
+            float4 a, b;
+            if (BORDER == MIE_BORDER_REFLECT) {
+                a = make_float4(n0, n1, x0[3], x1[3]);
+                b = make_float4(x0[2], x1[2], x0[1], x1[1]);
+            } else if (BORDER == MIE_BORDER_REPLICATE) {
+                a = b = make_float4(x0[0], x1[0], x0[0], x1[0]);
+            } else {
+                a = b = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            *reinterpret_cast<float4*>(A) = a;
+            *reinterpret_cast<float4*>(B) = b;
         }
     }
-    if (last_warp) {
-        float nb = 0.f;
-        if (BORDER == MIE_BORDER_REFLECT) nb = __shfl_up_sync(0xffffffffu, x[3], 1);  // column W-5 -> last thread
+    if (last_warp) {  // columns W..W+3 mirror onto W-2, W-3, W-4, W-5
+        float n0 = 0.f, n1 = 0.f;
+        if (BORDER == MIE_BORDER_REFLECT) {
+            n0 = __shfl_up_sync(0xffffffffu, x0[3], 1);
+            n1 = __shfl_up_sync(0xffffffffu, x1[3], 1);
+        }
         if (tid == T - 1) {
-            float4 hr;
-            if (BORDER == MIE_BORDER_REFLECT) hr = make_float4(x[2], x[1], x[0], nb);
-            else if (BORDER == MIE_BORDER_REPLICATE) hr = make_float4(x[3], x[3], x[3], x[3]);
-            else hr = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(rowbuf + 4 + W) = hr;
+            float4 a, b;
+            if (BORDER == MIE_BORDER_REFLECT) {
+                a = make_float4(x0[2], x1[2], x0[1], x1[1]);
+                b = make_float4(x0[0], x1[0], n0, n1);
+            } else if (BORDER == MIE_BORDER_REPLICATE) {
+                a = b = make_float4(x0[3], x1[3], x0[3], x1[3]);
+            } else {
+                a = b = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            *reinterpret_cast<float4*>(A + 4 * (T + 1)) = a;
+            *reinterpret_cast<float4*>(B + 4 * (T + 1)) = b;
         }
     }
 }
 
-// Horizontal 9-tap pass for the thread's four columns out of the row buffer (columns 4t-4 .. 4t+7).
-__device__ __forceinline__ void march_row_pass(const float* rowbuf, int tid, const Taps& wx, float2& m01, float2& m23) {
-    const float4* p = reinterpret_cast<const float4*>(rowbuf + 4 * tid);
-    const float4 a = p[0], b = p[1], c = p[2];
-    const float win[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-    float o[4];
+// Horizontal 9-tap pass of both rows of a pair for the thread's four columns, written straight into
+// the register ring.  Tap order and rounding as everywhere else (acc = w0 x0; acc = fma(w_t, x_t, acc)).
+// The window comes out of shared memory already packed — a 16-byte load is two (row s, row s+1)
+// operand pairs — so taps 0..7 run two rows per instruction.  The LAST tap is issued as scalar fmas:
+// their results are fresh registers, which lets ptxas place (column c, column c+1) of one row in an
+// aligned pair for the vertical pass at no cost (re-pairing the halves of packed results instead costs
+// two register copies at every one of their nine uses).
+__device__ __forceinline__ void pair_row_pass(const float* buf, int T, int tid, const Taps& wx,
+                                              f32x2 (&ring)[kMRing][2], const int slot) {
+    const ulonglong2* A = reinterpret_cast<const ulonglong2*>(buf) + tid;
+    const ulonglong2* B = reinterpret_cast<const ulonglong2*>(buf + 4 * (T + 2)) + tid;
+    f32x2 win[12];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const ulonglong2 a = A[q], b = B[q];
+        win[4 * q] = a.x; win[4 * q + 1] = a.y; win[4 * q + 2] = b.x; win[4 * q + 3] = b.y;
+    }
+    f32x2 acc[4];
+    const f32x2 w0 = f2_pack(wx.w[0], wx.w[0]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = f2_mul(w0, win[j]);
+#pragma unroll
+    for (int t = 1; t < 2 * kMR; ++t) {
+        const f32x2 wt = f2_pack(wx.w[t], wx.w[t]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = f2_fma(wt, win[j + t], acc[j]);
+    }
+    float m0[4], m1[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        float acc = __fmul_rn(wx.w[0], win[j]);
-#pragma unroll
-        for (int t = 1; t <= 2 * kMR; ++t) acc = __fmaf_rn(wx.w[t], win[j + t], acc);
-        o[j] = acc;
+        float al, ah, xl, xh;
+        f2_unpack(acc[j], al, ah);
+        f2_unpack(win[j + 2 * kMR], xl, xh);
+        m0[j] = __fmaf_rn(wx.w[2 * kMR], xl, al);
+        m1[j] = __fmaf_rn(wx.w[2 * kMR], xh, ah);
     }
-    m01 = make_float2(o[0], o[1]);
-    m23 = make_float2(o[2], o[3]);
+    ring[slot % kMRing][0] = f2_pack(m0[0], m0[1]);
+    ring[slot % kMRing][1] = f2_pack(m0[2], m0[3]);
+    ring[(slot + 1) % kMRing][0] = f2_pack(m1[0], m1[1]);
+    ring[(slot + 1) % kMRing][1] = f2_pack(m1[2], m1[3]);
 }
 
 // Vertical 9-tap pass out of the register ring; OLDEST = ring slot of the topmost tap (a constant
 // after unrolling, so the ring stays in registers).
-__device__ __forceinline__ void march_col_pass(const float2 (&ring)[kMRing][2], const int OLDEST, const Taps& wy,
+__device__ __forceinline__ void march_col_pass(const f32x2 (&ring)[kMRing][2], const int OLDEST, const Taps& wy,
                                                float* g) {
-    const float2 w0 = make_float2(wy.w[0], wy.w[0]);
-    float2 a = __fmul2_rn(w0, ring[OLDEST][0]);
-    float2 b = __fmul2_rn(w0, ring[OLDEST][1]);
+    const f32x2 w0 = f2_pack(wy.w[0], wy.w[0]);
+    f32x2 a = f2_mul(w0, ring[OLDEST % kMRing][0]);
+    f32x2 b = f2_mul(w0, ring[OLDEST % kMRing][1]);
 #pragma unroll
     for (int t = 1; t <= 2 * kMR; ++t) {
-        const float2 wt = make_float2(wy.w[t], wy.w[t]);
-        a = __ffma2_rn(wt, ring[(OLDEST + t) % kMRing][0], a);
-        b = __ffma2_rn(wt, ring[(OLDEST + t) % kMRing][1], b);
+        const f32x2 wt = f2_pack(wy.w[t], wy.w[t]);
+        a = f2_fma(wt, ring[(OLDEST + t) % kMRing][0], a);
+        b = f2_fma(wt, ring[(OLDEST + t) % kMRing][1], b);
     }
-    g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
+    f2_unpack(a, g[0], g[1]);
+    f2_unpack(b, g[2], g[3]);
 }
 
-struct TrueC { static constexpr bool value = true; };
-struct FalseC { static constexpr bool value = false; };
+// ---------------------------------------------------------------- bulk-copy (TMA) row ring
+// chain_a streams its source rows through shared memory with cp.async.bulk: one elected thread issues
+// four row copies per mbarrier, up to sixteen rows (16 KB for uint16, W = 512) ahead of their use.  A
+// register prefetch of the same depth would cost 32 registers per thread; with two 8-byte loads per
+// thread in flight the kernel could not cover the DRAM latency (Little's law: 16 KB per SM in flight at
+// ~1 us is 2.4 TB/s for the whole chip, barely the 1.6 TB/s this kernel needs).
+constexpr int kRawRows = 16;   // ring slots (row s lives in slot s % 16)
+constexpr int kRawBatch = 4;   // rows per mbarrier
+constexpr int kRawBars = kRawRows / kRawBatch;
+
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+// Byte offsets (int32) of the band's source rows, mirrored at the image border; -1 marks rows outside
+// the image with a constant border.  stride_bytes * h < 2^31 is checked on the host.
+template <int BORDER>
+__device__ __forceinline__ void fill_row_offsets(int* s_off, int ty0, int h, int stride_bytes, int tid, int T) {
+    for (int s = tid; s < kMOffRows; s += T) {
+        const int sy = march_src_row<BORDER>(ty0 - kMR + s, h);
+        s_off[s] = sy < 0 ? -1 : sy * stride_bytes;
+    }
+}
 
 // ================================================================ chain_a (marching)
-// grid = n * gh blocks of W/4 threads.  Per source row: load (two rows ahead) -> convert -> row
-// buffer -> horizontal pass -> register ring -> vertical pass -> lookup index (32-bit store into the
-// index plane) and histogram bin (ATOMS.POPC.INC into the thread's tile histogram).  After the walk
-// each warp turns tile histograms into LUTs.  The first nine rows (which emit one output row) are a
-// separate copy of the loop body, so the steady state carries no "is there an output yet" test.
+// grid = n * gh blocks of W/4 threads.  Per row pair: load (ahead) -> convert -> pair buffer ->
+// horizontal pass -> register ring -> vertical pass of the two rows that became complete -> lookup index
+// (32-bit store into the index plane) and histogram bin (ATOMS.POPC.INC into the thread's tile
+// histogram).  After the walk each warp turns tile histograms into LUTs.
 // LE1: the host has proven that every blurred value lies in [0, 1] (integer pixels and
 // gauss_of_ones_le1), which removes the range tests from the index / bin rules.
-template <typename SrcT, int BORDER, bool LE1>
-__global__ void __launch_bounds__(256)
+template <typename SrcT, int BORDER, bool LE1, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
     typedef typename Fast<SrcT>::raw4 raw4;
     constexpr bool NN = !(sizeof(SrcT) == 4);
     static_assert(!LE1 || NN, "LE1 needs integer pixels");
     extern __shared__ __align__(16) float smem[];
-    const int W = a.g.w, T = blockDim.x, pitch = W + 8, gw = a.g.gw, h = a.g.h;
-    float* s_row = smem;                                       // 3 x pitch
-    int* s_hist = reinterpret_cast<int*>(smem + 3 * pitch);    // gw x kHistPitch
+    const int W = a.g.w, T = blockDim.x, gw = a.g.gw, h = a.g.h;
+    const int pbuf = pairbuf_floats(T);
+    float* s_buf = smem;                                              // 2 pair buffers
+    int* s_hist = reinterpret_cast<int*>(smem + 2 * pbuf);            // gw x kHistPitch
+    int* s_off = s_hist + gw * kHistPitch;                            // kMOffRows
+    unsigned long long* s_bar = reinterpret_cast<unsigned long long*>(s_off + kMOffRows);  // kRawBars mbarriers
+    float* s_raw = reinterpret_cast<float*>(s_bar + kRawBars);        // kRawRows source rows (raw pixels)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
-    for (int i = tid; i < gw * kHistPitch; i += T) s_hist[i] = 0;
-
     const int ty = (int)(blockIdx.x % a.g.gh);
     const int64_t n = blockIdx.x / a.g.gh;
     const int ty0 = ty * kTile;
-    const SrcT* plane = (const SrcT*)a.src + n * a.ssn + 4 * tid;
-    const int ssh = (int)a.ssh;
-    int* my_hist = s_hist + (tid >> 4) * kHistPitch;
+    for (int i = tid; i < gw * kHistPitch; i += T) s_hist[i] = 0;
+    fill_row_offsets<BORDER>(s_off, ty0, h, (int)a.ssh * (int)sizeof(SrcT), tid, T);
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < kRawBars; ++b)
+            mbar_init((uint32_t)__cvta_generic_to_shared(s_bar + b), 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int* const my_hist = s_hist + (tid >> 4) * kHistPitch;
     const uint32_t my_hist32 = hist_base32(my_hist);
     uint8_t* ip = a.idx + (n * h + ty0) * (int64_t)W + 4 * tid;
     const bool first_warp = warp == 0, last_warp = warp == nwarps - 1;
 
-    // rows kMRows .. kMRows+2*kMBatch-1 are fetched but never used (they exist or mirror onto existing rows)
-    auto fetch = [&](int s) -> raw4 {
-        const int sy = march_src_row<BORDER>(ty0 - kMR + s, h);
-        if (BORDER == MIE_BORDER_CONSTANT && sy < 0) return Fast<SrcT>::zero4();
-        return Fast<SrcT>::ldg4(plane + (unsigned)(sy * ssh));
+    // source rows through the bulk-copy ring: batch b = band rows 4b .. 4b+3 -> ring slots (4b + j) % 16,
+    // mbarrier b % 4, phase parity (b / 4) & 1
+    const int row_bytes = W * (int)sizeof(SrcT);
+    const uint32_t ring32 = (uint32_t)__cvta_generic_to_shared(s_raw);
+    const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(s_bar);
+    const char* plane0 = reinterpret_cast<const char*>((const SrcT*)a.src + n * a.ssn);
+    auto issue_batch = [&](const int b) {  // thread 0 only
+        const int4 o = *reinterpret_cast<const int4*>(s_off + kRawBatch * b);
+        const int off[4] = {o.x, o.y, o.z, o.w};
+        const uint32_t mb = bar32 + 8 * (b % kRawBars);
+        int valid = 0;
+#pragma unroll
+        for (int j = 0; j < kRawBatch; ++j) valid += (BORDER != MIE_BORDER_CONSTANT || off[j] >= 0) ? 1 : 0;
+        mbar_expect_tx(mb, (uint32_t)(valid * row_bytes));
+#pragma unroll
+        for (int j = 0; j < kRawBatch; ++j)
+            if (BORDER != MIE_BORDER_CONSTANT || off[j] >= 0)
+                bulk_g2s(ring32 + (uint32_t)(((kRawBatch * b + j) % kRawRows) * row_bytes), plane0 + (unsigned)off[j],
+                         (uint32_t)row_bytes, mb);
     };
-    raw4 raw[kMRing];
+    if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kMBatch; ++s) raw[s] = fetch(s);
-    float2 ring[kMRing][2];
-    float* const my_buf = s_row + 4 + 4 * tid;
+        for (int b = 0; b < kRawBars; ++b) issue_batch(b);
+    }
+    f32x2 ring[kMRing][2];
+    const char* my_raw = reinterpret_cast<const char*>(s_raw) + 4 * tid * (int)sizeof(SrcT);
 
-    auto nine = [&](auto first_c, const int s0) {
-        constexpr bool FIRST = decltype(first_c)::value;
-#pragma unroll
-        for (int u = 0; u < kMRing; ++u) {
-            const int s = s0 + u;
-            float x[4];
-            Fast<SrcT>::cvt_raw4(raw[u], x);
-            if (u % kMBatch == 0) {
-#pragma unroll
-                for (int j = 0; j < kMBatch; ++j) raw[(u + kMBatch + j) % kMRing] = fetch(s + kMBatch + j);
-            }
-            if (BORDER == MIE_BORDER_CONSTANT && (unsigned)(ty0 - kMR + s) >= (unsigned)h) {
-                x[0] = x[1] = x[2] = x[3] = 0.0f;
-            }
-            float* rowbuf = s_row + (u % 3) * pitch;
-            *reinterpret_cast<float4*>(my_buf + (u % 3) * pitch) = make_float4(x[0], x[1], x[2], x[3]);
-            march_halo<BORDER>(rowbuf, x, W, first_warp, last_warp, tid, T);
-            __syncthreads();
-            march_row_pass(rowbuf, tid, wx, ring[u][0], ring[u][1]);
-            if (!FIRST || u == kMRing - 1) {
-                float g[4];
-                march_col_pass(ring, (u + 1) % kMRing, wy, g);
-                if (LE1) {
-                    *reinterpret_cast<uint32_t*>(ip) =
-                        pack_low_bytes(fast_idx_bits_le1(g[0]), fast_idx_bits_le1(g[1]), fast_idx_bits_le1(g[2]),
-                                       fast_idx_bits_le1(g[3]));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) hist_add_le1(my_hist32, g[k]);
-                } else {
-                    *reinterpret_cast<uint32_t*>(ip) =
-                        pack_low_bytes(fast_idx_bits<NN>(g[0]), fast_idx_bits<NN>(g[1]), fast_idx_bits<NN>(g[2]),
-                                       fast_idx_bits<NN>(g[3]));
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) hist_add_nobranch(my_hist, fast_bin<NN>(g[k]));
-                }
-                ip += W;
-            }
+    // rows 2p, 2p+1 (ring slots rslot, rslot + 1); p even = first use of batch p / 2
+    auto convert = [&](const int p, const int rslot, float* x0, float* x1) {
+        if (p % 2 == 0) mbar_wait(bar32 + 8 * ((p / 2) % kRawBars), (uint32_t)((p / 2 / kRawBars) & 1));
+        const raw4 r0 = *reinterpret_cast<const raw4*>(my_raw + (rslot % kRawRows) * row_bytes);
+        const raw4 r1 = *reinterpret_cast<const raw4*>(my_raw + ((rslot + 1) % kRawRows) * row_bytes);
+        Fast<SrcT>::cvt_raw4(r0, x0);
+        Fast<SrcT>::cvt_raw4(r1, x1);
+        if (BORDER == MIE_BORDER_CONSTANT) {
+            if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
+            if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
         }
     };
-    nine(TrueC(), 0);
-    for (int s0 = kMRing; s0 < kMRows; s0 += kMRing) nine(FalseC(), s0);
+    // after the barrier of an odd row pair p its batch (p - 1) / 2 is consumed: refill the slots
+    auto refill = [&](const int p) {
+        const int b = (p - 1) / 2 + kRawBars;
+        if (tid == 0 && b < kMRows / kRawBatch) issue_batch(b);
+    };
+    auto emit = [&](const float* g) {
+        if (LE1) {
+            *reinterpret_cast<uint32_t*>(ip) =
+                pack_low_bytes(fast_idx_bits_le1(g[0]), fast_idx_bits_le1(g[1]), fast_idx_bits_le1(g[2]),
+                               fast_idx_bits_le1(g[3]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hist_add_le1(my_hist32, g[k]);
+        } else {
+            *reinterpret_cast<uint32_t*>(ip) =
+                pack_low_bytes(fast_idx_bits<NN>(g[0]), fast_idx_bits<NN>(g[1]), fast_idx_bits<NN>(g[2]),
+                               fast_idx_bits<NN>(g[3]));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hist_add_nobranch(my_hist, fast_bin<NN>(g[k]));
+        }
+        ip += W;
+    };
 
+    // ---- prologue: row pairs 0..3 fill ring slots 0..7
+#pragma unroll
+    for (int p = 0; p < kMPro; ++p) {
+        float x0[4], x1[4];
+        convert(p, 2 * p, x0, x1);
+        float* buf = s_buf + (p % 2) * pbuf;
+        pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+        __syncthreads();
+        if (p % 2 == 1) refill(p);
+        pair_row_pass(buf, T, tid, wx, ring, 2 * p);
+    }
+    // ---- main loop: 4 x 8 row pairs; pair q of an iteration = rows 8 + 16 i + 2q (+1) -> ring slots
+    //      8 + 2q (+1); the two rows that become complete are the ones eight rows above
+    for (int p0 = kMPro; p0 < kMPairs; p0 += kMUnroll) {
+#pragma unroll
+        for (int q = 0; q < kMUnroll; ++q) {
+            const int p = p0 + q;
+            float x0[4], x1[4];
+            convert(p, 2 * kMPro + 2 * q, x0, x1);
+            float* buf = s_buf + (q % 2) * pbuf;
+            pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+            __syncthreads();
+            if (q % 2 == 1) refill(p);
+            pair_row_pass(buf, T, tid, wx, ring, 2 * kMPro + 2 * q);
+            float g[4];
+            march_col_pass(ring, 2 * q, wy, g);
+            emit(g);
+            march_col_pass(ring, 2 * q + 1, wy, g);
+            emit(g);
+        }
+    }
     __syncthreads();
     uint8_t* luts = a.luts + (n * a.g.gh + ty) * (int64_t)gw * kBins;
     for (int t = warp; t < gw; t += nwarps)
@@ -200,10 +345,10 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
 // ================================================================ chain_b (marching, 9-tap unsharp)
 // grid = n * gh blocks of W/4 threads.  The band's 72 source rows lie in two rows of interpolation
 // cells; their 2 (gw+1) cell tables (2 KB each, contiguous in the workspace) are staged in shared
-// memory once.  Per source row: index bytes (two rows ahead) -> one 64-bit table lookup per pixel ->
-// CLAHE output C -> row buffer -> horizontal pass -> register ring -> vertical pass ->
-// C + (C - blur(C)) -> quantise -> one 64-bit store per thread.  The C values of the last nine rows
-// stay in the row-buffer ring, which is where the epilogue re-reads its centre pixels.
+// memory once.  Per row pair: index bytes (ahead) -> one 64-bit table lookup per pixel -> CLAHE output
+// C -> pair buffer -> horizontal pass -> register ring -> vertical pass -> C + (C - blur(C)) -> quantise
+// -> one 64-bit store per thread and row.  The C values of the last four row pairs stay in the
+// pair-buffer ring, which is where the epilogue re-reads its centre pixels.
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -214,9 +359,11 @@ template <typename DstT, int BORDER>
 __global__ void __launch_bounds__(256)
 chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy) {
     extern __shared__ __align__(16) float smem[];
-    const int W = a.g.w, T = blockDim.x, pitch = W + 8, gw = a.g.gw, gh = a.g.gh, h = a.g.h;
-    uint2* s_tab = reinterpret_cast<uint2*>(smem);       // 2 x (gw+1) x 256 entries
-    float* s_row = smem + 2 * (gw + 1) * kBins * 2;      // kMRing x pitch
+    const int W = a.g.w, T = blockDim.x, gw = a.g.gw, gh = a.g.gh, h = a.g.h;
+    const int pbuf = pairbuf_floats(T);
+    uint2* s_tab = reinterpret_cast<uint2*>(smem);            // 2 x (gw+1) x 256 entries
+    float* s_buf = smem + 2 * (gw + 1) * kBins * 2;           // 4 pair buffers
+    int* s_off = reinterpret_cast<int*>(s_buf + 4 * pbuf);    // kMOffRows
 
     const int tid = threadIdx.x, warp = tid >> 5, nwarps = T >> 5;
     const int ty = (int)(blockIdx.x % gh);
@@ -224,23 +371,35 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
     const int ty0 = ty * kTile;
     const bool first_warp = warp == 0, last_warp = warp == nwarps - 1;
 
-    const uint8_t* iplane = a.idx + n * (int64_t)h * W + 4 * tid;
-    auto fetch = [&](int s) -> uint32_t {
-        const int sy = march_src_row<BORDER>(ty0 - kMR + s, h);
-        if (BORDER == MIE_BORDER_CONSTANT && sy < 0) return 0u;
-        return __ldg(reinterpret_cast<const uint32_t*>(iplane + (unsigned)(sy * W)));
-    };
-    uint32_t raw[kMRing];
-#pragma unroll
-    for (int s = 0; s < kMBatch; ++s) raw[s] = fetch(s);
+    fill_row_offsets<BORDER>(s_off, ty0, h, W, tid, T);
     {
         const uint4* src = reinterpret_cast<const uint4*>(cells + (n * (gh + 1) + ty) * (int64_t)(gw + 1) * kBins);
         uint4* dst4 = reinterpret_cast<uint4*>(s_tab);
         const int total = 2 * (gw + 1) * kBins / 2;  // 16-byte pieces
         for (int i = tid; i < total; i += T) dst4[i] = __ldg(src + i);
     }
+    __syncthreads();
+
+    const uint8_t* iplane = a.idx + n * (int64_t)h * W + 4 * tid;
+    // raw[p % 8][j] = index word of row 2p + j, loaded 4..5 row pairs ahead of its use (one register
+    // per row, so depth is cheap here)
+    uint32_t raw[8][2];
+    auto fetch_pairs = [&](const int p, const int slot) {
+        const int4 o = *reinterpret_cast<const int4*>(s_off + 2 * p);
+        const int off[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t v = 0u;
+            if (BORDER != MIE_BORDER_CONSTANT || off[j] >= 0)
+                v = __ldg(reinterpret_cast<const uint32_t*>(iplane + (unsigned)off[j]));
+            raw[(slot + j / 2) % 8][j & 1] = v;
+        }
+    };
+    fetch_pairs(0, 0);
+    fetch_pairs(2, 2);
+
     // cells of this thread's columns: column cell (4t + 32) / 64; row cell 0 (rows above the tile
-    // centre line ty0 + 32) or 1.  Shared-window byte addresses, so a lookup is LEA + LDS.64.
+    // centre line ty0 + 32, i.e. band rows < 36) or 1.  Shared-window byte addresses: lookup = LEA + LDS.64.
     const uint32_t tb0 = (uint32_t)__cvta_generic_to_shared(s_tab + ((tid + 8) >> 4) * kBins);
     const uint32_t tb_step = (uint32_t)((gw + 1) * kBins * 8);
     float wxv[4];
@@ -248,53 +407,64 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
     for (int k = 0; k < 4; ++k) wxv[k] = aw.w[4 + ((4 * tid + k) & (kTile - 1))];
     DstT* op = (DstT*)a.dst + n * a.dsn + (int64_t)ty0 * a.dsh + 4 * tid;
     const int dsh = (int)a.dsh;
-    float2 ring[kMRing][2];
-    float* const my_buf = s_row + 4 + 4 * tid;
-    __syncthreads();  // tables staged
+    f32x2 ring[kMRing][2];
 
-    auto nine = [&](auto first_c, const int s0) {
-        constexpr bool FIRST = decltype(first_c)::value;
-        // Row cell: source rows at or below the tile centre line ty0 + 32 use the lower cell row.  Band
-        // row s maps to source row ty0 - 4 + s (or its mirror image, which lies in the same cell row), so
-        // the switch happens at s = 36 — a multiple of nine, i.e. between two calls of this lambda.
-        static_assert((kTile / 2 + kMR) % kMRing == 0, "cell-row switch must fall on a ring boundary");
-        const uint32_t tb = tb0 + (s0 >= kTile / 2 + kMR ? tb_step : 0u);
-#pragma unroll
-        for (int u = 0; u < kMRing; ++u) {
-            const int s = s0 + u;
-            const float wyv = aw.w[s];
-            const uint32_t iw = raw[u];
-            if (u % kMBatch == 0) {
-#pragma unroll
-                for (int j = 0; j < kMBatch; ++j) raw[(u + kMBatch + j) % kMRing] = fetch(s + kMBatch + j);
-            }
-            float x[4];
-            x[0] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4440) << 3)), wxv[0], wyv);
-            x[1] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4441) << 3)), wxv[1], wyv);
-            x[2] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4442) << 3)), wxv[2], wyv);
-            x[3] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4443) << 3)), wxv[3], wyv);
-            if (BORDER == MIE_BORDER_CONSTANT && (unsigned)(ty0 - kMR + s) >= (unsigned)h) {
-                x[0] = x[1] = x[2] = x[3] = 0.0f;
-            }
-            float* rowbuf = s_row + u * pitch;
-            *reinterpret_cast<float4*>(my_buf + u * pitch) = make_float4(x[0], x[1], x[2], x[3]);
-            march_halo<BORDER>(rowbuf, x, W, first_warp, last_warp, tid, T);
-            __syncthreads();
-            march_row_pass(rowbuf, tid, wx, ring[u][0], ring[u][1]);
-            if (!FIRST || u == kMRing - 1) {
-                float g[4];
-                march_col_pass(ring, (u + 1) % kMRing, wy, g);
-                const float4 c = *reinterpret_cast<const float4*>(my_buf + ((u + 5) % kMRing) * pitch);
-                float y[4];
-                y[0] = __fadd_rn(c.x, __fsub_rn(c.x, g[0])); y[1] = __fadd_rn(c.y, __fsub_rn(c.y, g[1]));
-                y[2] = __fadd_rn(c.z, __fsub_rn(c.z, g[2])); y[3] = __fadd_rn(c.w, __fsub_rn(c.w, g[3]));
-                Fast<DstT>::store4(op, y);
-                op += dsh;
-            }
+    auto clahe_row = [&](const uint32_t tb, const uint32_t iw, const float wyv, float* x) {
+        x[0] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4440) << 3)), wxv[0], wyv);
+        x[1] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4441) << 3)), wxv[1], wyv);
+        x[2] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4442) << 3)), wxv[2], wyv);
+        x[3] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4443) << 3)), wxv[3], wyv);
+    };
+    auto clahe_pair = [&](const int p, const int pslot, float* x0, float* x1) {
+        // both rows of a pair lie in the same cell row (the switch is at band row 36)
+        const uint32_t tb = tb0 + (2 * p >= kTile / 2 + kMR ? tb_step : 0u);
+        clahe_row(tb, raw[pslot][0], aw.w[2 * p], x0);
+        clahe_row(tb, raw[pslot][1], aw.w[2 * p + 1], x1);
+        if (BORDER == MIE_BORDER_CONSTANT) {
+            if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
+            if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
         }
     };
-    nine(TrueC(), 0);
-    for (int s0 = kMRing; s0 < kMRows; s0 += kMRing) nine(FalseC(), s0);
+
+#pragma unroll
+    for (int p = 0; p < kMPro; ++p) {
+        if (p % 2 == 0) fetch_pairs(p + 4, (p + 4) % 8);
+        float x0[4], x1[4];
+        clahe_pair(p, p % 8, x0, x1);
+        float* buf = s_buf + (p % 4) * pbuf;
+        pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+        __syncthreads();
+        pair_row_pass(buf, T, tid, wx, ring, 2 * p);
+    }
+    for (int p0 = kMPro; p0 < kMPairs; p0 += kMUnroll) {
+#pragma unroll
+        for (int q = 0; q < kMUnroll; ++q) {
+            const int p = p0 + q;
+            if (q % 2 == 0) fetch_pairs(p + 4, (kMPro + q + 4) % 8);
+            float x0[4], x1[4];
+            clahe_pair(p, (kMPro + q) % 8, x0, x1);
+            float* buf = s_buf + (q % 4) * pbuf;
+            pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+            __syncthreads();
+            pair_row_pass(buf, T, tid, wx, ring, 2 * kMPro + 2 * q);
+            // centre pixels of the two completed rows: rows (2p - 4, 2p - 3) = pair p - 2
+            const float* cbuf = s_buf + ((q + 2) % 4) * pbuf;
+            const float4 ca = *reinterpret_cast<const float4*>(cbuf + 4 * (tid + 1));
+            const float4 cb = *reinterpret_cast<const float4*>(cbuf + 4 * (T + 2) + 4 * (tid + 1));
+            const float c0[4] = {ca.x, ca.z, cb.x, cb.z}, c1[4] = {ca.y, ca.w, cb.y, cb.w};
+            float g[4], y[4];
+            march_col_pass(ring, 2 * q, wy, g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(c0[k], __fsub_rn(c0[k], g[k]));
+            Fast<DstT>::store4(op, y);
+            op += dsh;
+            march_col_pass(ring, 2 * q + 1, wy, g);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(c1[k], __fsub_rn(c1[k], g[k]));
+            Fast<DstT>::store4(op, y);
+            op += dsh;
+        }
+    }
 }
 
 // ================================================================ host side
@@ -305,9 +475,12 @@ bool march_chain_ok(const ClaheGeom& g, int kg, int ku) {
     return true;
 }
 
-static size_t march_a_smem(const ClaheGeom& g) { return (size_t)(3 * (g.w + 8) + g.gw * kHistPitch) * 4; }
+static size_t march_a_smem(const ClaheGeom& g, int elem_bytes) {
+    return (size_t)(2 * 8 * (g.w / 4 + 2) + g.gw * kHistPitch + kMOffRows) * 4 + kRawBars * 8 +
+           (size_t)kRawRows * g.w * elem_bytes;
+}
 static size_t march_b_smem(const ClaheGeom& g) {
-    return (size_t)(2 * (g.gw + 1) * kBins * 2 + kMRing * (g.w + 8)) * 4;
+    return (size_t)(2 * (g.gw + 1) * kBins * 2 + 4 * 8 * (g.w / 4 + 2) + kMOffRows) * 4;
 }
 
 // Blur of an all-ones image in the kernels' operation order.  Every fma is monotone in its data
@@ -324,8 +497,24 @@ static bool gauss_of_ones_le1(const Taps& wx, const Taps& wy) {
 
 template <typename SrcT, int BORDER, bool LE1>
 static int launch_a_march_tbl(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st) {
-    MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1>), 64 * 1024);
-    chain_a_march_kernel<SrcT, BORDER, LE1><<<blocks, a.g.w / 4, march_a_smem(a.g), st>>>(a, wx, wy);
+    // W <= 512: 128 threads per block, registers capped so that MINB blocks fit on an SM
+    static const int minb_env = [] { const char* e = getenv("MIE_MARCH_A_MINB"); return e ? atoi(e) : 5; }();
+    const size_t smem = march_a_smem(a.g, (int)sizeof(SrcT));
+    if (a.g.w <= 512) {
+        if (minb_env >= 6) {
+            MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 6>), 100 * 1024);
+            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 6><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy);
+        } else if (minb_env == 5) {
+            MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5>), 100 * 1024);
+            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy);
+        } else {
+            MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 4>), 100 * 1024);
+            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 4><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy);
+        }
+    } else {
+        MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2>), 100 * 1024);
+        chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy);
+    }
     return check_launch();
 }
 template <typename SrcT, int BORDER>

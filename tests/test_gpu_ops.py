@@ -198,8 +198,13 @@ def test_host_pipeline_equals_direct_call(dev):
     xh = torch.from_numpy(x).pin_memory()
     yh = torch.empty_like(xh).pin_memory()
     pipe = M.HostSlicePipeline(dev, (256, 256), torch.uint16, chunk=32, config=cfg)
-    for _ in range(2):                                                 # buffers are reused across runs
+    for _ in range(4):                              # buffers are reused: runs 2+ capture / replay a CUDA graph
         yh.zero_()
         pipe.run(xh, yh)
         assert np.array_equal(yh.numpy(), ref)
+    assert pipe._graph is not None
+    x2 = synthetic.phantom((70, 1, 256, 256), np.uint16, seed=13)      # new contents, same staging buffers
+    xh.copy_(torch.from_numpy(x2))
+    pipe.run(xh, yh)
+    assert np.array_equal(yh.numpy(), cpu(M.enhance_chain(gpu(x2, dev), cfg)))
     assert np.array_equal(M.enhance_chain_host(torch.from_numpy(x), cfg, device=dev).numpy(), ref)

@@ -241,6 +241,48 @@ def test_chain_geometries(dev, case, dtype):
     assert np.array_equal(got, ref), int((got != ref).sum())
 
 
+@pytest.mark.parametrize("case", [
+    dict(shape=(2, 1, 128, 128), grid=(2, 2)),                         # one warp per band, both image edges in it
+    dict(shape=(1, 1, 256, 1024), grid=(4, 16)),                       # 256 threads per band
+    dict(shape=(3, 1, 64, 256), grid=(1, 4)),                          # single band: top and bottom mirrored
+    dict(shape=(2, 1, 192, 384), grid=(3, 6)),
+    dict(shape=(2, 1, 128, 256), grid=(2, 4), border="replicate"),
+    dict(shape=(2, 1, 128, 256), grid=(2, 4), border="constant"),
+    dict(shape=(1, 1, 320, 512), grid=(5, 8), clip=0.0),
+])
+@pytest.mark.parametrize("dtype", [np.uint16, np.int16, np.uint8, np.float32])
+def test_chain_marching_kernels(dev, case, dtype):
+    """Geometries served by the marching kernels (64-px tiles, 9 taps, W % 128 == 0, W <= 1024):
+    bit-exact against the oracle for every dtype and border mode, integer and float output."""
+    import mie_b200 as M
+    import oracle as O
+
+    assert M._lib().mie_chain_is_fused(case["shape"][-2], case["shape"][-1], *case["grid"], 9, 9, 9, 9) == 2
+    for kind in ("P", "U", "K"):
+        x = images(kind, case["shape"], dtype, seed=7)
+        border, clip = case.get("border", "reflect"), case.get("clip", 2.0)
+        cfg = M.ChainConfig(grid_size=case["grid"], border_type=border, clip_limit=clip)
+        ref, st = O.chain_gauss_clahe_unsharp(x, 9, 1.0, clip, case["grid"], 9, 1.0, border, return_stages=True)
+        got = cpu(M.enhance_chain(gpu(x, dev), cfg))
+        assert np.array_equal(got, ref), (kind, int((got != ref).sum()))
+        gf = cpu(M.enhance_chain(gpu(x, dev), cfg, out_dtype=torch.float32))
+        assert np.array_equal(gf, st["unsharp"]), kind
+
+
+def test_chain_plan_graph_replay(dev):
+    """ChainPlan (CUDA-graph replay on fixed buffers) == enhance_chain, and follows new input contents."""
+    import mie_b200 as M
+
+    x = gpu(images("P", (5, 1, 512, 512), np.uint16, seed=1), dev)
+    plan = M.ChainPlan(x)
+    a = cpu(plan.replay()).copy()
+    assert np.array_equal(a, cpu(M.enhance_chain(x)))
+    x.copy_(gpu(images("U", (5, 1, 512, 512), np.uint16, seed=2), dev))
+    b = cpu(plan.replay())
+    assert np.array_equal(b, cpu(M.enhance_chain(x)))
+    assert not np.array_equal(a, b)
+
+
 def test_chain_full_config2_batch(dev):
     """BASELINE.json config 2 at full size (256 x 512 x 512 uint16): bit-exact against the oracle, and
     batch-independent (a checksum of per-slice checksums equals the one from slice-at-a-time calls)."""
