@@ -123,6 +123,17 @@ int mie_clahe(const void* src, void* dst, int src_dtype, int dst_dtype,
               int gh, int gw, double clip_limit, int semantics, float lo, float hi,
               void* workspace, size_t workspace_bytes, void* stream);
 
+/* 65 536-bin mode: semantics = MIE_CLAHE_OPENCV with MIE_U16 planes (cv::CLAHE on CV_16UC1; SURVEY.md
+ * §8(a) A1', §8(f) F2) — no quantisation to 256 levels, bit-exact against cv2.  mie_clahe accepts it
+ * (dst_dtype must be MIE_U16); the LUTs are uint16[n][gh][gw][65536] = mie_clahe16_lut_bytes(gh, gw)
+ * per image, and `workspace` must hold the LUTs of at least ONE image: the batch is processed in groups
+ * of floor(workspace_bytes / mie_clahe16_lut_bytes) images, so a workspace of a few images' LUTs keeps
+ * them in L2.  mie_clahe16_luts is the stage entry point for parity tests. */
+size_t mie_clahe16_lut_bytes(int gh, int gw);
+int mie_clahe16_luts(const void* src, int64_t n, int h, int w,
+                     int64_t src_stride_n, int64_t src_stride_h,
+                     int gh, int gw, double clip_limit, uint16_t* luts, void* stream);
+
 /* ------------------------------------------------------------------ global equalisation
  * Replaces kornia.enhance.equalize(input) == torchvision equalize rule
  * (reference pyproject.toml:8,16): 256-bin histogram of

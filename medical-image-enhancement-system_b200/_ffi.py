@@ -39,6 +39,8 @@ SIGNATURES = {
     "mie_clahe_luts": ([_p, _i, _i64, _i, _i, _i64, _i64, _i, _i, _d, _i, _f, _f, _p, _p], _i),
     "mie_clahe_apply": ([_p, _p, _i, _i, *_planes, _i, _i, _i, _f, _f, _p, _p], _i),
     "mie_clahe": ([_p, _p, _i, _i, *_planes, _i, _i, _d, _i, _f, _f, _p, _sz, _p], _i),
+    "mie_clahe16_lut_bytes": ([_i, _i], _sz),
+    "mie_clahe16_luts": ([_p, _i64, _i, _i, _i64, _i64, _i, _i, _d, _p, _p], _i),
     "mie_equalize_workspace_bytes": ([_i64], _sz),
     "mie_equalize": ([_p, _p, _i, _i, *_planes, _f, _f, _p, _sz, _p], _i),
     "mie_median2d": ([_p, _p, _i, *_planes, _i, _i, _i, _p], _i),

@@ -117,7 +117,7 @@ static int clahe_common_checks(const void* src, int sd, int64_t n, int h, int w,
     if (!valid_dtype(sd)) return MIE_E_DTYPE;
     if (ssh < w || (n > 1 && ssn < (int64_t)(h - 1) * ssh + w)) return MIE_E_STRIDE;
     if (semantics != MIE_CLAHE_KORNIA && semantics != MIE_CLAHE_OPENCV) return MIE_E_UNSUPPORTED;
-    if (semantics == MIE_CLAHE_OPENCV && sd != MIE_U8) return MIE_E_UNSUPPORTED;  // 65536-bin mode: not built yet
+    if (semantics == MIE_CLAHE_OPENCV && sd != MIE_U8) return MIE_E_UNSUPPORTED;  // uint16: mie_clahe / mie_clahe16_luts
     if (semantics == MIE_CLAHE_KORNIA && sd != MIE_F32 && !(hi > lo)) return MIE_E_RANGE;
     return make_clahe_geom(h, w, gh, gw, semantics, g);
 }
@@ -177,6 +177,11 @@ int clahe_apply_impl(const void* src, void* dst, int sd, int dd, int64_t n, int 
 
 }  // namespace mie
 
+namespace mie {
+int clahe16_impl(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int64_t dsn, int64_t dsh,
+                 int gh, int gw, double clip_limit, void* workspace, size_t workspace_bytes, cudaStream_t st);
+}
+
 using namespace mie;
 
 extern "C" {
@@ -214,6 +219,13 @@ int mie_clahe(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t 
               int64_t src_stride_n, int64_t src_stride_h, int64_t dst_stride_n, int64_t dst_stride_h, int gh, int gw,
               double clip_limit, int semantics, float lo, float hi, void* workspace, size_t workspace_bytes,
               void* stream) {
+    if (semantics == MIE_CLAHE_OPENCV && src_dtype == MIE_U16) {  // 65 536-bin mode (clahe16.cu)
+        if (dst_dtype != MIE_U16) return MIE_E_DTYPE;
+        int rc16 = check_planes(src, dst, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h);
+        if (rc16) return rc16;
+        return clahe16_impl(src, dst, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h, gh, gw,
+                            clip_limit, workspace, workspace_bytes, (cudaStream_t)stream);
+    }
     if (!workspace) return MIE_E_NULL;
     if (workspace_bytes < mie_clahe_workspace_bytes(n, h, w, gh, gw)) return MIE_E_WORKSPACE;
     int rc = clahe_luts_impl(src, src_dtype, n, h, w, src_stride_n, src_stride_h, gh, gw, clip_limit, semantics, lo,

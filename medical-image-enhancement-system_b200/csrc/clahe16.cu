@@ -1,0 +1,259 @@
+// clahe16.cu — CLAHE in OpenCV semantics for uint16 images: 65 536 bins, uint16 LUTs
+// (cv::CLAHE::apply on CV_16UC1; SURVEY.md §8(a) A1', §8(f) F2, Appendix A).  This is the only CLAHE
+// variant with an executable third-party oracle in the image (cv2 4.13), and the natural mode for
+// 12/16-bit CT / MR / X-ray data: no quantisation to 256 levels anywhere.
+//
+// A 65 536-bin histogram does not fit next to a block's other state as 32-bit counters (256 KB), and
+// 16-bit counters overflow for tiles of >= 65 536 pixels, so one block (1024 threads) owns one tile and
+// sweeps the grey range in two halves of 32 768 bins (128 KB of 32-bit shared-memory counters, padded
+// by one word per 32 so that "thread t owns bins 32t .. 32t+31" is bank-conflict free):
+//   phase A (only when clipping):  clipped = sum max(h - clip, 0)          -> redistribution batch / residual
+//   phase B:  h' = min(h, clip) + batch + residual term;  running prefix sum;  lut = sat(rint(cum * scale))
+// Each half re-reads the tile (8 KB .. 128 KB, L1/L2 resident); the 128 KB LUT per tile is written once
+// with 16-byte stores and stays in L2 for the interpolation pass, which gathers four uint16 entries
+// per pixel.  The caller's workspace bounds how many images' LUTs exist at a time (mie_clahe loops over
+// groups of images), so a batch never needs more LUT memory than fits in L2.
+#include "clahe.cuh"
+
+namespace mie {
+
+constexpr int kBins16 = 65536;
+constexpr int kHalf16 = 32768;
+constexpr int kThreads16 = 1024;
+constexpr int kOwn16 = kHalf16 / kThreads16;  // 32 consecutive bins per thread and half
+
+__device__ __forceinline__ int pad16(int i) { return i + (i >> 5); }
+
+struct Lut16Params {
+    int clip;         // per-bin ceiling (0 = clipping disabled)
+    float lut_scale;  // float(65535) / float(area)
+};
+
+// Histogram of one half of the grey range of the block's tile (reflect-101 padded beyond the image).
+__device__ __forceinline__ void tile_hist_half(const uint16_t* __restrict__ plane, int64_t ssh, const ClaheGeom& g,
+                                               int ty, int tx, int half, int* s_h) {
+    for (int i = threadIdx.x; i < kHalf16 + kHalf16 / 32; i += kThreads16) s_h[i] = 0;
+    __syncthreads();
+    const int area = g.th * g.tw;
+    for (int i = threadIdx.x; i < area; i += kThreads16) {
+        const int yy = i / g.tw, xx = i - yy * g.tw;
+        const int sy = border_index(ty * g.th + yy, g.h, MIE_BORDER_REFLECT);
+        const int sx = border_index(tx * g.tw + xx, g.w, MIE_BORDER_REFLECT);
+        const int v = plane[(int64_t)sy * ssh + sx];
+        if ((v >> 15) == half) atomicAdd(&s_h[pad16(v & (kHalf16 - 1))], 1);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int block_sum_1024(int v, int* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    int t = s_red[lane];
+    t = warp_sum(t);
+    return t;
+}
+
+// Exclusive prefix over the 1024 threads; *total receives the block sum.
+__device__ __forceinline__ int block_excl_scan_1024(int v, int* s_red, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_red[warp] = incl;
+    __syncthreads();
+    int wv = s_red[lane], winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+    }
+    const int warp_off = __shfl_sync(0xffffffffu, winc - wv, warp);
+    *total = __shfl_sync(0xffffffffu, winc, 31);
+    return warp_off + incl - v;
+}
+
+__global__ void __launch_bounds__(kThreads16)
+clahe16_lut_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, Lut16Params lp,
+                   uint16_t* __restrict__ luts) {
+    extern __shared__ __align__(16) int s_h[];  // kHalf16 + kHalf16/32 counters
+    __shared__ int s_red[32];
+    const int64_t tile = blockIdx.x;
+    const int tx = (int)(tile % g.gw), ty = (int)((tile / g.gw) % g.gh);
+    const int64_t n = tile / ((int64_t)g.gw * g.gh);
+    const uint16_t* plane = src + n * ssn;
+    const int tid = threadIdx.x;
+
+    int rb = 0, res = 0, step = 1;
+    if (lp.clip > 0) {
+        int local = 0;
+        for (int half = 0; half < 2; ++half) {
+            tile_hist_half(plane, ssh, g, ty, tx, half, s_h);
+#pragma unroll 8
+            for (int k = 0; k < kOwn16; ++k) local += max(s_h[tid * (kOwn16 + 1) + k] - lp.clip, 0);
+            __syncthreads();
+        }
+        const int clipped = block_sum_1024(local, s_red);
+        rb = clipped / kBins16;
+        res = clipped - rb * kBins16;
+        step = res ? max(kBins16 / res, 1) : 1;
+    }
+    int running = 0;
+    uint16_t* lut = luts + tile * (int64_t)kBins16;
+    for (int half = 0; half < 2; ++half) {
+        tile_hist_half(plane, ssh, g, ty, tx, half, s_h);
+        int hv[kOwn16];
+        const int u0 = half * kHalf16 + tid * kOwn16;
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < kOwn16; ++k) {
+            int c = s_h[tid * (kOwn16 + 1) + k];
+            if (lp.clip > 0) {
+                const int u = u0 + k;
+                const int q = u / step;
+                c = min(c, lp.clip) + rb + ((res && q * step == u && q < res) ? 1 : 0);
+            }
+            sum += c;
+            hv[k] = sum;  // inclusive within the thread
+        }
+        int total;
+        const int base = running + block_excl_scan_1024(sum, s_red, &total);
+        running += total;
+        uint32_t packed[kOwn16 / 2];
+#pragma unroll
+        for (int k = 0; k < kOwn16; k += 2) {
+            float f0 = rintf(__fmul_rn((float)(base + hv[k]), lp.lut_scale));
+            float f1 = rintf(__fmul_rn((float)(base + hv[k + 1]), lp.lut_scale));
+            f0 = fminf(fmaxf(f0, 0.0f), 65535.0f);
+            f1 = fminf(fmaxf(f1, 0.0f), 65535.0f);
+            packed[k / 2] = (uint32_t)(int)f0 | ((uint32_t)(int)f1 << 16);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(lut + u0);
+#pragma unroll
+        for (int k = 0; k < kOwn16 / 8; ++k)
+            dst[k] = make_uint4(packed[4 * k], packed[4 * k + 1], packed[4 * k + 2], packed[4 * k + 3]);
+        __syncthreads();
+    }
+}
+
+// Interpolation pass (cv::CLAHE_Interpolation_Body, fp32 in OpenCV's operation order): 4 pixels per thread.
+__global__ void __launch_bounds__(256)
+clahe16_apply_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                     int64_t dsh, ClaheGeom g, const uint16_t* __restrict__ luts) {
+    const int x0 = (blockIdx.x * 64 + (threadIdx.x & 63)) * 4;
+    const int y = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int64_t n = blockIdx.z;
+    if (y >= g.h || x0 >= g.w) return;
+    const uint16_t* srow = src + n * ssn + (int64_t)y * ssh;
+    uint16_t* drow = dst + n * dsn + (int64_t)y * dsh;
+    const uint16_t* nl = luts + n * (int64_t)g.gh * g.gw * kBins16;
+    int j0, j1;
+    float ya, ya1;
+    opencv_axis(y, __fdiv_rn(1.0f, (float)g.th), g.gh, j0, j1, ya, ya1);
+    const uint16_t* r0 = nl + (int64_t)j0 * g.gw * kBins16;
+    const uint16_t* r1 = nl + (int64_t)j1 * g.gw * kBins16;
+    const float inv_tw = __fdiv_rn(1.0f, (float)g.tw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int x = x0 + k;
+        if (x >= g.w) break;
+        int i0, i1;
+        float xa, xa1;
+        opencv_axis(x, inv_tw, g.gw, i0, i1, xa, xa1);
+        const int v = srow[x];
+        const float l11 = (float)__ldg(r0 + (int64_t)i0 * kBins16 + v), l12 = (float)__ldg(r0 + (int64_t)i1 * kBins16 + v);
+        const float l21 = (float)__ldg(r1 + (int64_t)i0 * kBins16 + v), l22 = (float)__ldg(r1 + (int64_t)i1 * kBins16 + v);
+        float res = rintf(opencv_blend(l11, l12, l21, l22, xa, xa1, ya, ya1));
+        res = fminf(fmaxf(res, 0.0f), 65535.0f);
+        drow[x] = (uint16_t)(int)res;
+    }
+}
+
+static Lut16Params make_lut16_params(const ClaheGeom& g, double clip_limit) {
+    Lut16Params p;
+    const int area = g.th * g.tw;
+    p.clip = 0;
+    if (clip_limit > 0.0) {
+        const double q = clip_limit * (double)area / (double)kBins16;
+        const int c = q > 2147483647.0 ? 2147483647 : (int)q;
+        p.clip = c < 1 ? 1 : c;
+    }
+    p.lut_scale = (float)(kBins16 - 1) / (float)area;
+    return p;
+}
+
+int clahe16_luts_impl(const void* src, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int gh, int gw,
+                      double clip_limit, uint16_t* luts, cudaStream_t st) {
+    if (n < 0 || h <= 0 || w <= 0) return MIE_E_SHAPE;
+    if (n > 0 && (!src || !luts)) return MIE_E_NULL;
+    if (ssh < w || (n > 1 && ssn < (int64_t)(h - 1) * ssh + w)) return MIE_E_STRIDE;
+    ClaheGeom g;
+    int rc = make_clahe_geom(h, w, gh, gw, MIE_CLAHE_OPENCV, &g);
+    if (rc) return rc;
+    if ((int64_t)g.th * g.tw > 2147483647LL / 2) return MIE_E_SHAPE;
+    const int64_t tiles = n * gh * gw;
+    if (tiles == 0) return MIE_OK;
+    if (tiles > 2147483647LL) return MIE_E_SHAPE;
+    const size_t smem = (size_t)(kHalf16 + kHalf16 / 32) * sizeof(int);
+    MIE_ENSURE_SMEM(clahe16_lut_kernel, smem);
+    clahe16_lut_kernel<<<(unsigned)tiles, kThreads16, smem, st>>>((const uint16_t*)src, ssn, ssh, g,
+                                                               make_lut16_params(g, clip_limit), luts);
+    return check_launch();
+}
+
+int clahe16_apply_impl(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int64_t dsn,
+                       int64_t dsh, int gh, int gw, const uint16_t* luts, cudaStream_t st) {
+    ClaheGeom g;
+    int rc = make_clahe_geom(h, w, gh, gw, MIE_CLAHE_OPENCV, &g);
+    if (rc) return rc;
+    if (n == 0) return MIE_OK;
+    if (n > 65535) return MIE_E_SHAPE;
+    dim3 grid(ceil_div(w, 256), ceil_div(h, 4), (unsigned)n);
+    clahe16_apply_kernel<<<grid, 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, ssn, ssh, dsn, dsh, g, luts);
+    return check_launch();
+}
+
+// luts + apply for a batch, LUTs of at most `group` images alive at a time.
+int clahe16_impl(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int64_t dsn, int64_t dsh,
+                 int gh, int gw, double clip_limit, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    const size_t per_image = (size_t)gh * gw * kBins16 * sizeof(uint16_t);
+    if (n == 0) return MIE_OK;
+    if (!workspace) return MIE_E_NULL;
+    if (workspace_bytes < per_image) return MIE_E_WORKSPACE;
+    int64_t group = (int64_t)(workspace_bytes / per_image);
+    if (group > 65535) group = 65535;
+    for (int64_t i0 = 0; i0 < n; i0 += group) {
+        const int64_t m = (n - i0) < group ? (n - i0) : group;
+        const uint16_t* s = (const uint16_t*)src + i0 * ssn;
+        uint16_t* d = (uint16_t*)dst + i0 * dsn;
+        int rc = clahe16_luts_impl(s, m, h, w, ssn, ssh, gh, gw, clip_limit, (uint16_t*)workspace, st);
+        if (rc) return rc;
+        rc = clahe16_apply_impl(s, d, m, h, w, ssn, ssh, dsn, dsh, gh, gw, (const uint16_t*)workspace, st);
+        if (rc) return rc;
+    }
+    return MIE_OK;
+}
+
+}  // namespace mie
+
+using namespace mie;
+
+extern "C" {
+
+size_t mie_clahe16_lut_bytes(int gh, int gw) {
+    if (gh <= 0 || gw <= 0) return 0;
+    return (size_t)gh * gw * kBins16 * sizeof(uint16_t);
+}
+
+int mie_clahe16_luts(const void* src, int64_t n, int h, int w, int64_t src_stride_n, int64_t src_stride_h, int gh,
+                     int gw, double clip_limit, uint16_t* luts, void* stream) {
+    return clahe16_luts_impl(src, n, h, w, src_stride_n, src_stride_h, gh, gw, clip_limit, luts, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -19,7 +19,10 @@ import torch
 from . import _ffi
 from ._ffi import CLAHE_KORNIA, CLAHE_OPENCV, DTYPE_CODE, as_planes, check, lib, require_cuda, stream_ptr, value_range_of
 
-__all__ = ["equalize_clahe", "equalize", "clahe_histograms", "clahe_luts", "clahe_apply"]
+__all__ = ["equalize_clahe", "equalize", "clahe_histograms", "clahe_luts", "clahe_apply", "clahe16_luts"]
+
+# LUT memory the 65 536-bin mode keeps alive at a time (a few images' LUTs: stays in the 126 MB L2)
+CLAHE16_WORKSPACE_BYTES = 64 << 20
 
 _SEMANTICS = {"kornia": CLAHE_KORNIA, "opencv": CLAHE_OPENCV}
 
@@ -48,10 +51,12 @@ def _out_like(x: torch.Tensor, out_dtype) -> torch.Tensor:
 def equalize_clahe(input: torch.Tensor, clip_limit: float = 40.0, grid_size: tuple = (8, 8),
                    slow_and_differentiable: bool = False, *, value_range=None, semantics: str = "kornia",
                    out_dtype=None) -> torch.Tensor:
-    """Contrast-limited adaptive histogram equalisation (256 bins).
+    """Contrast-limited adaptive histogram equalisation.
 
     Shapes (H,W), (C,H,W), (B,C,H,W); the result has the input's shape.
-    semantics='opencv' (uint8 only) reproduces cv2.createCLAHE bit for bit.
+    semantics='kornia': 256 bins on [0,1] data (kornia.enhance.equalize_clahe).
+    semantics='opencv': cv2.createCLAHE(clip_limit, (grid_size[1], grid_size[0])).apply, bit for bit —
+    256 bins for uint8 tensors, 65 536 bins for uint16 tensors (no quantisation of 12/16-bit data).
     """
     _check_clahe_args(clip_limit, grid_size)
     if slow_and_differentiable:
@@ -63,7 +68,11 @@ def equalize_clahe(input: torch.Tensor, clip_limit: float = 40.0, grid_size: tup
     gh, gw = int(grid_size[0]), int(grid_size[1])
     L = lib()
     with torch.cuda.device(x.device):
-        ws_bytes = L.mie_clahe_workspace_bytes(n, h, w, gh, gw)
+        if semantics == "opencv" and x.dtype == torch.uint16:
+            per_image = L.mie_clahe16_lut_bytes(gh, gw)
+            ws_bytes = per_image * max(1, min(n, CLAHE16_WORKSPACE_BYTES // max(per_image, 1)))
+        else:
+            ws_bytes = L.mie_clahe_workspace_bytes(n, h, w, gh, gw)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)
         check(L.mie_clahe(x.data_ptr(), dst.data_ptr(), DTYPE_CODE[x.dtype], DTYPE_CODE[dst.dtype], n, h, w,
                           h * w, w, h * w, w, gh, gw, float(clip_limit), _SEMANTICS[semantics], lo, hi,
@@ -95,6 +104,20 @@ def clahe_luts(input: torch.Tensor, clip_limit: float = 40.0, grid_size=(8, 8), 
     with torch.cuda.device(x.device):
         check(lib().mie_clahe_luts(x.data_ptr(), DTYPE_CODE[x.dtype], n, h, w, h * w, w, gh, gw, float(clip_limit),
                                    _SEMANTICS[semantics], lo, hi, luts.data_ptr(), stream_ptr(x.device)))
+    return luts
+
+
+def clahe16_luts(input: torch.Tensor, clip_limit: float = 40.0, grid_size=(8, 8)) -> torch.Tensor:
+    """Stage output of the 65 536-bin OpenCV mode: uint16 LUTs (*, gh, gw, 65536) of a uint16 tensor."""
+    require_cuda(input)
+    x, n, h, w = as_planes(input)
+    if x.dtype != torch.uint16:
+        raise TypeError("clahe16_luts takes uint16 tensors")
+    gh, gw = int(grid_size[0]), int(grid_size[1])
+    luts = torch.empty(x.shape[:-2] + (gh, gw, 65536), dtype=torch.uint16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().mie_clahe16_luts(x.data_ptr(), n, h, w, h * w, w, gh, gw, float(clip_limit), luts.data_ptr(),
+                                     stream_ptr(x.device)))
     return luts
 
 

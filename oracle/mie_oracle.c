@@ -383,6 +383,97 @@ int orc_clahe_apply_opencv_u8(const uint8_t* in, uint8_t* out, int64_t n, int h,
     return 0;
 }
 
+/* ------------------------------------------------------------------ CLAHE, OpenCV semantics (uint16, 65 536 bins)
+ * cv::CLAHE::apply on CV_16UC1 — SURVEY.md §8(a) A1', Appendix A (bit-exact against cv2 4.13,
+ * tests/test_oracle.py).  Same algorithm as the uint8 mode with bins = 65536:
+ * lutScale = float(65535) / float(area); clip = max(int(clipLimit * area / 65536), 1); the residual of
+ * the clipped mass goes to bins 0, step, 2 step, ... (step = max(65536 / residual, 1)).
+ * luts_out (optional) receives n * gh * gw * 65536 uint16 entries. */
+int orc_clahe_opencv_u16(const uint16_t* in, uint16_t* out, int64_t n, int h, int w, int gh, int gw,
+                         double clip_limit, uint16_t* luts_out) {
+    if (gh <= 0 || gw <= 0) return -5;
+    geom_t g;
+    opencv_geom(h, w, gh, gw, &g);
+    const int bins = 65536;
+    const int area = g.th * g.tw;
+    int clip = 0;
+    if (clip_limit > 0.0) {
+        double q = clip_limit * (double)area / (double)bins;
+        clip = q > 2147483647.0 ? 2147483647 : (int)q;
+        if (clip < 1) clip = 1;
+    }
+    const float lut_scale = (float)(bins - 1) / (float)area;
+    const float inv_th = 1.0f / (float)g.th, inv_tw = 1.0f / (float)g.tw;
+    int rc = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t i = 0; i < n; ++i) {
+        const uint16_t* img = in + (size_t)i * h * w;
+        uint16_t* o = out ? out + (size_t)i * h * w : NULL;
+        uint16_t* luts = luts_out ? luts_out + (size_t)i * gh * gw * bins
+                                  : (uint16_t*)malloc((size_t)gh * gw * bins * sizeof(uint16_t));
+        int* hv = (int*)malloc((size_t)bins * sizeof(int));
+        if (!luts || !hv) { rc = -20; free(hv); if (!luts_out) free(luts); continue; }
+        for (int ty = 0; ty < gh; ++ty)
+            for (int tx = 0; tx < gw; ++tx) {
+                memset(hv, 0, (size_t)bins * sizeof(int));
+                for (int y = ty * g.th; y < (ty + 1) * g.th; ++y) {
+                    int sy = border_index(y, h, B_REFLECT);
+                    for (int x = tx * g.tw; x < (tx + 1) * g.tw; ++x)
+                        hv[img[(size_t)sy * w + border_index(x, w, B_REFLECT)]] += 1;
+                }
+                if (clip > 0) {
+                    int clipped = 0;
+                    for (int b = 0; b < bins; ++b)
+                        if (hv[b] > clip) { clipped += hv[b] - clip; hv[b] = clip; }
+                    int rb = clipped / bins, res = clipped - rb * bins;
+                    for (int b = 0; b < bins; ++b) hv[b] += rb;
+                    if (res != 0) {
+                        int step = bins / res;
+                        if (step < 1) step = 1;
+                        for (int b = 0; b < bins && res > 0; b += step, --res) hv[b] += 1;
+                    }
+                }
+                uint16_t* lut = luts + ((size_t)ty * gw + tx) * bins;
+                int cum = 0;
+                for (int b = 0; b < bins; ++b) {
+                    cum += hv[b];
+                    float f = rintf((float)cum * lut_scale);
+                    f = fminf(fmaxf(f, 0.0f), 65535.0f);
+                    lut[b] = (uint16_t)(int)f;
+                }
+            }
+        if (o) {
+            for (int y = 0; y < h; ++y) {
+                float tyf = (float)y * inv_th - 0.5f;
+                int ty1 = (int)floorf(tyf);
+                float ya = tyf - (float)ty1, ya1 = 1.0f - ya;
+                int ty2 = ty1 + 1;
+                if (ty1 < 0) ty1 = 0;
+                if (ty2 > gh - 1) ty2 = gh - 1;
+                for (int x = 0; x < w; ++x) {
+                    float txf = (float)x * inv_tw - 0.5f;
+                    int tx1 = (int)floorf(txf);
+                    float xa = txf - (float)tx1, xa1 = 1.0f - xa;
+                    int tx2 = tx1 + 1;
+                    if (tx1 < 0) tx1 = 0;
+                    if (tx2 > gw - 1) tx2 = gw - 1;
+                    int v = img[(size_t)y * w + x];
+                    float l11 = luts[((size_t)ty1 * gw + tx1) * bins + v], l12 = luts[((size_t)ty1 * gw + tx2) * bins + v];
+                    float l21 = luts[((size_t)ty2 * gw + tx1) * bins + v], l22 = luts[((size_t)ty2 * gw + tx2) * bins + v];
+                    float top = l11 * xa1 + l12 * xa;
+                    float bot = l21 * xa1 + l22 * xa;
+                    float res = rintf(top * ya1 + bot * ya);
+                    res = fminf(fmaxf(res, 0.0f), 65535.0f);
+                    o[(size_t)y * w + x] = (uint16_t)(int)res;
+                }
+            }
+        }
+        free(hv);
+        if (!luts_out) free(luts);
+    }
+    return rc;
+}
+
 /* ------------------------------------------------------------------ median (pure selection)
  * 2-D: kornia.filters.median_blur (zero padding; torch.median = lower median, the
  * true median for odd windows) / skimage.filters.median 2-D ('nearest');

@@ -54,6 +54,7 @@ class _Sig:
     orc_clahe_hist_opencv_u8 = ([_p, _i64, _i, _i, _i, _i, _p], _i)
     orc_clahe_luts_from_hist_opencv = ([_p, _i64, _i, _i, _d, _p], _i)
     orc_clahe_apply_opencv_u8 = ([_p, _p, _i64, _i, _i, _i, _i, _p], _i)
+    orc_clahe_opencv_u16 = ([_p, _p, _i64, _i, _i, _i, _i, _d, _p], _i)
     orc_median2d = ([_p, _p, _i64, _i, _i, _i, _i, _i], _i)
     orc_median3d = ([_p, _p, _i, _i, _i, _p, _p, _i], _i)
     orc_exp = ([_p, _p, _i64], None)
@@ -213,8 +214,22 @@ def opencv_clahe_luts(img, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
     return luts
 
 
+def opencv_clahe16(img, clip_limit=40.0, grid_size=(8, 8), return_luts=False):
+    """cv2.createCLAHE(clipLimit, tileGridSize=(gw, gh)).apply(img) for uint16 (65 536 bins)."""
+    x, n, h, w = _planes(img, np.uint16)
+    gh, gw = grid_size
+    out = np.empty_like(x)
+    luts = np.empty((n, gh, gw, 65536), np.uint16) if return_luts else None
+    _check(lib().orc_clahe_opencv_u16(_ptr(x), _ptr(out), n, h, w, gh, gw, float(clip_limit),
+                                      _ptr(luts) if return_luts else None))
+    out = out.reshape(np.asarray(img).shape)
+    return (out, luts) if return_luts else out
+
+
 def opencv_clahe(img, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
     """cv2.createCLAHE(clipLimit, tileGridSize=(gw, gh)).apply(img) for uint8; grid_size is (rows, cols)."""
+    if np.asarray(img).dtype == np.uint16:
+        return opencv_clahe16(img, clip_limit, grid_size)
     x, n, h, w = _planes(img, np.uint8)
     gh, gw = grid_size
     luts = opencv_clahe_luts(x, clip_limit, grid_size)

@@ -132,6 +132,70 @@ def test_clahe_opencv_semantics_matches_cv2(dev):
         assert np.array_equal(got, ref), (h, w, g, clip, int((got != ref).sum()))
 
 
+# ---------------------------------------------------------------------------- CLAHE, OpenCV semantics, 65 536 bins
+def _cv2_cases():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cv2_clahe.json")) as f:
+        return json.load(f)["cases"]
+
+
+def _golden_sha(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(str(a.dtype).encode() + str(a.shape).encode() + a.tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", sorted(_cv2_cases()))
+def test_clahe_opencv_reproduces_committed_cv2_vectors(dev, name):
+    """CUDA path vs the vectors cv2.createCLAHE produced (tests/golden/make_cv2_golden.py): bit-exact,
+    for uint8 (256 bins) and uint16 (65 536 bins); and equal to the oracle incl. the uint16 LUTs."""
+    import os
+    import sys
+    import mie_b200 as M
+    import oracle as O
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from cv2_inputs import image
+
+    c = _cv2_cases()[name]
+    img = image(c["h"], c["w"], np.dtype(c["dtype"]), c["seed"], c["bits"])
+    grid = tuple(c["grid"])
+    got = cpu(M.equalize_clahe(gpu(img, dev), float(c["clip"]), grid, semantics="opencv"))
+    assert _golden_sha(got) == c["output_sha256"]
+    if c["dtype"] == "uint16":
+        ref, luts = O.opencv_clahe16(img, c["clip"], grid, return_luts=True)
+        assert np.array_equal(got, ref)
+        assert np.array_equal(cpu(M.clahe16_luts(gpu(img, dev), float(c["clip"]), grid)), luts[0])
+
+
+def test_clahe16_batches_groups_and_edge_images(dev):
+    """Batches larger than the LUT workspace (processed in groups), constant / extreme images, tiles of
+    more than 65 535 equal pixels (a 16-bit counter would wrap), strided batches."""
+    import mie_b200 as M
+    from mie_b200 import enhance as E
+    import oracle as O
+
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 4096, (5, 1, 128, 192), dtype=np.uint16)
+    x[1] = 777
+    x[2] = 0
+    x[3] = 65535
+    ref = O.opencv_clahe(x, 2.0, (4, 4))
+    old = E.CLAHE16_WORKSPACE_BYTES
+    try:
+        for budget in (old, 2 * 16 * 131072 + 5, 1):       # all at once / groups of 2 / one image at a time
+            E.CLAHE16_WORKSPACE_BYTES = budget
+            assert np.array_equal(cpu(M.equalize_clahe(gpu(x, dev), 2.0, (4, 4), semantics="opencv")), ref)
+    finally:
+        E.CLAHE16_WORKSPACE_BYTES = old
+    big = np.full((1, 1, 512, 512), 1234, np.uint16)         # one 262 144-pixel tile, single grey level
+    for clip in (2.0, 0.0):
+        assert np.array_equal(cpu(M.equalize_clahe(gpu(big, dev), clip, (1, 1), semantics="opencv")),
+                              O.opencv_clahe(big, clip, (1, 1)))
+    with pytest.raises((ValueError, TypeError, RuntimeError)):
+        M.equalize_clahe(gpu(x.astype(np.int16), dev), 2.0, (4, 4), semantics="opencv")
+
+
 # ---------------------------------------------------------------------------- Gaussian / unsharp
 GAUSS_CASES = [
     # (shape, kernel_size, sigma, border)

@@ -34,6 +34,66 @@ def test_opencv_clahe_oracle_is_bit_exact_against_cv2(h, w, grid, clip):
     assert np.array_equal(O.opencv_clahe(img, clip, grid), ref)
 
 
+def smooth_u16(h, w, seed=0, bits=16):
+    """Smooth-plus-noise image using `bits` of a uint16 container (12 = CT-like occupancy)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = 0.5 + 0.23 * np.sin(xx / 37.0) + 0.2 * np.cos(yy / 23.0) + rng.normal(0, 0.05, (h, w))
+    return (np.clip(img, 0, 1) * (2 ** bits - 1)).astype(np.uint16)
+
+
+@pytest.mark.parametrize("h,w,grid,clip,bits", [
+    (512, 512, (8, 8), 2.0, 16), (512, 512, (8, 8), 40.0, 16), (300, 500, (8, 8), 2.0, 16), (1024, 1024, (16, 16), 2.0, 12),
+    (512, 512, (8, 8), 0.0, 16), (512, 512, (4, 4), 300.0, 12), (37, 53, (3, 5), 1.5, 16), (64, 64, (8, 8), 0.3, 16),
+    (512, 512, (2, 2), 2.0, 8), (256, 256, (1, 1), 2.0, 4), (512, 512, (8, 8), 40000.0, 12)])
+def test_opencv_clahe16_oracle_is_bit_exact_against_cv2(h, w, grid, clip, bits):
+    """The 65 536-bin mode of cv::CLAHE (uint16 in, uint16 out): includes tiles of >= 65 536 pixels
+    (2x2 and 1x1 grids), few-level images (heavy clipping) and a clip limit that never binds."""
+    cv2 = pytest.importorskip("cv2")
+    img = smooth_u16(h, w, seed=3, bits=bits)
+    ref = cv2.createCLAHE(clip, (grid[1], grid[0])).apply(img)
+    assert np.array_equal(O.opencv_clahe(img, clip, grid), ref)
+
+
+def test_opencv_clahe16_constant_and_extremes_against_cv2():
+    cv2 = pytest.importorskip("cv2")
+    for img in (np.full((128, 128), 777, np.uint16), np.zeros((128, 128), np.uint16),
+                np.full((128, 128), 65535, np.uint16),
+                np.random.default_rng(5).integers(0, 65536, (128, 192), dtype=np.uint16)):
+        for clip in (2.0, 0.0):
+            ref = cv2.createCLAHE(clip, (4, 4)).apply(img)
+            assert np.array_equal(O.opencv_clahe(img, clip, (4, 4)), ref)
+
+
+def _cv2_golden_cases():
+    with open(os.path.join(GOLDEN, "cv2_clahe.json")) as f:
+        return json.load(f)["cases"]
+
+
+def _sha(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(str(a.dtype).encode() + str(a.shape).encode() + a.tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("name", sorted(_cv2_golden_cases()))
+def test_oracle_reproduces_committed_cv2_vectors(name):
+    """tests/golden/cv2_clahe.json holds sha256 of cv2.createCLAHE outputs (made by make_cv2_golden.py):
+    the oracle must reproduce them without cv2 being importable (the GPU box runs the same check)."""
+    sys_path_golden = os.path.join(GOLDEN)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_cv2_golden_inputs", os.path.join(sys_path_golden, "cv2_inputs.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    c = _cv2_golden_cases()[name]
+    img = mod.image(c["h"], c["w"], np.dtype(c["dtype"]), c["seed"], c["bits"])
+    assert _sha(img) == c["input_sha256"]
+    assert _sha(O.opencv_clahe(img, c["clip"], tuple(c["grid"]))) == c["output_sha256"]
+
+
+def test_oracle_reproduces_cv2_fixture():
+    z = np.load(os.path.join(GOLDEN, "cv2_clahe16_128.npz"))
+    assert np.array_equal(O.opencv_clahe(z["input"], float(z["clip"]), tuple(int(v) for v in z["grid"])), z["output"])
+
+
 # ---------------------------------------------------------------------------- A1 kornia CLAHE vs twin
 @pytest.mark.parametrize("h,w,grid,clip", [
     (512, 512, (8, 8), 2.0), (64, 64, (8, 8), 40.0), (100, 130, (4, 6), 2.0), (20, 20, (8, 8), 1.0),
