@@ -52,6 +52,9 @@ def main():
     report("C1 clahe 1x512x512 u16 (python call -> 2 launches)", 512 * 512, ms, latency_us=round(ms * 1e3, 1))
     ms = timed(lambda: M.enhance_chain(x1), 200)
     report("C1' chain 1x512x512 u16 (3 launches)", 512 * 512, ms, latency_us=round(ms * 1e3, 1))
+    ms = timed(lambda: M.equalize_clahe(x1, 2.0, (8, 8), semantics="opencv"), 100)
+    report("C1 clahe 1x512x512 u16, OpenCV semantics, 65536 bins (cv2: ~20 ms on 8 threads)", 512 * 512, ms,
+           latency_us=round(ms * 1e3, 1))
 
     # C2 pieces: the standalone ops on the config-2 batch
     x2 = torch.from_numpy(synthetic.phantom((256, 1, 512, 512), np.uint16, 0)).to(dev)
@@ -62,7 +65,16 @@ def main():
     report("C2 equalize_clahe 8x8 u16->u16", px2, timed(lambda: M.equalize_clahe(x2, 2.0, (8, 8)), reps))
     report("C2 equalize (global) u16->u16", px2, timed(lambda: M.equalize(x2), reps))
     report("C2 median_blur 3x3 u16", px2, timed(lambda: M.median_blur(x2, 3), reps))
+    report("C2 equalize_clahe 8x8 u16, OpenCV semantics, 65536 bins (64 MB LUT workspace)", px2,
+           timed(lambda: M.equalize_clahe(x2, 2.0, (8, 8), semantics="opencv"), max(reps // 4, 2)))
     del x2
+
+    # C5: non-local means 7x7 patches, search radius 11, on 256x256 slices (batch 512; sample when --quick)
+    nb5 = 64 if args.quick else 512
+    x5 = torch.from_numpy(synthetic.phantom((nb5, 1, 256, 256), np.uint16, 0)).to(dev)
+    report(f"C5 denoise_nl_means 7x7 d=11 {nb5}x256x256 u16", nb5 * 256 * 256,
+           timed(lambda: M.denoise_nl_means(x5, 7, 11, 0.1), 2, warm=1))
+    del x5
 
     # C3: 512^3 int16 volume, 3x3x3 median + per-slice CLAHE (one GPU = one slab with no halos)
     d = 128 if args.quick else 512

@@ -180,6 +180,20 @@ int mie_bilateral(const void* src, void* dst, int src_dtype, int dst_dtype,
                   const float* wspace, int ky, int kx, float sigma_color, int border,
                   float lo, float hi, void* stream);
 
+/* ------------------------------------------------------------------ non-local means
+ * Replaces skimage.restoration.denoise_nl_means(image, patch_size, patch_distance, h,
+ * fast_mode=True, sigma) on 2-D single-channel planes (reference pyproject.toml:12; SURVEY.md §8(a)
+ * A8; BASELINE.json config 5).  Fast-mode semantics restated in csrc/nlm.cu: uniform patch weights,
+ * search window [-patch_distance, patch_distance]^2 over the reflect-padded image, weight
+ * exp(-max(D,0) / (h^2 s^2)) cut off at distance 5.  patch_size <= 9, patch_distance <= 16.
+ * fp32 arithmetic, within rel 1e-5 of the float64 oracle (not bit-exact: exp is ex2.approx).       */
+int mie_nlm(const void* src, void* dst, int src_dtype, int dst_dtype,
+            int64_t n, int h, int w,
+            int64_t src_stride_n, int64_t src_stride_h,
+            int64_t dst_stride_n, int64_t dst_stride_h,
+            int patch_size, int patch_distance, float h_param, float sigma,
+            float lo, float hi, void* stream);
+
 /* ------------------------------------------------------------------ fused chain (BASELINE.json config 2)
  * Gaussian denoise -> CLAHE -> unsharp mask in two launches; equals
  * mie_gaussian2d -> mie_clahe -> mie_unsharp (F32 intermediates) bit for bit.

@@ -9,7 +9,7 @@ include/mie.h; there is no CPU or PyTorch fallback.
 from ._ffi import lib as _lib  # noqa: F401
 from .chain import ChainConfig, ChainPlan, chain_workspace_bytes, enhance_chain
 from .enhance import clahe16_luts, clahe_apply, clahe_histograms, clahe_luts, equalize, equalize_clahe
-from .filters import bilateral_blur, gaussian_blur2d, get_gaussian_kernel1d, median, median_blur, unsharp_mask
+from .filters import bilateral_blur, denoise_nl_means, gaussian_blur2d, get_gaussian_kernel1d, median, median_blur, unsharp_mask
 from .loader import HostSlicePipeline, enhance_chain_host
 from .volume import exchange_z_halos, median3d_clahe_slab, shard_range, start_z_halo_exchange
 
@@ -18,6 +18,7 @@ __version__ = "0.1.0"
 __all__ = [
     "equalize_clahe", "equalize", "clahe_histograms", "clahe_luts", "clahe_apply", "clahe16_luts",
     "gaussian_blur2d", "unsharp_mask", "median_blur", "bilateral_blur", "median", "get_gaussian_kernel1d",
+    "denoise_nl_means",
     "ChainConfig", "ChainPlan", "enhance_chain", "chain_workspace_bytes",
     "HostSlicePipeline", "enhance_chain_host",
     "shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab",

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mie_median2d": ([_p, _p, _i, *_planes, _i, _i, _i, _p], _i),
     "mie_median3d": ([_p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _i, _p], _i),
     "mie_bilateral": ([_p, _p, _i, _i, *_planes, _p, _i, _i, _f, _i, _f, _f, _p], _i),
+    "mie_nlm": ([_p, _p, _i, _i, *_planes, _i, _i, _f, _f, _f, _f, _p], _i),
     "mie_chain_workspace_bytes": ([_i64, _i, _i, _i, _i], _sz),
     "mie_chain_gauss_clahe_unsharp": (
         [_p, _p, _i, _i, *_planes, *_taps, _i, _i, _d, *_taps, _i, _f, _f, _i, _p, _sz, _p], _i),

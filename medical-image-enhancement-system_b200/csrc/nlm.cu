@@ -1,0 +1,163 @@
+// nlm.cu — non-local means denoising, skimage.restoration.denoise_nl_means(fast_mode=True) semantics
+// (scikit-image 0.26.0, reference pyproject.toml:12 / uv.lock:619-650; SURVEY.md §8(a) A8, BASELINE.json
+// config 5's "else" branch: 7x7 patches on 256x256 slices).  The upstream source is not on disk; the
+// algorithm below restates its published fast mode (Darbon et al., ISBI 2008, integral images) [RECALLED]:
+//
+//   s = patch_size (+1 if even), o = s / 2, d = patch_distance, I = image reflect-padded by o + d + 1
+//   out(p) = sum_t c_t w_t(p) I(p + t) / sum_t c_t w_t(p),      t in [-d, d]^2,  c_0 = 2, c_t = 1 otherwise
+//   w_t(p) = exp(-dist) if dist <= 5 else 0,   dist = max(D, 0) / (h^2 s^2)
+//   D      = sum_{q in (-o, o]^2} ((I(p + q) - I(p + q + t))^2 - 2 sigma^2)
+// (the box of the upstream integral-image difference spans rows/columns p - o + 1 .. p + o, i.e.
+// (s - 1)^2 pixels, and the centre pixel is accumulated twice — both quirks are kept).
+//
+// This op is compute bound outright: (2d+1)^2 = 529 shifts per pixel.  One block owns
+// a 32x32 output tile with its (32 + 2(o + d))^2 neighbourhood in shared memory; per shift it forms the
+// squared differences once, sums them separably (horizontal sliding sums into shared memory, vertical
+// sums in registers) and accumulates the weighted shifted pixel — ~35 instructions per pixel and shift
+// instead of ~110 for the direct 36-term patch distance.  exp() is ex2.approx (MUFU): the result is
+// within the north star's fp32 tolerance (rel 1e-5) of the float64 oracle, not bit-exact.
+#include "mie_common.cuh"
+
+namespace mie {
+
+constexpr int kNlmTile = 32;
+constexpr int kNlmMaxO = 4;    // patch size <= 9
+constexpr int kNlmMaxD = 16;   // patch distance <= 16
+
+struct NlmArgs {
+    int h, w, tiles_x, tiles_y;
+    int o, d;
+    float inv_h2s2;   // 1 / (h^2 s^2)
+    float var_term;   // (s-1)^2 * 2 sigma^2
+    float lo, rg;
+};
+
+template <typename SrcT, typename DstT, int O>
+__global__ void __launch_bounds__(256)
+nlm_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn, int64_t dsh,
+           NlmArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int T = kNlmTile;
+    constexpr int o = O;
+    const int d = a.d, R = o + d;
+    const int E = T + 2 * R, pitch = E | 1;      // neighbourhood edge, odd pitch
+    const int HR = T + 2 * o - 1;                // rows of horizontal sums: tile rows -o+1 .. T-1+o
+    float* S = smem;                             // E x pitch
+    float* H = smem + E * pitch;                 // HR x (T + 1)
+    const int64_t tile = blockIdx.x;
+    const int tx0 = (int)(tile % a.tiles_x) * T, ty0 = (int)((tile / a.tiles_x) % a.tiles_y) * T;
+    const int64_t n = tile / ((int64_t)a.tiles_x * a.tiles_y);
+    const SrcT* plane = src + n * ssn;
+    for (int i = threadIdx.x; i < E * E; i += 256) {
+        const int r = i / E, c = i - r * E;
+        const int sy = border_index(ty0 - R + r, a.h, MIE_BORDER_REFLECT);
+        const int sx = border_index(tx0 - R + c, a.w, MIE_BORDER_REFLECT);
+        S[r * pitch + c] = Px<SrcT>::to01(plane[(int64_t)sy * ssh + sx], a.lo, a.rg);
+    }
+    __syncthreads();
+
+    // stage-2 ownership: column lx, rows ly0 + 8k (k = 0..3)
+    const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
+    float num[4] = {0.f, 0.f, 0.f, 0.f}, den[4] = {0.f, 0.f, 0.f, 0.f};
+    // stage-1 ownership: (row hy of H, 8-column segment hs); HR * 4 items over 256 threads
+    constexpr int box = 2 * O;                   // pixels per box side
+    const float neg_log2e = -1.4426950408889634f;
+
+    for (int ty = -d; ty <= d; ++ty) {
+        for (int tx = -d; tx <= d; ++tx) {
+            // ---- horizontal sums of squared differences
+            for (int it = threadIdx.x; it < HR * 4; it += 256) {
+                const int hy = it >> 2, hs = it & 3;
+                const float* p = S + (hy + 1 + d) * pitch + (8 * hs + 1 + d);   // tile row hy - o + 1, column 8hs - o + 1
+                const float* q = p + ty * pitch + tx;
+                float d2[8 + box - 1];
+#pragma unroll
+                for (int k = 0; k < 8 + box - 1; ++k) {
+                    const float df = p[k] - q[k];
+                    d2[k] = df * df;
+                }
+                float* hrow = H + hy * (T + 1) + 8 * hs;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float sacc = d2[j];
+#pragma unroll
+                    for (int k = 1; k < box; ++k) sacc += d2[j + k];
+                    hrow[j] = sacc;
+                }
+            }
+            __syncthreads();
+            // ---- vertical sums, weights, accumulation
+            const float cmul = (ty == 0 && tx == 0) ? 2.0f : 1.0f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int oy = ly0 + 8 * k;
+                float D = H[oy * (T + 1) + lx];
+#pragma unroll
+                for (int j = 1; j < box; ++j) D += H[(oy + j) * (T + 1) + lx];
+                const float dist = fmaxf(D - a.var_term, 0.0f) * a.inv_h2s2;
+                if (dist <= 5.0f) {
+                    const float wgt = cmul * exp2f(dist * neg_log2e);
+                    num[k] = fmaf(wgt, S[(oy + R + ty) * pitch + lx + R + tx], num[k]);
+                    den[k] += wgt;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    const int x = tx0 + lx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = ty0 + ly0 + 8 * k;
+        if (y < a.h && x < a.w) dst[n * dsn + (int64_t)y * dsh + x] = Px<DstT>::from01(num[k] / den[k], a.lo, a.rg);
+    }
+}
+
+int nlm_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
+             int64_t dsn, int64_t dsh, int patch_size, int patch_distance, float hpar, float sigma, float lo, float hi,
+             cudaStream_t st) {
+    int rc = check_planes(src, dst, n, h, w, ssn, ssh, dsn, dsh);
+    if (rc) return rc;
+    rc = check_dtypes(sd, dd, lo, hi);
+    if (rc) return rc;
+    if (patch_size <= 0 || patch_distance < 0) return MIE_E_KERNEL;
+    const int s = patch_size + (patch_size % 2 == 0 ? 1 : 0);
+    const int o = s / 2;
+    if (o < 1 || o > kNlmMaxO || patch_distance > kNlmMaxD) return MIE_E_KERNEL;
+    if (!(hpar > 0.0f) || sigma < 0.0f) return MIE_E_RANGE;
+    // numpy 'reflect' padding by o + d + 1 must be a single reflection
+    if (o + patch_distance + 1 >= h || o + patch_distance + 1 >= w) return MIE_E_BORDER;
+    if (n == 0) return MIE_OK;
+    NlmArgs a;
+    a.h = h; a.w = w; a.tiles_x = ceil_div(w, kNlmTile); a.tiles_y = ceil_div(h, kNlmTile);
+    a.o = o; a.d = patch_distance;
+    a.inv_h2s2 = (float)(1.0 / ((double)hpar * hpar * s * s));
+    a.var_term = (float)((double)(2 * o) * (2 * o) * 2.0 * (double)sigma * sigma);
+    a.lo = lo; a.rg = hi - lo;
+    const int64_t blocks = n * a.tiles_x * a.tiles_y;
+    if (blocks > 2147483647LL) return MIE_E_SHAPE;
+    const int E = kNlmTile + 2 * (o + patch_distance);
+    const size_t smem = (size_t)(E * (E | 1) + (kNlmTile + 2 * o - 1) * (kNlmTile + 1)) * 4;
+#define MIE_NLM_LAUNCH(O_)                                                                               \
+    MIE_ENSURE_SMEM((nlm_kernel<SrcT, DstT, O_>), 64 * 1024);                                            \
+    nlm_kernel<SrcT, DstT, O_><<<(unsigned)blocks, 256, smem, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, dsn, dsh, a)
+    switch (o) {
+        case 1: MIE_DISPATCH_SRC_DST(sd, dd, MIE_NLM_LAUNCH(1)); break;
+        case 2: MIE_DISPATCH_SRC_DST(sd, dd, MIE_NLM_LAUNCH(2)); break;
+        case 3: MIE_DISPATCH_SRC_DST(sd, dd, MIE_NLM_LAUNCH(3)); break;
+        default: MIE_DISPATCH_SRC_DST(sd, dd, MIE_NLM_LAUNCH(4)); break;
+    }
+#undef MIE_NLM_LAUNCH
+    return check_launch();
+}
+
+}  // namespace mie
+
+using namespace mie;
+
+extern "C" int mie_nlm(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t n, int h, int w,
+                       int64_t src_stride_n, int64_t src_stride_h, int64_t dst_stride_n, int64_t dst_stride_h,
+                       int patch_size, int patch_distance, float h_param, float sigma, float lo, float hi,
+                       void* stream) {
+    return nlm_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h,
+                    patch_size, patch_distance, h_param, sigma, lo, hi, (cudaStream_t)stream);
+}

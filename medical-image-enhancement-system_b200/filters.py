@@ -146,6 +146,30 @@ def bilateral_blur(input: torch.Tensor, kernel_size, sigma_color, sigma_space, b
     return dst
 
 
+def denoise_nl_means(image: torch.Tensor, patch_size: int = 7, patch_distance: int = 11, h: float = 0.1,
+                     channel_axis=None, fast_mode: bool = True, sigma: float = 0.0, *, preserve_range: bool = False,
+                     value_range=None, out_dtype=None) -> torch.Tensor:
+    """skimage.restoration.denoise_nl_means on 2-D planes ((H,W), (C,H,W), (B,C,H,W): every plane is
+    filtered on its own).  Only the default fast mode (uniform patch weights) is built.  `h` and `sigma`
+    are on the [0,1] scale of the normalised image, as in skimage after img_as_float; integer tensors
+    use this package's normalisation (value_range, default the dtype's range) and come back in the same
+    dtype unless out_dtype=torch.float32.  `preserve_range` is accepted for signature compatibility and
+    only meaningful for float tensors (which are never rescaled here)."""
+    if channel_axis is not None:
+        raise NotImplementedError("multichannel non-local means is not supported (planes are filtered separately)")
+    if not fast_mode:
+        raise NotImplementedError("only fast_mode=True is implemented")
+    require_cuda(image)
+    x, n, hh, ww = as_planes(image)
+    lo, hi = value_range_of(x, value_range)
+    dst = _out_like(x, out_dtype)
+    with torch.cuda.device(x.device):
+        check(lib().mie_nlm(x.data_ptr(), dst.data_ptr(), DTYPE_CODE[x.dtype], DTYPE_CODE[dst.dtype], n, hh, ww,
+                            hh * ww, ww, hh * ww, ww, int(patch_size), int(patch_distance), float(h), float(sigma),
+                            lo, hi, stream_ptr(x.device)))
+    return dst
+
+
 _MEDIAN_MODES = {"nearest": "replicate", "constant": "constant"}
 
 

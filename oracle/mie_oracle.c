@@ -474,6 +474,53 @@ int orc_clahe_opencv_u16(const uint16_t* in, uint16_t* out, int64_t n, int h, in
     return rc;
 }
 
+/* ------------------------------------------------------------------ non-local means (skimage fast mode)
+ * skimage.restoration.denoise_nl_means(image, patch_size, patch_distance, h, fast_mode=True, sigma)
+ * — scikit-image 0.26.0 (reference pyproject.toml:12); the Cython source is not on disk, the loop below
+ * restates _fast_nl_means_denoising_2d [RECALLED] in float64, as skimage computes for
+ * integer / float64 images:  pad 'reflect' by o + d + 1;  for every shift t in [-d, d]^2 the patch
+ * distance is the integral-image box difference over rows / columns p-o+1 .. p+o of
+ * (I(q) - I(q + t))^2 - 2 sigma^2, clamped at 0 and divided by h^2 s^2;  weights exp(-dist) (dist <= 5),
+ * the zero shift counted twice (upstream accumulates it into both endpoints, which coincide).
+ * in: float64 planes in [0,1] (already normalised); out: float64.  tests/test_oracle.py checks this
+ * closed form against a literal transcription of the upstream accumulation loops on small images. */
+int orc_nlm_fast(const double* in, double* out, int64_t n, int h, int w, int patch_size, int patch_distance,
+                 double hpar, double sigma) {
+    int s = patch_size + (patch_size % 2 == 0 ? 1 : 0);
+    const int o = s / 2, d = patch_distance;
+    if (o < 1 || d < 0 || !(hpar > 0.0) || o + d + 1 >= h || o + d + 1 >= w) return -7;
+    const double var2 = 2.0 * sigma * sigma;
+    const double h2s2 = hpar * hpar * (double)s * (double)s;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+    for (int64_t i = 0; i < n; ++i) {
+        for (int y = 0; y < h; ++y) {
+            const double* img = in + (size_t)i * h * w;
+            for (int x = 0; x < w; ++x) {
+                double num = 0.0, den = 0.0;
+                for (int ty = -d; ty <= d; ++ty)
+                    for (int tx = -d; tx <= d; ++tx) {
+                        double D = 0.0;
+                        for (int qy = -o + 1; qy <= o; ++qy) {
+                            const int ay = border_index(y + qy, h, B_REFLECT), by = border_index(y + qy + ty, h, B_REFLECT);
+                            for (int qx = -o + 1; qx <= o; ++qx) {
+                                const int ax = border_index(x + qx, w, B_REFLECT), bx = border_index(x + qx + tx, w, B_REFLECT);
+                                const double df = img[(size_t)ay * w + ax] - img[(size_t)by * w + bx];
+                                D += df * df - var2;
+                            }
+                        }
+                        const double dist = (D > 0.0 ? D : 0.0) / h2s2;
+                        if (dist > 5.0) continue;
+                        const double wgt = ((ty == 0 && tx == 0) ? 2.0 : 1.0) * exp(-dist);
+                        num += wgt * img[(size_t)border_index(y + ty, h, B_REFLECT) * w + border_index(x + tx, w, B_REFLECT)];
+                        den += wgt;
+                    }
+                out[(size_t)i * h * w + (size_t)y * w + x] = num / den;
+            }
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ median (pure selection)
  * 2-D: kornia.filters.median_blur (zero padding; torch.median = lower median, the
  * true median for odd windows) / skimage.filters.median 2-D ('nearest');

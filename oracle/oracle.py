@@ -55,6 +55,7 @@ class _Sig:
     orc_clahe_luts_from_hist_opencv = ([_p, _i64, _i, _i, _d, _p], _i)
     orc_clahe_apply_opencv_u8 = ([_p, _p, _i64, _i, _i, _i, _i, _p], _i)
     orc_clahe_opencv_u16 = ([_p, _p, _i64, _i, _i, _i, _i, _d, _p], _i)
+    orc_nlm_fast = ([_p, _p, _i64, _i, _i, _i, _i, _d, _d], _i)
     orc_median2d = ([_p, _p, _i64, _i, _i, _i, _i, _i], _i)
     orc_median3d = ([_p, _p, _i, _i, _i, _p, _p, _i], _i)
     orc_exp = ([_p, _p, _i64], None)
@@ -235,6 +236,57 @@ def opencv_clahe(img, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
     luts = opencv_clahe_luts(x, clip_limit, grid_size)
     out = np.empty_like(x)
     _check(lib().orc_clahe_apply_opencv_u8(_ptr(x), _ptr(out), n, h, w, gh, gw, _ptr(luts)))
+    return out
+
+
+# ------------------------------------------------------------------ non-local means (skimage fast mode)
+def denoise_nl_means(x01, patch_size=7, patch_distance=11, h=0.1, sigma=0.0) -> np.ndarray:
+    """skimage.restoration.denoise_nl_means(fast_mode=True) on (..., H, W) planes of [0,1] data; float64."""
+    x, n, hh, ww = _planes(np.asarray(x01), np.float64)
+    out = np.empty_like(x)
+    rc = lib().orc_nlm_fast(_ptr(x), _ptr(out), n, hh, ww, int(patch_size), int(patch_distance), float(h), float(sigma))
+    if rc:
+        raise ValueError("invalid non-local-means parameters (patch / distance too large for the image?)")
+    return out
+
+
+def nlm_fast_literal(image, patch_size=7, patch_distance=11, h=0.1, sigma=0.0) -> np.ndarray:
+    """Literal numpy transcription of skimage's _fast_nl_means_denoising_2d loops [RECALLED] (integral
+    image per shift, symmetric accumulation with alpha = 0.5 on the t_col == 0 column), single 2-D image,
+    float64.  Slow: for pinning orc_nlm_fast on small images only."""
+    image = np.asarray(image, np.float64)
+    s = patch_size + (1 if patch_size % 2 == 0 else 0)
+    offset, d = s // 2, patch_distance
+    pad = offset + d + 1
+    padded = np.pad(image, pad, mode="reflect")
+    n_row, n_col = padded.shape
+    result = np.zeros_like(padded)
+    weights = np.zeros_like(padded)
+    var = 2.0 * sigma * sigma
+    h2s2 = h * h * s * s
+    for t_row in range(-d, d + 1):
+        row_start, row_end = max(offset, offset - t_row), min(n_row - offset, n_row - offset - t_row)
+        for t_col in range(0, d + 1):
+            alpha = 0.5 if (t_col == 0 and t_row != 0) else 1.0
+            col_start, col_end = max(offset, offset - t_col), min(n_col - offset, n_col - offset - t_col)
+            integral = np.zeros_like(padded)
+            r0, r1 = max(1, -t_row), min(n_row, n_row - t_row)
+            c0, c1 = max(1, -t_col), min(n_col, n_col - t_col)
+            diff = (padded[r0:r1, c0:c1] - padded[r0 + t_row:r1 + t_row, c0 + t_col:c1 + t_col]) ** 2 - var
+            integral[r0:r1, c0:c1] = np.cumsum(np.cumsum(diff, axis=0), axis=1)
+            for row in range(row_start, row_end):
+                for col in range(col_start, col_end):
+                    dist = (integral[row + offset, col + offset] + integral[row - offset, col - offset]
+                            - integral[row - offset, col + offset] - integral[row + offset, col - offset])
+                    dist = max(dist, 0.0) / h2s2
+                    if dist > 5.0:
+                        continue
+                    wgt = alpha * np.exp(-dist)
+                    weights[row, col] += wgt
+                    weights[row + t_row, col + t_col] += wgt
+                    result[row, col] += wgt * padded[row + t_row, col + t_col]
+                    result[row + t_row, col + t_col] += wgt * padded[row, col]
+    out = result[pad:-pad, pad:-pad] / weights[pad:-pad, pad:-pad]
     return out
 
 

@@ -208,3 +208,44 @@ def test_host_pipeline_equals_direct_call(dev):
     pipe.run(xh, yh)
     assert np.array_equal(yh.numpy(), cpu(M.enhance_chain(gpu(x2, dev), cfg)))
     assert np.array_equal(M.enhance_chain_host(torch.from_numpy(x), cfg, device=dev).numpy(), ref)
+
+
+# ---------------------------------------------------------------------------- non-local means (config 5)
+@pytest.mark.parametrize("case", [
+    dict(shape=(2, 1, 64, 80), ps=7, pd=11, h=0.1, sigma=0.0),       # skimage defaults on a ragged tile grid
+    dict(shape=(1, 1, 96, 96), ps=7, pd=5, h=0.08, sigma=0.04),
+    dict(shape=(1, 2, 40, 50), ps=5, pd=3, h=0.2, sigma=0.0),
+    dict(shape=(1, 1, 33, 47), ps=3, pd=2, h=0.05, sigma=0.01),
+    dict(shape=(1, 1, 64, 64), ps=8, pd=4, h=0.1, sigma=0.0),        # even patch size -> 9
+])
+def test_nlm_within_tolerance_of_float64_oracle(dev, case):
+    """fp32 kernel (ex2.approx weights) vs the float64 oracle: rel/abs 1e-5 on [0,1] data (the north
+    star's bar for floating-point filters) and <= 1 LSB after quantisation."""
+    import mie_b200 as M
+    import oracle as O
+    from mie_b200 import synthetic
+
+    x = synthetic.phantom(case["shape"], np.uint16, seed=5)
+    x = (x.astype(np.float64) * (65535.0 / 4095.0)).clip(0, 65535).astype(np.uint16)    # use the full range
+    kw = dict(patch_size=case["ps"], patch_distance=case["pd"], h=case["h"], sigma=case["sigma"])
+    ref = O.denoise_nl_means(O.to01(x).astype(np.float64), case["ps"], case["pd"], case["h"], case["sigma"])
+    gf = cpu(M.denoise_nl_means(gpu(x, dev), out_dtype=torch.float32, **kw)).astype(np.float64)
+    assert np.abs(gf - ref).max() <= 1e-5, float(np.abs(gf - ref).max())
+    gq = cpu(M.denoise_nl_means(gpu(x, dev), **kw)).astype(np.int64)
+    rq = np.rint(np.clip(ref, 0, 1) * 65535.0).astype(np.int64)
+    assert np.abs(gq - rq).max() <= 1
+    xf = O.to01(x)
+    gff = cpu(M.denoise_nl_means(gpu(xf, dev), **kw)).astype(np.float64)
+    assert np.abs(gff - ref).max() <= 1e-5
+
+
+def test_nlm_argument_errors(dev):
+    import mie_b200 as M
+
+    x = torch.zeros((1, 1, 64, 64), dtype=torch.float32, device=dev)
+    with pytest.raises(NotImplementedError):
+        M.denoise_nl_means(x, fast_mode=False)
+    with pytest.raises((ValueError, RuntimeError)):
+        M.denoise_nl_means(x, patch_size=11)
+    with pytest.raises((ValueError, RuntimeError)):
+        M.denoise_nl_means(torch.zeros((1, 1, 12, 12), device=dev))      # padding would exceed the image

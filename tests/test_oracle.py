@@ -265,3 +265,27 @@ def test_golden_hashes():
         want = json.load(f)
     got = make_golden.compute()
     assert got == want
+
+
+# ---------------------------------------------------------------------------- A8 non-local means
+@pytest.mark.parametrize("ps,pd,h,sigma", [(3, 2, 0.1, 0.0), (5, 3, 0.08, 0.05), (7, 4, 0.15, 0.02), (4, 2, 0.1, 0.0)])
+def test_nlm_closed_form_equals_literal_upstream_loops(ps, pd, h, sigma):
+    """orc_nlm_fast (per-pixel closed form) vs a literal transcription of skimage's fast-mode loops
+    (integral image per shift, symmetric accumulation, alpha = 0.5 on the t_col == 0 column)."""
+    rng = np.random.default_rng(0)
+    img = np.clip(0.5 + 0.2 * np.sin(np.arange(28)[:, None] / 3.0) + 0.1 * rng.normal(size=(28, 30)), 0, 1)
+    a = O.denoise_nl_means(img, ps, pd, h, sigma)
+    b = O.nlm_fast_literal(img, ps, pd, h, sigma)
+    assert np.abs(a - b).max() < 1e-12
+
+
+def test_nlm_properties():
+    rng = np.random.default_rng(1)
+    const = np.full((40, 40), 0.3)
+    assert np.allclose(O.denoise_nl_means(const, 7, 5, 0.1), 0.3, atol=1e-15)      # constants are fixed points
+    noisy = np.clip(0.5 + 0.05 * rng.normal(size=(48, 48)), 0, 1)
+    den = O.denoise_nl_means(noisy, 7, 5, 0.1, sigma=0.05)
+    assert den.std() < 0.5 * noisy.std()                                            # it denoises
+    assert den.min() >= noisy.min() - 1e-12 and den.max() <= noisy.max() + 1e-12    # convex combination
+    with pytest.raises(ValueError):
+        O.denoise_nl_means(np.zeros((8, 8)), 7, 11, 0.1)
