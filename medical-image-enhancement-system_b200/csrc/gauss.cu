@@ -5,6 +5,13 @@
 
 namespace mie {
 
+// gauss_march.cu
+bool gauss_march_ok(const void* src, const void* dst, int sd, int dd, int h, int w, int64_t ssn, int64_t ssh,
+                    int64_t dsn, int64_t dsh, int kx, int ky, int border, float lo, float hi);
+int launch_gauss_march(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
+                       int64_t dsn, int64_t dsh, const Taps& wx, const Taps& wy, int border, int unsharp,
+                       cudaStream_t st);
+
 struct GaussArgs {
     const void* src;
     void* dst;
@@ -175,6 +182,9 @@ int gauss_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int
         wx.w[i] = i < kx ? wxp[i] : 0.f;
         wy.w[i] = i < ky ? wyp[i] : 0.f;
     }
+    // common geometry (square 9-tap kernel, W % 128 == 0, H % 64 == 0): marching kernel (gauss_march.cu)
+    if (gauss_march_ok(src, dst, sd, dd, h, w, ssn, ssh, dsn, dsh, kx, ky, border, lo, hi))
+        return launch_gauss_march(src, dst, sd, dd, n, h, w, ssn, ssh, dsn, dsh, wx, wy, border, unsharp, st);
     GaussArgs a;
     a.src = src; a.dst = dst; a.ssn = ssn; a.ssh = ssh; a.dsn = dsn; a.dsh = dsh;
     a.h = h; a.w = w; a.tiles_x = a.tiles_y = 0; a.border = border; a.unsharp = unsharp;

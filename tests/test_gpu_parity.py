@@ -208,6 +208,12 @@ GAUSS_CASES = [
     ((1, 1, 50, 60), (3, 9), (0.7, 1.5), "reflect"),  # generic path (non-square)
     ((1, 1, 9, 9), 9, 1.0, "reflect"),           # halo == dim-1 (largest legal reflect)
     ((1, 1, 40, 40), 33, 5.0, "replicate"),      # maximum taps
+    # marching kernel (9 taps, W % 128 == 0, H % 64 == 0): one-warp bands, 256-thread bands, all borders
+    ((2, 1, 128, 128), 9, 1.0, "reflect"),
+    ((2, 1, 128, 256), 9, 1.0, "replicate"),
+    ((1, 1, 64, 128), 9, 1.5, "constant"),
+    ((1, 1, 192, 1024), 9, 1.0, "reflect"),
+    ((1, 3, 64, 384), 9, 0.7, "reflect"),
 ]
 
 
