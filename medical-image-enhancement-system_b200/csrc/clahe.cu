@@ -8,6 +8,17 @@
 
 namespace mie {
 
+// clahe_fast.cu
+bool clahe_lut_fast_ok(const ClaheGeom& g, int sd, const void* src, int64_t ssn, int64_t ssh, float lo, float hi);
+int launch_clahe_lut_fast(const void* src, int sd, int64_t n, int64_t ssn, int64_t ssh, const ClaheGeom& g,
+                          const LutParams& lp, uint32_t* hist, uint8_t* luts, cudaStream_t st);
+size_t clahe_cells_bytes(int64_t n, int gh, int gw);
+bool clahe_apply_fast_ok(const ClaheGeom& g, int sd, int dd, const void* src, const void* dst, int64_t ssn,
+                         int64_t ssh, int64_t dsn, int64_t dsh, float lo, float hi);
+int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t n, int64_t ssn, int64_t ssh,
+                            int64_t dsn, int64_t dsh, const ClaheGeom& g, const uint8_t* luts, void* cells,
+                            cudaStream_t st);
+
 // ---------------------------------------------------------------- LUT kernel
 template <typename SrcT, int SEM>
 __global__ void __launch_bounds__(256)
@@ -146,6 +157,8 @@ int clahe_luts_impl(const void* src, int sd, int64_t n, int h, int w, int64_t ss
     if ((int64_t)g.th * g.tw >= (1 << 24)) return MIE_E_SHAPE;  // counts are carried in fp32-exact range
     const LutParams lp = make_lut_params(g, clip_limit, semantics);
     const float rg = hi - lo;
+    if (semantics == MIE_CLAHE_KORNIA && clahe_lut_fast_ok(g, sd, src, ssn, ssh, lo, hi))
+        return launch_clahe_lut_fast(src, sd, n, ssn, ssh, g, lp, hist, luts, st);
     MIE_DISPATCH_SRC(sd, return launch_lut<SrcT>(src, n, ssn, ssh, g, lo, rg, lp, semantics, hist, luts, st));
     return MIE_OK;
 }
@@ -186,10 +199,14 @@ using namespace mie;
 
 extern "C" {
 
+// LUTs (256 B per tile, rounded up to 256 B) followed by the packed cell tables of the tuned
+// interpolation kernel (2 KB per interpolation cell)
+static size_t clahe_lut_region(int64_t n, int gh, int gw) { return ((size_t)n * gh * gw * kBins + 255) & ~(size_t)255; }
+
 size_t mie_clahe_workspace_bytes(int64_t n, int h, int w, int gh, int gw) {
     (void)h; (void)w;
     if (n <= 0 || gh <= 0 || gw <= 0) return 0;
-    return (size_t)n * gh * gw * kBins;
+    return clahe_lut_region(n, gh, gw) + clahe_cells_bytes(n, gh, gw);
 }
 
 int mie_clahe_hist(const void* src, int src_dtype, int64_t n, int h, int w, int64_t src_stride_n,
@@ -231,6 +248,17 @@ int mie_clahe(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t 
     int rc = clahe_luts_impl(src, src_dtype, n, h, w, src_stride_n, src_stride_h, gh, gw, clip_limit, semantics, lo,
                              hi, nullptr, (uint8_t*)workspace, (cudaStream_t)stream);
     if (rc) return rc;
+    if (semantics == MIE_CLAHE_KORNIA && dst && n > 0) {
+        ClaheGeom g;
+        if (make_clahe_geom(h, w, gh, gw, semantics, &g) == MIE_OK && check_dtypes(src_dtype, dst_dtype, lo, hi) == MIE_OK &&
+            check_planes(src, dst, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h) == MIE_OK &&
+            n <= 65535 &&
+            clahe_apply_fast_ok(g, src_dtype, dst_dtype, src, dst, src_stride_n, src_stride_h, dst_stride_n,
+                                dst_stride_h, lo, hi))
+            return launch_clahe_apply_fast(src, dst, src_dtype, dst_dtype, n, src_stride_n, src_stride_h, dst_stride_n,
+                                           dst_stride_h, g, (const uint8_t*)workspace,
+                                           (uint8_t*)workspace + clahe_lut_region(n, gh, gw), (cudaStream_t)stream);
+    }
     return clahe_apply_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n,
                             dst_stride_h, gh, gw, semantics, lo, hi, (const uint8_t*)workspace, (cudaStream_t)stream);
 }

@@ -1,0 +1,192 @@
+// clahe_fast.cu — tuned standalone CLAHE (kornia semantics, 256 bins) for unpadded geometries: tile
+// width a multiple of 8, 16-byte aligned rows, the dtype's default value range.  Same integer artefacts
+// (histograms, LUTs) and the same fp32 blend, bit for bit, as clahe.cu; what changes:
+//   * LUT kernel: 128-bit loads, divide-free pixel mapping, one ATOMS.POPC.INC per pixel into ONE block
+//     histogram (hardware aggregates colliding lanes), LUT built by a single warp;
+//   * interpolation: the four neighbouring LUT entries of every interpolation cell are packed into one
+//     8-byte table entry per grey level (chain_fast.cu: chain_pack_cells_kernel), a block stages the
+//     (gw + 1) tables of one cell row in shared memory, and a pixel costs ONE shared-memory lookup;
+//     threads own 4 consecutive columns (64-bit loads / stores), no divides, no F2I.
+#include <cstdlib>
+
+#include "chain_fast.cuh"
+
+namespace mie {
+
+// ---------------------------------------------------------------- histogram -> LUT, one block per tile
+template <typename SrcT>
+__global__ void __launch_bounds__(256)
+clahe_lut_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, LutParams lp,
+                      uint32_t* __restrict__ hist_out, uint8_t* __restrict__ lut_out) {
+    constexpr bool INT = sizeof(SrcT) != 4;  // integer pixels map into [0, 1]: no range tests
+    __shared__ __align__(16) int s_hist[kBins + 8];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kBins + 8; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t tile = blockIdx.x;
+    const int tx = (int)(tile % g.gw), ty = (int)((tile / g.gw) % g.gh);
+    const int64_t n = tile / ((int64_t)g.gw * g.gh);
+    const SrcT* base = src + n * ssn + (int64_t)ty * g.th * ssh + (int64_t)tx * g.tw;
+    const uint32_t h32 = hist_base32(s_hist);
+    const int chunks = g.tw >> 3;              // 8-pixel chunks per tile row
+    const int total = chunks * g.th;
+    for (int i = tid; i < total; i += 256) {
+        const int r = i / chunks, c = i - r * chunks;
+        float x[8];
+        Fast<SrcT>::load8(base + (int64_t)r * ssh + 8 * c, x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (INT) hist_add_le1(h32, x[k]);
+            else hist_add_nobranch(s_hist, fast_bin<false>(x[k]));
+        }
+    }
+    __syncthreads();
+    if (hist_out && tid < kBins) {
+        int v = s_hist[tid];
+        if (INT && tid == kBins - 1) v += s_hist[kBins];   // slot 256 = pixels equal to 1.0 (see hist_add_le1)
+        hist_out[tile * kBins + tid] = (uint32_t)v;
+    }
+    if (lut_out && tid < 32) {
+        if (INT) warp_build_lut<true>(s_hist, lp, lut_out + tile * kBins, tid);
+        else warp_build_lut<false>(s_hist, lp, lut_out + tile * kBins, tid);
+    }
+}
+
+// ---------------------------------------------------------------- interpolation pass
+struct ApplyFastArgs {
+    const void* src;
+    void* dst;
+    int64_t ssn, ssh, dsn, dsh;
+    ClaheGeom g;
+    int rows_per_block;   // divides th / 2
+    int blocks_per_image;
+    float inv_tm1_y, inv_tm1_x;  // unused (weights use the exact division below)
+};
+
+__device__ __forceinline__ uint2 lds64_(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+
+// weight of the upper / left tile at coordinate y of an axis with tile size T (kornia_axis); in the
+// outer half-tiles both neighbours are the same tile and the value is irrelevant (t == b there)
+__device__ __forceinline__ float axis_weight(int y, int T) {
+    const int hh = T >> 1;
+    int r = y - hh;
+    r = r < 0 ? 0 : r % T;
+    return __fdiv_rn((float)(T - 1 - r), (float)(T - 1));
+}
+
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(1024)
+clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells) {
+    constexpr bool INT = sizeof(SrcT) != 4;
+    extern __shared__ __align__(16) uint2 s_tab[];   // (gw + 1) x 256 entries: one row of cells
+    const ClaheGeom g = a.g;
+    const int tid = threadIdx.x, T = blockDim.x;
+    const int64_t n = blockIdx.x / a.blocks_per_image;
+    const int y0 = (int)(blockIdx.x % a.blocks_per_image) * a.rows_per_block;
+    const int cy = (y0 + (g.th >> 1)) / g.th;        // cell row of all rows of this block
+    {
+        const uint4* s = reinterpret_cast<const uint4*>(cells + (n * (g.gh + 1) + cy) * (int64_t)(g.gw + 1) * kBins);
+        uint4* d = reinterpret_cast<uint4*>(s_tab);
+        for (int i = tid; i < (g.gw + 1) * kBins / 2; i += T) d[i] = __ldg(s + i);
+    }
+    const int x0 = 4 * tid;
+    const int cx = (x0 + (g.tw >> 1)) / g.tw;
+    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(s_tab + cx * kBins);
+    float wxv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wxv[k] = axis_weight(x0 + k, g.tw);
+    const SrcT* sp = (const SrcT*)a.src + n * a.ssn + (int64_t)y0 * a.ssh + x0;
+    DstT* dp = (DstT*)a.dst + n * a.dsn + (int64_t)y0 * a.dsh + x0;
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < a.rows_per_block; ++r) {
+        float x[4], y[4];
+        Fast<SrcT>::load4(sp + (int64_t)r * a.ssh, x);
+        const float wyv = axis_weight(y0 + r, g.th);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t bits = INT ? fast_idx_bits_le1(x[k]) : fast_idx_bits<false>(x[k]);
+            y[k] = clahe_px(lds64_(tb + (__byte_perm(bits, 0u, 0x4440) << 3)), wxv[k], wyv);
+        }
+        Fast<DstT>::store4(dp + (int64_t)r * a.dsh, y);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static bool default_range_c(int dtype, float lo, float hi) {
+    switch (dtype) {
+        case MIE_U8: return lo == 0.0f && hi == 255.0f;
+        case MIE_U16: return lo == 0.0f && hi == 65535.0f;
+        case MIE_I16: return lo == -32768.0f && hi == 32767.0f;
+        default: return true;
+    }
+}
+static const int kEsz[4] = {1, 2, 2, 4};
+static bool fast_disabled() {
+    static const bool off = [] { const char* e = getenv("MIE_CLAHE_NO_FAST"); return e && e[0] == '1'; }();
+    return off;
+}
+
+bool clahe_lut_fast_ok(const ClaheGeom& g, int sd, const void* src, int64_t ssn, int64_t ssh, float lo, float hi) {
+    if (fast_disabled()) return false;
+    if (g.hp != g.h || g.wp != g.w || (g.tw & 7)) return false;
+    if (!default_range_c(sd, lo, hi)) return false;
+    if (((uintptr_t)src % 16) || ((ssn * kEsz[sd]) % 16) || ((ssh * kEsz[sd]) % 16)) return false;
+    if (((int64_t)g.tw * kEsz[sd]) % 16) return false;   // tile origins 16-byte aligned for load8
+    return true;
+}
+
+int launch_clahe_lut_fast(const void* src, int sd, int64_t n, int64_t ssn, int64_t ssh, const ClaheGeom& g,
+                          const LutParams& lp, uint32_t* hist, uint8_t* luts, cudaStream_t st) {
+    const int64_t tiles = n * g.gh * g.gw;
+    if (tiles == 0) return MIE_OK;
+    if (tiles > 2147483647LL) return MIE_E_SHAPE;
+    MIE_DISPATCH_SRC(sd, (clahe_lut_fast_kernel<SrcT><<<(unsigned)tiles, 256, 0, st>>>((const SrcT*)src, ssn, ssh, g, lp,
+                                                                                    hist, luts)));
+    return check_launch();
+}
+
+size_t clahe_cells_bytes(int64_t n, int gh, int gw) { return chain_cells_bytes(n, gh, gw); }
+
+bool clahe_apply_fast_ok(const ClaheGeom& g, int sd, int dd, const void* src, const void* dst, int64_t ssn,
+                         int64_t ssh, int64_t dsn, int64_t dsh, float lo, float hi) {
+    if (fast_disabled()) return false;
+    if (g.hp != g.h || g.wp != g.w || (g.tw & 7) || (g.w & 3) || g.w > 4096 || g.gw > 32) return false;
+    if (dd != sd && dd != MIE_F32) return false;
+    if (!default_range_c(sd, lo, hi) || !default_range_c(dd, lo, hi)) return false;
+    if (((uintptr_t)src % 16) || ((ssn * kEsz[sd]) % 16) || ((ssh * kEsz[sd]) % 16)) return false;
+    if (((uintptr_t)dst % 16) || ((dsn * kEsz[dd]) % 16) || ((dsh * kEsz[dd]) % 16)) return false;
+    return true;
+}
+
+// luts -> cell tables (in `cells`, clahe_cells_bytes) -> interpolation
+int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t n, int64_t ssn, int64_t ssh,
+                            int64_t dsn, int64_t dsh, const ClaheGeom& g, const uint8_t* luts, void* cells,
+                            cudaStream_t st) {
+    if (n == 0) return MIE_OK;
+    int rc = launch_pack_cells(luts, cells, n, g.gh, g.gw, st);
+    if (rc) return rc;
+    ApplyFastArgs a;
+    a.src = src; a.dst = dst; a.ssn = ssn; a.ssh = ssh; a.dsn = dsn; a.dsh = dsh; a.g = g;
+    int rows = g.th / 2;                        // rows of a block stay inside one cell row
+    for (int d = 32; d >= 1; --d)
+        if ((g.th / 2) % d == 0) { rows = d; break; }
+    a.rows_per_block = rows;
+    a.blocks_per_image = g.h / rows;
+    a.inv_tm1_y = a.inv_tm1_x = 0.f;
+    const int64_t blocks = n * a.blocks_per_image;
+    if (blocks > 2147483647LL) return MIE_E_SHAPE;
+    const size_t smem = (size_t)(g.gw + 1) * kBins * 8;
+#define MIE_APPLY_FAST                                                                                     \
+    MIE_ENSURE_SMEM((clahe_apply_fast_kernel<SrcT, DstT>), 80 * 1024);                                     \
+    clahe_apply_fast_kernel<SrcT, DstT><<<(unsigned)blocks, g.w / 4, smem, st>>>(a, (const uint2*)cells)
+    MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST);
+#undef MIE_APPLY_FAST
+    return check_launch();
+}
+
+}  // namespace mie

@@ -48,7 +48,9 @@ def test_workspace_queries_need_no_gpu():
     from mie_b200 import _ffi
 
     L = _ffi.lib()
-    assert L.mie_clahe_workspace_bytes(256, 512, 512, 8, 8) == 256 * 64 * 256
+    # LUTs (256 B per tile) + packed cell tables of the tuned interpolation pass (2 KB per cell)
+    assert L.mie_clahe_workspace_bytes(256, 512, 512, 8, 8) == 256 * 64 * 256 + 256 * 81 * 2048
+    assert L.mie_clahe16_lut_bytes(8, 8) == 64 * 65536 * 2
     assert L.mie_chain_workspace_bytes(2, 64, 64, 2, 2) == 2 * 4 * 256 + 2 * 64 * 64 * 4
     assert L.mie_chain_workspace_bytes(0, 64, 64, 2, 2) == 0
 
