@@ -70,7 +70,10 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
     const uint32_t ring32 = (uint32_t)__cvta_generic_to_shared(s_raw);
     const uint32_t bar32 = (uint32_t)__cvta_generic_to_shared(s_bar);
     const char* plane0 = reinterpret_cast<const char*>((const SrcT*)a.src + n * a.ssn);
-    auto issue_batch = [&](const int b) {  // thread 0 only
+    // the producer is the first lane of warp 1 when there is one: warps 0 and nwarps-1 already carry the
+    // image-border halo work, and every warp waits for the slowest one at the per-step barrier
+    const int producer = nwarps > 2 ? 32 : 0;
+    auto issue_batch = [&](const int b) {  // producer thread only
         const int4 o = *reinterpret_cast<const int4*>(s_off + kRawBatch * b);
         const int off[4] = {o.x, o.y, o.z, o.w};
         const uint32_t mb = bar32 + 8 * (b % kRawBars);
@@ -84,7 +87,7 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
                 bulk_g2s(ring32 + (uint32_t)(((kRawBatch * b + j) % kRawRows) * row_bytes), plane0 + (unsigned)off[j],
                          (uint32_t)row_bytes, mb);
     };
-    if (tid == 0) {
+    if (tid == producer) {
 #pragma unroll
         for (int b = 0; b < kRawBars; ++b) issue_batch(b);
     }
@@ -106,7 +109,7 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
     // after the barrier of an odd row pair p its batch (p - 1) / 2 is consumed: refill the slots
     auto refill = [&](const int p) {
         const int b = (p - 1) / 2 + kRawBars;
-        if (tid == 0 && b < kMRows / kRawBatch) issue_batch(b);
+        if (tid == producer && b < kMRows / kRawBatch) issue_batch(b);
     };
     auto emit = [&](const float* g) {
         if (LE1) {
