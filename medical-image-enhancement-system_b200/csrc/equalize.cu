@@ -9,6 +9,8 @@
 // Three launches: per-plane histogram (shared-memory sub-histograms, warp-voted
 // adds, one global atomic per non-empty bin per block), LUT (one block per plane),
 // apply.
+#include <cstdlib>
+
 #include "chain_fast.cuh"
 
 namespace mie {
@@ -108,6 +110,118 @@ equalize_apply_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int6
     dst[n * dsn + (int64_t)y * dsh + x] = Px<DstT>::from01(div255(r), lo, rg);
 }
 
+
+// ---------------------------------------------------------------- tuned path: integer pixels, default range
+// Same integers (histogram, LUT) and the same fp32 mapping as the kernels above, but 128-bit loads /
+// stores, the divide-free pixel conversion of chain_fast.cuh, one ATOMS.POPC.INC per pixel into a single
+// block histogram, and — because lut[trunc(v)] takes only 256 values — a per-block table of the 256
+// possible OUTPUT codes, so a pixel costs one conversion, one shared-memory lookup and a pack.
+template <typename SrcT>
+__global__ void __launch_bounds__(256)
+equalize_hist_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, int h, int w, int rows_per_block,
+                          EqPlaneState* __restrict__ state) {
+    __shared__ __align__(16) int s_hist[kBins + 8];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kBins + 8; i += 256) s_hist[i] = 0;
+    __syncthreads();
+    const int64_t n = blockIdx.y;
+    const int y0 = blockIdx.x * rows_per_block, y1 = min(y0 + rows_per_block, h);
+    const SrcT* base = src + n * ssn + (int64_t)y0 * ssh;
+    const uint32_t h32 = hist_base32(s_hist);
+    const int chunks = w >> 3, total = chunks * (y1 - y0);
+    for (int i = tid; i < total; i += 256) {
+        const int r = i / chunks, c = i - r * chunks;
+        float x[8];
+        Fast<SrcT>::load8(base + (int64_t)r * ssh + 8 * c, x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hist_add_le1(h32, div255(__fmul_rn(x[k], 255.0f)));  // eq_bin, x in [0,1]
+    }
+    __syncthreads();
+    int hv = s_hist[tid];
+    if (tid == kBins - 1) hv += s_hist[kBins];   // slot 256 = pixels equal to 1.0 (see hist_add_le1)
+    if (hv) atomicAdd(&state[n].hist[tid], (unsigned int)hv);
+}
+
+__device__ __forceinline__ void eq_store8(uint16_t* p, const uint16_t* s_out, const uint32_t* i) {
+    uint4 o;
+    o.x = (uint32_t)s_out[i[0]] | ((uint32_t)s_out[i[1]] << 16);
+    o.y = (uint32_t)s_out[i[2]] | ((uint32_t)s_out[i[3]] << 16);
+    o.z = (uint32_t)s_out[i[4]] | ((uint32_t)s_out[i[5]] << 16);
+    o.w = (uint32_t)s_out[i[6]] | ((uint32_t)s_out[i[7]] << 16);
+    *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ void eq_store8(int16_t* p, const int16_t* s_out, const uint32_t* i) {
+    eq_store8(reinterpret_cast<uint16_t*>(p), reinterpret_cast<const uint16_t*>(s_out), i);
+}
+__device__ __forceinline__ void eq_store8(uint8_t* p, const uint8_t* s_out, const uint32_t* i) {
+    uint2 o;
+    o.x = (uint32_t)s_out[i[0]] | ((uint32_t)s_out[i[1]] << 8) | ((uint32_t)s_out[i[2]] << 16) | ((uint32_t)s_out[i[3]] << 24);
+    o.y = (uint32_t)s_out[i[4]] | ((uint32_t)s_out[i[5]] << 8) | ((uint32_t)s_out[i[6]] << 16) | ((uint32_t)s_out[i[7]] << 24);
+    *reinterpret_cast<uint2*>(p) = o;
+}
+__device__ __forceinline__ void eq_store8(float* p, const float* s_out, const uint32_t* i) {
+    *reinterpret_cast<float4*>(p) = make_float4(s_out[i[0]], s_out[i[1]], s_out[i[2]], s_out[i[3]]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(s_out[i[4]], s_out[i[5]], s_out[i[6]], s_out[i[7]]);
+}
+
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(256)
+equalize_apply_fast_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh,
+                           int64_t dsn, int64_t dsh, int h, int w, int rows_per_block, float lo, float rg,
+                           const EqPlaneState* __restrict__ state) {
+    __shared__ __align__(16) DstT s_out[kBins];
+    const int tid = threadIdx.x;
+    const int64_t n = blockIdx.y;
+    const EqPlaneState& st = state[n];
+    const int active = st.step_nonzero;
+    s_out[tid] = Px<DstT>::from01(div255(st.lut[tid]), lo, rg);
+    __syncthreads();
+    const int y0 = blockIdx.x * rows_per_block, y1 = min(y0 + rows_per_block, h);
+    const SrcT* sp = src + n * ssn + (int64_t)y0 * ssh;
+    DstT* dp = dst + n * dsn + (int64_t)y0 * dsh;
+    const int chunks = w >> 3, total = chunks * (y1 - y0);
+    if (active) {
+#pragma unroll 2
+        for (int i = tid; i < total; i += 256) {
+            const int r = i / chunks, c = i - r * chunks;
+            float x[8];
+            uint32_t idx[8];
+            Fast<SrcT>::load8(sp + (int64_t)r * ssh + 8 * c, x);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) idx[k] = fast_idx_bits_le1(x[k]) & 0xFFu;   // trunc(x*255)
+            eq_store8(dp + (int64_t)r * dsh + 8 * c, s_out, idx);
+        }
+    } else {   // step == 0 (e.g. a constant plane): v/255 goes back unchanged
+        for (int i = tid; i < total; i += 256) {
+            const int r = i / chunks, c = i - r * chunks;
+            float x[8];
+            Fast<SrcT>::load8(sp + (int64_t)r * ssh + 8 * c, x);
+            DstT* o = dp + (int64_t)r * dsh + 8 * c;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[k] = Px<DstT>::from01(div255(__fmul_rn(x[k], 255.0f)), lo, rg);
+        }
+    }
+}
+
+static bool eq_default_range(int dtype, float lo, float hi) {
+    switch (dtype) {
+        case MIE_U8: return lo == 0.0f && hi == 255.0f;
+        case MIE_U16: return lo == 0.0f && hi == 65535.0f;
+        case MIE_I16: return lo == -32768.0f && hi == 32767.0f;
+        default: return false;   // float planes may hold values outside [0,1]: generic kernels
+    }
+}
+static bool equalize_fast_ok(int sd, int dd, const void* src, const void* dst, int w, int64_t ssn, int64_t ssh,
+                             int64_t dsn, int64_t dsh, float lo, float hi) {
+    static const bool off = [] { const char* e = getenv("MIE_EQUALIZE_NO_FAST"); return e && e[0] == '1'; }();
+    static const int esz[4] = {1, 2, 2, 4};
+    if (off || (w & 7) || !eq_default_range(sd, lo, hi)) return false;
+    const int sa = 8 * esz[sd], da = dd == MIE_F32 ? 16 : 8 * esz[dd];
+    if (((uintptr_t)src % sa) || ((ssn * esz[sd]) % sa) || ((ssh * esz[sd]) % sa)) return false;
+    if (((uintptr_t)dst % da) || ((dsn * esz[dd]) % da) || ((dsh * esz[dd]) % da)) return false;
+    return true;
+}
+
 }  // namespace mie
 
 using namespace mie;
@@ -133,6 +247,29 @@ int mie_equalize(const void* src, void* dst, int src_dtype, int dst_dtype, int64
     cudaError_t e = cudaMemsetAsync(state, 0, (size_t)n * sizeof(EqPlaneState), st);
     if (e != cudaSuccess) return (int)e;
     const float rg = hi - lo;
+    if (equalize_fast_ok(src_dtype, dst_dtype, src, dst, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h, lo,
+                         hi)) {
+        // ~8 blocks per SM in flight; at least 8 rows per block so the 256 global atomics per block stay rare
+        int bpp = (int)((8 * 148 + n - 1) / n);
+        int rows = ceil_div(h, bpp < 1 ? 1 : bpp);
+        if (rows < 8) rows = 8;
+        if (rows > 64) rows = 64;
+        dim3 grid((unsigned)ceil_div(h, rows), (unsigned)n);
+        switch (src_dtype) {
+            case MIE_U8: equalize_hist_fast_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, src_stride_n, src_stride_h, h, w, rows, state); break;
+            case MIE_U16: equalize_hist_fast_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, src_stride_n, src_stride_h, h, w, rows, state); break;
+            default: equalize_hist_fast_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)src, src_stride_n, src_stride_h, h, w, rows, state); break;
+        }
+        rc = check_launch();
+        if (rc) return rc;
+        equalize_lut_kernel<<<(unsigned)n, 256, 0, st>>>(state);
+        rc = check_launch();
+        if (rc) return rc;
+        MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, (equalize_apply_fast_kernel<SrcT, DstT><<<grid, 256, 0, st>>>(
+                                                       (const SrcT*)src, (DstT*)dst, src_stride_n, src_stride_h,
+                                                       dst_stride_n, dst_stride_h, h, w, rows, lo, rg, state)));
+        return check_launch();
+    }
     // enough blocks per plane to fill the machine when n is small, few enough to keep global atomics rare
     int blocks_per_plane = (int)((4 * 148 + n - 1) / n);
     if (blocks_per_plane < 1) blocks_per_plane = 1;

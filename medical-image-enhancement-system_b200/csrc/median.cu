@@ -209,15 +209,35 @@ struct PackedU16 {
 struct PackedS16 {
     uint32_t v;
 };
+// min and max are separate (non-volatile) asm statements so that halves of a compare-exchange whose
+// result is never read are removed by the compiler (the pruned selection networks below rely on it).
+__device__ __forceinline__ PackedU16 pmin(PackedU16 a, PackedU16 b) {
+    PackedU16 r;
+    asm("min.u16x2 %0, %1, %2;" : "=r"(r.v) : "r"(a.v), "r"(b.v));
+    return r;
+}
+__device__ __forceinline__ PackedU16 pmax(PackedU16 a, PackedU16 b) {
+    PackedU16 r;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(r.v) : "r"(a.v), "r"(b.v));
+    return r;
+}
+__device__ __forceinline__ PackedS16 pmin(PackedS16 a, PackedS16 b) {
+    PackedS16 r;
+    asm("min.s16x2 %0, %1, %2;" : "=r"(r.v) : "r"(a.v), "r"(b.v));
+    return r;
+}
+__device__ __forceinline__ PackedS16 pmax(PackedS16 a, PackedS16 b) {
+    PackedS16 r;
+    asm("max.s16x2 %0, %1, %2;" : "=r"(r.v) : "r"(a.v), "r"(b.v));
+    return r;
+}
 __device__ __forceinline__ void cswap(PackedU16& a, PackedU16& b) {
-    uint32_t lo, hi;
-    asm("min.u16x2 %0, %2, %3;\n\tmax.u16x2 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a.v), "r"(b.v));
-    a.v = lo; b.v = hi;
+    const PackedU16 lo = pmin(a, b), hi = pmax(a, b);
+    a = lo; b = hi;
 }
 __device__ __forceinline__ void cswap(PackedS16& a, PackedS16& b) {
-    uint32_t lo, hi;
-    asm("min.s16x2 %0, %2, %3;\n\tmax.s16x2 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(a.v), "r"(b.v));
-    a.v = lo; b.v = hi;
+    const PackedS16 lo = pmin(a, b), hi = pmax(a, b);
+    a = lo; b = hi;
 }
 __device__ __forceinline__ bool operator<(const PackedU16& a, const PackedU16& b) { return a.v < b.v; }  // unused
 __device__ __forceinline__ bool operator<(const PackedS16& a, const PackedS16& b) { return a.v < b.v; }  // unused
@@ -232,6 +252,49 @@ template <int NEXT, int N>
 struct Forget<2, NEXT, N, PackedS16> {
     static __device__ __forceinline__ PackedS16 run(PackedS16* a, const PackedS16*) { return packed_min(a[0], a[1]); }
 };
+
+// ---- rank 13 of 27 from three SORTED 9-lists (the 3x3 neighbourhoods of planes z-1, z, z+1)
+// A z-step sorts only the incoming plane's nine samples (25 compare-exchanges, Dobbelaere's optimal
+// 9-input network) and reuses the sorted lists of the other two planes, i.e. one sort per output.
+// Selection: write the lists as the rows of a 3x9 matrix and sort its columns — rows stay sorted, so
+// element (r,c) has (r+1)(c+1)-1 others below it and (3-r)(9-c)-1 above; 14 or more on either side
+// rules it out.  Seven entries drop out as too small, seven as too large, and the median of 27 is
+// the median (rank 6) of the remaining 13: row0[5..8], row1[2..6], row2[0..3] — three sorted runs.
+// Merge the two 4-runs (Batcher odd-even merge, 9 compare-exchanges) into W and finish with
+// rank_r(W u Y) = min(w_r, min_{i+j=r-1} max(w_i, y_j)).  ~110 min/max per voxel PAIR instead of the
+// ~350 of the forgetful selection (verified exhaustively on 0/1 inputs and on random ties:
+// tests/test_host_logic.py::test_median27_selection_network).
+template <typename P>
+__device__ __forceinline__ void sort9(P* a) {
+#define MIE_CS(i, j) cswap(a[i], a[j]);
+    MIE_CS(0, 3) MIE_CS(1, 7) MIE_CS(2, 5) MIE_CS(4, 8)
+    MIE_CS(0, 7) MIE_CS(2, 4) MIE_CS(3, 8) MIE_CS(5, 6)
+    MIE_CS(0, 2) MIE_CS(1, 3) MIE_CS(4, 5) MIE_CS(7, 8)
+    MIE_CS(1, 4) MIE_CS(3, 6) MIE_CS(5, 7)
+    MIE_CS(0, 1) MIE_CS(2, 4) MIE_CS(3, 5) MIE_CS(6, 8)
+    MIE_CS(2, 3) MIE_CS(4, 5) MIE_CS(6, 7)
+    MIE_CS(1, 2) MIE_CS(3, 4) MIE_CS(5, 6)
+#undef MIE_CS
+}
+template <typename P>
+__device__ __forceinline__ P select27_sorted(const P* A, const P* B, const P* C) {
+    P W[8], Y[5];
+    // columns 5..8 -> minimum (row 0), columns 0..3 -> maximum (row 2), columns 2..6 -> middle (row 1)
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+        const P lo = pmin(A[c], B[c]), hi = pmax(A[c], B[c]);
+        if (c >= 5) W[c - 5] = pmin(lo, C[c]);
+        if (c <= 3) W[4 + c] = pmax(hi, C[c]);
+        if (c >= 2 && c <= 6) Y[c - 2] = c <= 4 ? pmax(lo, pmin(hi, C[c])) : pmin(hi, pmax(lo, C[c]));
+    }
+    cswap(W[0], W[4]); cswap(W[1], W[5]); cswap(W[2], W[6]); cswap(W[3], W[7]);
+    cswap(W[2], W[4]); cswap(W[3], W[5]);
+    cswap(W[1], W[2]); cswap(W[3], W[4]); cswap(W[5], W[6]);
+    P m = W[6];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) m = pmin(m, pmax(W[5 - j], Y[j]));
+    return m;
+}
 
 template <typename T> struct PackedOf;
 template <> struct PackedOf<uint16_t> { using type = PackedU16; };
@@ -286,9 +349,11 @@ median3d_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t s
     load_plane(z0 - 1);
     load_plane(z0);
     __syncthreads();
-    P win[3][9];   // win[k] = plane z - 1 + k of the current step (rotated by register renaming below)
+    P win[3][9];   // win[k] = SORTED 3x3 neighbourhood of plane z - 1 + k (rotated by register renaming below)
     plane_words(z0 - 1, win[0]);
     plane_words(z0, win[1]);
+    sort9(win[0]);
+    sort9(win[1]);
     const int y = ty0 + ly, x = tx0 + 2 * lx;
     for (int zb = z0; zb < z1; zb += 3) {
 #pragma unroll
@@ -298,12 +363,8 @@ median3d_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t s
                 load_plane(z + 1);
                 __syncthreads();
                 plane_words(z + 1, win[(u + 2) % 3]);
-                P v[27];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) {
-                    v[k] = win[u % 3][k]; v[9 + k] = win[(u + 1) % 3][k]; v[18 + k] = win[(u + 2) % 3][k];
-                }
-                const uint32_t m = median_of<27, P>(v).v;
+                sort9(win[(u + 2) % 3]);
+                const uint32_t m = select27_sorted(win[u % 3], win[(u + 1) % 3], win[(u + 2) % 3]).v;
                 if (y < h && x < w) {
                     T* o = dst + (int64_t)z * dsd + (int64_t)y * dsh + x;
                     if (x + 1 < w && ((reinterpret_cast<uintptr_t>(o) & 3) == 0)) {
@@ -318,6 +379,116 @@ median3d_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t s
             }
         }
     }
+}
+
+// ---------------------------------------------------------------- 2-D 3x3, 16-bit pixels, marching rows
+// A lane owns 8 consecutive columns (one 128-bit load per row = four packed pixel pairs) and marches
+// down a band of rows with the last three rows in registers; the pair to the left / right comes from the
+// neighbouring lane by shuffle (from global memory or the border rule at the ends of the warp's 256-column
+// strip).  Per row the three vertical samples of every packed word are sorted once (3 compare-exchanges,
+// shared by the three windows that contain the column); the x-1 / x+1 neighbours of the sorted triples are
+// byte permutes of adjacent words (sorting columns commutes with shifting them).  Then the classic
+// median-of-9 identity: med3(max of the column minima, med3 of the column medians, min of the column
+// maxima).  ~27 integer-pipe instructions per pixel pair, no shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                        int64_t dsh, int64_t nplanes, int h, int w, int strips, int bands, int rows_per_band,
+                        int border) {
+    using P = typename PackedOf<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int strip = (int)(wg % strips), band = (int)((wg / strips) % bands);
+    const int64_t n = wg / ((int64_t)strips * bands);
+    if (n >= nplanes) return;                      // warp-uniform
+    const int x0 = strip * 256 + lane * 8;
+    const bool active = x0 < w;
+    const int y0 = band * rows_per_band, y1 = min(y0 + rows_per_band, h);
+    const T* plane = src + n * ssn;
+    T* oplane = dst + n * dsn;
+
+    // six packed words of image row y: [pair left of x0 | four own pairs | pair right of x0 + 7]
+    auto load_row = [&](int y, P* r) {
+        const int sy = border_index(y, h, border);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t left = 0u, right = 0u;
+        if (sy >= 0) {                              // uniform
+            const T* row = plane + (int64_t)sy * ssh;
+            if (active) v = __ldg(reinterpret_cast<const uint4*>(row + x0));
+            left = __shfl_up_sync(0xffffffffu, v.w, 1);
+            right = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (active) {
+                if (x0 == 0) {                      // pixel -1 sits in the high half
+                    left = border == MIE_BORDER_REFLECT ? (v.x & 0xFFFF0000u)
+                         : border == MIE_BORDER_REPLICATE ? (v.x << 16) : 0u;
+                } else if (lane == 0) {
+                    left = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
+                }
+                if (x0 + 8 == w) {                  // pixel w sits in the low half
+                    right = border == MIE_BORDER_REFLECT ? (v.w & 0xFFFFu)
+                          : border == MIE_BORDER_REPLICATE ? (v.w >> 16) : 0u;
+                } else if (lane == 31) {
+                    right = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
+                }
+            }
+        }
+        r[0].v = left; r[1].v = v.x; r[2].v = v.y; r[3].v = v.z; r[4].v = v.w; r[5].v = right;
+    };
+
+    P ring[3][6];
+    load_row(y0 - 1, ring[0]);
+    load_row(y0, ring[1]);
+    for (int yb = y0; yb < y1; yb += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int y = yb + u;
+            if (y < y1) {                           // uniform
+                load_row(y + 1, ring[(u + 2) % 3]);
+                P lo[6], mi[6], hi[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    P a = ring[u % 3][c], b = ring[(u + 1) % 3][c], cc = ring[(u + 2) % 3][c];
+                    cswap(a, b); cswap(b, cc); cswap(a, b);
+                    lo[c] = a; mi[c] = b; hi[c] = cc;
+                }
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    P Llo, Lmi, Lhi, Rlo, Rmi, Rhi;
+                    Llo.v = __byte_perm(lo[k].v, lo[k + 1].v, 0x5432); Rlo.v = __byte_perm(lo[k + 1].v, lo[k + 2].v, 0x5432);
+                    Lmi.v = __byte_perm(mi[k].v, mi[k + 1].v, 0x5432); Rmi.v = __byte_perm(mi[k + 1].v, mi[k + 2].v, 0x5432);
+                    Lhi.v = __byte_perm(hi[k].v, hi[k + 1].v, 0x5432); Rhi.v = __byte_perm(hi[k + 1].v, hi[k + 2].v, 0x5432);
+                    const P maxlo = pmax(pmax(Llo, lo[k + 1]), Rlo);
+                    const P minhi = pmin(pmin(Lhi, hi[k + 1]), Rhi);
+                    const P a = pmin(Lmi, mi[k + 1]), b = pmax(Lmi, mi[k + 1]);
+                    const P medmi = pmax(a, pmin(b, Rmi));
+                    const P c = pmin(maxlo, medmi), d = pmax(maxlo, medmi);
+                    o[k] = pmax(c, pmin(d, minhi)).v;
+                }
+                if (active) *reinterpret_cast<uint4*>(oplane + (int64_t)y * dsh + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
+// 0 = launched, < 0 = not applicable (caller falls back to the generic kernel), > 0 = CUDA error
+template <typename T>
+static int try_median3x3_packed(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
+                                int64_t dsn, int64_t dsh, int border, cudaStream_t st) {
+    static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
+    if (off || (w & 7) || h < 2) return -1;
+    if (((uintptr_t)src % 16) || ((ssn * 2) % 16) || ((ssh * 2) % 16)) return -1;
+    if (((uintptr_t)dst % 16) || ((dsn * 2) % 16) || ((dsh * 2) % 16)) return -1;
+    const int strips = ceil_div(w, 256);
+    int rows = 32;                                 // 2 halo rows per band: 6 % extra loads
+    while (rows > 8 && n * strips * ceil_div(h, rows) < 8 * 148 * 4) rows >>= 1;   // small jobs: more warps
+    const int bands = ceil_div(h, rows);
+    const int64_t warps = n * strips * bands;
+    const int64_t blocks = (warps + 7) / 8;
+    if (blocks > 2147483647LL) return MIE_E_SHAPE;
+    median3x3_packed_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)src, (T*)dst, ssn, ssh, dsn, dsh, n, h, w,
+                                                                strips, bands, rows, border);
+    return check_launch();
 }
 
 template <typename T>
@@ -357,6 +528,13 @@ int mie_median2d(const void* src, void* dst, int dtype, int64_t n, int h, int w,
     if (ky <= 0 || kx <= 0 || !(ky & 1) || !(kx & 1)) return MIE_E_KERNEL;
     if (n == 0) return MIE_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (ky == 3 && kx == 3 && (dtype == MIE_U16 || dtype == MIE_I16)) {
+        rc = dtype == MIE_U16 ? try_median3x3_packed<uint16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
+                                                               dst_stride_n, dst_stride_h, border, st)
+                              : try_median3x3_packed<int16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
+                                                              dst_stride_n, dst_stride_h, border, st);
+        if (rc >= 0) return rc;
+    }
     MIE_DISPATCH_SRC(dtype, return dispatch_median2d<SrcT>(ky, kx, src, dst, n, h, w, src_stride_n, src_stride_h,
                                                           dst_stride_n, dst_stride_h, border, st));
     return MIE_OK;

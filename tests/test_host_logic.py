@@ -120,3 +120,54 @@ def test_chain_config_validation_without_gpu():
         M.enhance_chain(x, M.ChainConfig(denoise_kernel_size=8))
     with pytest.raises(RuntimeError, match="no CPU path"):
         M.enhance_chain(x)
+
+
+# ---------------------------------------------------------------------------- median selection networks
+SORT9 = [(0, 3), (1, 7), (2, 5), (4, 8), (0, 7), (2, 4), (3, 8), (5, 6), (0, 2), (1, 3), (4, 5), (7, 8), (1, 4),
+         (3, 6), (5, 7), (0, 1), (2, 4), (3, 5), (6, 8), (2, 3), (4, 5), (6, 7), (1, 2), (3, 4), (5, 6)]
+MERGE44 = [(0, 4), (1, 5), (2, 6), (3, 7), (2, 4), (3, 5), (1, 2), (3, 4), (5, 6)]
+
+
+def _cs(a, i, j):
+    lo, hi = np.minimum(a[i], a[j]), np.maximum(a[i], a[j])
+    a[i], a[j] = lo, hi
+
+
+def _select27_sorted(A, B, C):
+    """Python twin of select27_sorted (csrc/median.cu): rank 13 of 27 from three sorted 9-lists."""
+    W, Y = [None] * 8, [None] * 5
+    for c in range(9):
+        lo, hi = np.minimum(A[c], B[c]), np.maximum(A[c], B[c])
+        if c >= 5:
+            W[c - 5] = np.minimum(lo, C[c])
+        if c <= 3:
+            W[4 + c] = np.maximum(hi, C[c])
+        if 2 <= c <= 6:
+            Y[c - 2] = np.maximum(lo, np.minimum(hi, C[c])) if c <= 4 else np.minimum(hi, np.maximum(lo, C[c]))
+    for i, j in MERGE44:
+        _cs(W, i, j)
+    m = W[6]
+    for j in range(5):
+        m = np.minimum(m, np.maximum(W[5 - j], Y[j]))
+    return m
+
+
+def test_median27_selection_network():
+    # the 9-input sorting network, exhaustively on 0/1 inputs (0-1 principle)
+    bits = ((np.arange(512)[:, None] >> np.arange(9)[None, :]) & 1).T.copy()
+    a = [bits[i].copy() for i in range(9)]
+    for i, j in SORT9:
+        _cs(a, i, j)
+    assert np.array_equal(np.stack(a), np.sort(bits, axis=0))
+    # the selection from three sorted planes: every 0/1 pattern class (counts of ones per list) ...
+    cnt = np.stack(np.meshgrid(np.arange(10), np.arange(10), np.arange(10), indexing="ij"), -1).reshape(-1, 3)
+    lists = [(np.arange(9)[:, None] >= 9 - cnt[None, :, k]).astype(np.int64) for k in range(3)]
+    got = _select27_sorted(list(lists[0]), list(lists[1]), list(lists[2]))
+    assert np.array_equal(got, (cnt.sum(1) >= 14).astype(np.int64))
+    # ... and random values with many ties
+    rng = np.random.default_rng(0)
+    for hi in (2, 3, 7, 1000):
+        v = rng.integers(0, hi, (27, 20000))
+        s = [np.sort(v[9 * k:9 * k + 9], axis=0) for k in range(3)]
+        got = _select27_sorted(list(s[0]), list(s[1]), list(s[2]))
+        assert np.array_equal(got, np.sort(v, axis=0)[13])
