@@ -381,6 +381,93 @@ median3d_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t s
     }
 }
 
+// ---------------------------------------------------------------- 3-D, 3x3x3, 16-bit, register marching, no smem
+// Even widths with 4-byte-aligned rows: a lane owns one voxel pair and reads the nine packed words of the
+// incoming plane (rows y-1..y+1, pairs x-2, x, x+2) straight from global memory — every word is fetched
+// by nine lanes of the same block, so the loads hit L1 — instead of staging planes in shared memory:
+// no per-voxel index arithmetic, no barriers.  The two older planes stay in registers as sorted 9-lists.
+template <typename T, bool EDGE>
+__device__ __forceinline__ void median3d_direct_body(const T* __restrict__ src, T* __restrict__ dst, int64_t ssd,
+                                                     int64_t ssh, int64_t dsd, int64_t dsh, int d, int h, int w, int x,
+                                                     int y, int z0, int z1, const T* __restrict__ halo_lo,
+                                                     const T* __restrict__ halo_hi, bool rep) {
+    using P = typename PackedOf<T>::type;
+    // Rows / pairs outside the volume are read from a clamped (always valid) address and replaced by the
+    // border value with a select, so the nine loads of a plane are independent and issue back to back;
+    // interior tiles (EDGE == false) need no selects at all.
+    const int yc[3] = {EDGE ? max(y - 1, 0) : y - 1, y, EDGE ? min(y + 1, h - 1) : y + 1};
+    const bool row_zero[3] = {EDGE && !rep && y == 0, false, EDGE && !rep && y + 1 >= h};
+    const bool has_l = !EDGE || x >= 2, has_r = !EDGE || x + 2 < w;
+    const int64_t xl = has_l ? -1 : 0, xr = has_r ? 1 : 0;
+
+    auto plane_words = [&](int z, P* out) {
+        const T* p = src + (int64_t)min(max(z, 0), d - 1) * ssd;   // replicate rule
+        int64_t rs = ssh;
+        bool plane_zero = false;
+        if (z < 0) {
+            if (halo_lo) { p = halo_lo; rs = w; }
+            else plane_zero = !rep;
+        } else if (z >= d) {
+            if (halo_hi) { p = halo_hi; rs = w; }
+            else plane_zero = !rep;
+        }
+        if (plane_zero) {                                          // uniform: constant rule beyond the volume
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out[k].v = 0u;
+            return;
+        }
+        uint32_t w0[3], w1[3], w2[3];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(p + (int64_t)yc[dy] * rs + x);
+            w1[dy] = __ldg(row);
+            w0[dy] = __ldg(row + xl);
+            w2[dy] = __ldg(row + xr);
+        }
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t c = row_zero[dy] ? 0u : w1[dy];
+            const uint32_t l = has_l ? (row_zero[dy] ? 0u : w0[dy]) : (rep ? c << 16 : 0u);   // voxel x-1, high half
+            const uint32_t r = has_r ? (row_zero[dy] ? 0u : w2[dy]) : (rep ? c >> 16 : 0u);   // voxel x+2, low half
+            out[dy * 3 + 0].v = __byte_perm(l, c, 0x5432);                                    // (x-1, x)
+            out[dy * 3 + 1].v = c;                                                            // (x, x+1)
+            out[dy * 3 + 2].v = __byte_perm(c, r, 0x5432);                                    // (x+1, x+2)
+        }
+        sort9(out);
+    };
+
+    P win[3][9];   // win[k] = SORTED 3x3 neighbourhood of plane z - 1 + k (rotated by register renaming)
+    plane_words(z0 - 1, win[0]);
+    plane_words(z0, win[1]);
+    T* o = dst + (int64_t)y * dsh + x;
+    for (int zb = z0; zb < z1; zb += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int z = zb + u;
+            if (z < z1) {   // uniform
+                plane_words(z + 1, win[(u + 2) % 3]);
+                const uint32_t m = select27_sorted(win[u % 3], win[(u + 1) % 3], win[(u + 2) % 3]).v;
+                *reinterpret_cast<uint32_t*>(o + (int64_t)z * dsd) = m;
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+median3d_direct_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t ssd, int64_t ssh, int64_t dsd,
+                       int64_t dsh, int d, int h, int w, int tiles_x, int zchunk, const T* __restrict__ halo_lo,
+                       const T* __restrict__ halo_hi, int border) {
+    const int tx0 = (int)(blockIdx.x % tiles_x) * 64, ty0 = (int)(blockIdx.x / tiles_x) * 8;
+    const int z0 = blockIdx.y * zchunk, z1 = min(z0 + zchunk, d);
+    const int x = tx0 + 2 * (threadIdx.x & 31), y = ty0 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;                  // no barriers below
+    const bool rep = border == MIE_BORDER_REPLICATE;
+    const bool interior = tx0 > 0 && tx0 + 64 < w && ty0 > 0 && ty0 + 8 < h;   // block-uniform
+    if (interior) median3d_direct_body<T, false>(src, dst, ssd, ssh, dsd, dsh, d, h, w, x, y, z0, z1, halo_lo, halo_hi, rep);
+    else median3d_direct_body<T, true>(src, dst, ssd, ssh, dsd, dsh, d, h, w, x, y, z0, z1, halo_lo, halo_hi, rep);
+}
+
 // ---------------------------------------------------------------- 2-D 3x3, 16-bit pixels, marching rows
 // A lane owns 8 consecutive columns (one 128-bit load per row = four packed pixel pairs) and marches
 // down a band of rows with the last three rows in registers; the pair to the left / right comes from the
@@ -497,6 +584,16 @@ static int launch_median3d(const void* src, void* dst, int d, int h, int w, int6
     const int zchunk = d >= 64 ? 32 : (d >= 16 ? 8 : d);
     if constexpr (sizeof(T) == 2) {
         static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
+        const bool words_ok = !(w & 1) && !(ssd & 1) && !(ssh & 1) && !(dsd & 1) && !(dsh & 1) &&
+                              !((uintptr_t)src & 3) && !((uintptr_t)dst & 3) && !((uintptr_t)lo & 3) &&
+                              !((uintptr_t)hi & 3);
+        if (!off && words_ok) {
+            const int tiles_x = ceil_div(w, 64), tiles_y = ceil_div(h, 8);
+            dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)ceil_div(d, zchunk));
+            median3d_direct_kernel<T><<<grid, 256, 0, st>>>((const T*)src, (T*)dst, ssd, ssh, dsd, dsh, d, h, w, tiles_x,
+                                                           zchunk, (const T*)lo, (const T*)hi, border);
+            return check_launch();
+        }
         if (!off) {
             const int tiles_x = ceil_div(w, 64), tiles_y = ceil_div(h, 8);
             dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)ceil_div(d, zchunk));

@@ -96,7 +96,7 @@ def test_median3d_bit_exact_against_oracle_and_scipy(dev, dtype):
     import mie_b200 as M
     import oracle as O
 
-    for shape in [(12, 20, 24), (70, 33, 65), (1, 9, 9), (3, 8, 40)]:
+    for shape in [(12, 20, 24), (70, 33, 65), (1, 9, 9), (3, 8, 40), (20, 21, 130), (9, 17, 66), (2, 1, 2)]:
         vol = rand(dtype, shape, 6)
         for mode in ("nearest", "constant"):
             got = cpu(M.median(gpu(vol, dev), mode=mode))
