@@ -41,8 +41,14 @@ extern "C" {
 enum mie_dtype { MIE_U8 = 0, MIE_U16 = 1, MIE_I16 = 2, MIE_F32 = 3 };
 
 /* kornia border_type names: 'constant' (zeros), 'reflect' (mirror, edge not
- * repeated), 'replicate', 'circular'.  scipy.ndimage 'nearest' == replicate. */
-enum mie_border { MIE_BORDER_CONSTANT = 0, MIE_BORDER_REFLECT = 1, MIE_BORDER_REPLICATE = 2, MIE_BORDER_CIRCULAR = 3 };
+ * repeated = scipy.ndimage 'mirror'), 'replicate' (= scipy 'nearest'), 'circular' (= scipy 'wrap').
+ * MIE_BORDER_SYMMETRIC mirrors WITH the edge sample repeated (d c b a | a b c d | d c b a): scipy.ndimage's
+ * 'reflect', the mode skimage.filters.unsharp_mask uses; accepted by mie_gaussian2d / mie_unsharp /
+ * mie_median2d. */
+enum mie_border {
+    MIE_BORDER_CONSTANT = 0, MIE_BORDER_REFLECT = 1, MIE_BORDER_REPLICATE = 2, MIE_BORDER_CIRCULAR = 3,
+    MIE_BORDER_SYMMETRIC = 4
+};
 
 /* CLAHE semantics selector. */
 enum mie_clahe_semantics { MIE_CLAHE_KORNIA = 0, MIE_CLAHE_OPENCV = 1 };
@@ -88,6 +94,18 @@ int mie_unsharp(const void* src, void* dst, int src_dtype, int dst_dtype,
                 int64_t dst_stride_n, int64_t dst_stride_h,
                 const float* wx, int kx, const float* wy, int ky, int border,
                 float lo, float hi, void* stream);
+
+/* skimage.filters.unsharp_mask(image, radius, amount) (reference pyproject.toml:12; SURVEY.md §2.2,
+ * §8(f) F3): out = x + amount * (x - blur(x)), computed as fma(amount, x - blur, x) (amount == 1 gives
+ * mie_unsharp's result bit for bit); clip != 0 clamps the result to [0, 1] before any quantisation
+ * (skimage without preserve_range).  skimage's blur is scipy.ndimage.gaussian_filter(sigma = radius,
+ * mode = 'reflect' = MIE_BORDER_SYMMETRIC, truncate = 4): taps 2*int(4*radius + 0.5) + 1.            */
+int mie_unsharp_amount(const void* src, void* dst, int src_dtype, int dst_dtype,
+                       int64_t n, int h, int w,
+                       int64_t src_stride_n, int64_t src_stride_h,
+                       int64_t dst_stride_n, int64_t dst_stride_h,
+                       const float* wx, int kx, const float* wy, int ky, int border,
+                       float amount, int clip, float lo, float hi, void* stream);
 
 /* ------------------------------------------------------------------ CLAHE
  * Replaces kornia.enhance.equalize_clahe(input, clip_limit, grid_size)
@@ -193,6 +211,28 @@ int mie_nlm(const void* src, void* dst, int src_dtype, int dst_dtype,
             int64_t dst_stride_n, int64_t dst_stride_h,
             int patch_size, int patch_distance, float h_param, float sigma,
             float lo, float hi, void* stream);
+
+/* ------------------------------------------------------------------ quality metrics
+ * Device-side reductions behind sewar.full_ref.mse / rmse / psnr / ssim (reference pyproject.toml:13,
+ * pin uv.lock:692-700: sewar 0.4.6, numpy/scipy code, not installable here — semantics RECALLED).
+ * Pixels are used raw (no [0,1] mapping).  `out` is a DEVICE array of n x 2 float64:
+ *   mie_sqdiff_sums: out[i] = { sum (a-b)^2, sum |a-b| } of plane i  (integer planes: exact 64-bit sums)
+ *   mie_ssim_sums  : out[i] = { sum ssim_map, sum cs_map } over the (h-ws+1) x (w-ws+1) 'valid' windows
+ *                    of a ws x ws UNIFORM filter (sewar's default fltr_specs), ws <= 16:
+ *                    mu = S/ws^2, var = S2/ws^2 - mu^2, cov = Sab/ws^2 - mu_a mu_b (window sums exact for
+ *                    integer planes), ssim = (2 mu_a mu_b + c1)(2 cov + c2) / ((mu_a^2 + mu_b^2 + c1)
+ *                    (var_a + var_b + c2)), cs = (2 cov + c2) / (var_a + var_b + c2), float64.
+ * The caller divides by the pixel / window count (and takes sqrt / log10).  workspace >=
+ * mie_metric_workspace_bytes(n, h, w, ws) with ws = 0 for mie_sqdiff_sums.  Reductions run in a
+ * fixed order: results are bit-reproducible from run to run.                                        */
+size_t mie_metric_workspace_bytes(int64_t n, int h, int w, int ws);
+int mie_sqdiff_sums(const void* a, const void* b, int dtype, int64_t n, int h, int w,
+                    int64_t a_stride_n, int64_t a_stride_h, int64_t b_stride_n, int64_t b_stride_h,
+                    double* out, void* workspace, size_t workspace_bytes, void* stream);
+int mie_ssim_sums(const void* a, const void* b, int dtype, int64_t n, int h, int w,
+                  int64_t a_stride_n, int64_t a_stride_h, int64_t b_stride_n, int64_t b_stride_h,
+                  int ws, double c1, double c2,
+                  double* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ fused chain (BASELINE.json config 2)
  * Gaussian denoise -> CLAHE -> unsharp mask in two launches; equals

@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libmie_b200.so")
 
 MIE_U8, MIE_U16, MIE_I16, MIE_F32 = 0, 1, 2, 3
-BORDER = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3}
+BORDER = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3, "symmetric": 4}
 CLAHE_KORNIA, CLAHE_OPENCV = 0, 1
 
 DTYPE_CODE = {torch.uint8: MIE_U8, torch.uint16: MIE_U16, torch.int16: MIE_I16, torch.float32: MIE_F32}
@@ -34,6 +34,7 @@ SIGNATURES = {
     "mie_device_info": ([C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)], _i),
     "mie_gaussian2d": ([_p, _p, _i, _i, *_planes, *_taps, _i, _f, _f, _p], _i),
     "mie_unsharp": ([_p, _p, _i, _i, *_planes, *_taps, _i, _f, _f, _p], _i),
+    "mie_unsharp_amount": ([_p, _p, _i, _i, *_planes, *_taps, _i, _f, _i, _f, _f, _p], _i),
     "mie_clahe_workspace_bytes": ([_i64, _i, _i, _i, _i], _sz),
     "mie_clahe_hist": ([_p, _i, _i64, _i, _i, _i64, _i64, _i, _i, _i, _f, _f, _p, _p], _i),
     "mie_clahe_luts": ([_p, _i, _i64, _i, _i, _i64, _i64, _i, _i, _d, _i, _f, _f, _p, _p], _i),
@@ -47,6 +48,9 @@ SIGNATURES = {
     "mie_median3d": ([_p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _i, _p], _i),
     "mie_bilateral": ([_p, _p, _i, _i, *_planes, _p, _i, _i, _f, _i, _f, _f, _p], _i),
     "mie_nlm": ([_p, _p, _i, _i, *_planes, _i, _i, _f, _f, _f, _f, _p], _i),
+    "mie_metric_workspace_bytes": ([_i64, _i, _i, _i], _sz),
+    "mie_sqdiff_sums": ([_p, _p, _i, *_planes, _p, _p, _sz, _p], _i),
+    "mie_ssim_sums": ([_p, _p, _i, *_planes, _i, _d, _d, _p, _p, _sz, _p], _i),
     "mie_chain_workspace_bytes": ([_i64, _i, _i, _i, _i], _sz),
     "mie_chain_gauss_clahe_unsharp": (
         [_p, _p, _i, _i, *_planes, *_taps, _i, _i, _d, *_taps, _i, _f, _f, _i, _p, _sz, _p], _i),

@@ -22,7 +22,7 @@ namespace mie {
 
 int gauss_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
                int64_t dsn, int64_t dsh, const float* wxp, int kx, const float* wyp, int ky, int border, float lo,
-               float hi, int unsharp, bool internal, cudaStream_t st);
+               float hi, int unsharp, bool internal, cudaStream_t st, float amount = 1.0f, int clip = 0);
 int check_taps(const float* wx, int kx, const float* wy, int ky, int border, int h, int w);
 int clahe_luts_impl(const void* src, int sd, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int gh, int gw,
                     double clip_limit, int semantics, float lo, float hi, uint32_t* hist, uint8_t* luts,

@@ -278,7 +278,7 @@ bool fast_chain_ok(const ClaheGeom& g, int sd, int dd, const void* src, int64_t 
     static const int esz[4] = {1, 2, 2, 4};
     if (g.th != kTile || g.tw != kTile || g.hp != g.h || g.wp != g.w) return false;
     if (kg < 3 || kg > 9 || ku < 3 || ku > 9) return false;
-    if (border == MIE_BORDER_CIRCULAR) return false;
+    if (border == MIE_BORDER_CIRCULAR || border == MIE_BORDER_SYMMETRIC) return false;
     if (!default_range(sd, lo, hi) || !default_range(dd, lo, hi)) return false;
     // 16-byte aligned rows for the vector loads / stores
     if (((uintptr_t)src % 16) || ((ssn * esz[sd]) % 16) || ((ssh * esz[sd]) % 16)) return false;

@@ -20,6 +20,8 @@ struct GaussArgs {
     int tiles_x, tiles_y;
     int border;
     int unsharp;
+    float amount;   // out = fma(amount, x - blur, x); amount == 1 is kornia's x + (x - blur), bit for bit
+    int clip;       // clamp the result to [0, 1] (skimage.filters.unsharp_mask without preserve_range)
     float lo, rg;
 };
 
@@ -62,7 +64,10 @@ gauss_tile_kernel(GaussArgs a, Taps wx, Taps wy) {
         if (a.unsharp) {
             const float* ctr = s_in + (r + R) * TileSmem<R>::pin + c + R;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = __fadd_rn(ctr[k], __fsub_rn(ctr[k], o[k]));
+            for (int k = 0; k < 4; ++k) {
+                o[k] = __fmaf_rn(a.amount, __fsub_rn(ctr[k], o[k]), ctr[k]);
+                if (a.clip) o[k] = fminf(fmaxf(o[k], 0.0f), 1.0f);
+            }
         }
         DstT* drow = oplane + (int64_t)y * a.dsh;
 #pragma unroll
@@ -112,7 +117,8 @@ gauss_generic_kernel(GaussArgs a, Taps wx, int rx, Taps wy, int ry) {
         for (int t = 1; t <= 2 * ry; ++t) acc = __fmaf_rn(wy.w[t], p[t * T], acc);
         if (a.unsharp) {
             const float ctr = s_in[(r + ry) * ew + c + rx];
-            acc = __fadd_rn(ctr, __fsub_rn(ctr, acc));
+            acc = __fmaf_rn(a.amount, __fsub_rn(ctr, acc), ctr);
+            if (a.clip) acc = fminf(fmaxf(acc, 0.0f), 1.0f);
         }
         oplane[(int64_t)y * a.dsh + x] = Px<DstT>::from01(acc, a.lo, a.rg);
     }
@@ -157,7 +163,7 @@ static int launch_any(const GaussArgs& a, const Taps& wx, int kx, const Taps& wy
 int check_taps(const float* wx, int kx, const float* wy, int ky, int border, int h, int w) {
     if (!wx || !wy) return MIE_E_NULL;
     if (kx <= 0 || ky <= 0 || !(kx & 1) || !(ky & 1) || kx > MIE_MAX_TAPS || ky > MIE_MAX_TAPS) return MIE_E_KERNEL;
-    if (border < MIE_BORDER_CONSTANT || border > MIE_BORDER_CIRCULAR) return MIE_E_BORDER;
+    if (border < MIE_BORDER_CONSTANT || border > MIE_BORDER_SYMMETRIC) return MIE_E_BORDER;
     // torch F.pad: reflect needs pad < dim, circular pad <= dim.
     if (border == MIE_BORDER_REFLECT && (kx / 2 >= w || ky / 2 >= h)) return MIE_E_BORDER;
     if (border == MIE_BORDER_CIRCULAR && (kx / 2 > w || ky / 2 > h)) return MIE_E_BORDER;
@@ -168,7 +174,7 @@ int check_taps(const float* wx, int kx, const float* wy, int ky, int border, int
 // unfused chain fallback); the public ABI restricts dst to {src, F32}.
 int gauss_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
                int64_t dsn, int64_t dsh, const float* wxp, int kx, const float* wyp, int ky, int border, float lo,
-               float hi, int unsharp, bool internal, cudaStream_t st) {
+               float hi, int unsharp, bool internal, cudaStream_t st, float amount, int clip) {
     int rc = check_planes(src, dst, n, h, w, ssn, ssh, dsn, dsh);
     if (rc) return rc;
     if (!valid_dtype(sd) || !valid_dtype(dd)) return MIE_E_DTYPE;
@@ -183,11 +189,13 @@ int gauss_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int
         wy.w[i] = i < ky ? wyp[i] : 0.f;
     }
     // common geometry (square 9-tap kernel, W % 128 == 0, H % 64 == 0): marching kernel (gauss_march.cu)
-    if (gauss_march_ok(src, dst, sd, dd, h, w, ssn, ssh, dsn, dsh, kx, ky, border, lo, hi))
+    if ((!unsharp || (amount == 1.0f && !clip)) &&
+        gauss_march_ok(src, dst, sd, dd, h, w, ssn, ssh, dsn, dsh, kx, ky, border, lo, hi))
         return launch_gauss_march(src, dst, sd, dd, n, h, w, ssn, ssh, dsn, dsh, wx, wy, border, unsharp, st);
     GaussArgs a;
     a.src = src; a.dst = dst; a.ssn = ssn; a.ssh = ssh; a.dsn = dsn; a.dsh = dsh;
     a.h = h; a.w = w; a.tiles_x = a.tiles_y = 0; a.border = border; a.unsharp = unsharp;
+    a.amount = amount; a.clip = clip;
     a.lo = lo; a.rg = hi - lo;
     if (sd == MIE_F32 && dd != MIE_F32) {
         switch (dd) {
@@ -210,14 +218,23 @@ int mie_gaussian2d(const void* src, void* dst, int src_dtype, int dst_dtype, int
                    int64_t src_stride_n, int64_t src_stride_h, int64_t dst_stride_n, int64_t dst_stride_h,
                    const float* wx, int kx, const float* wy, int ky, int border, float lo, float hi, void* stream) {
     return gauss_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n,
-                      dst_stride_h, wx, kx, wy, ky, border, lo, hi, 0, false, (cudaStream_t)stream);
+                      dst_stride_h, wx, kx, wy, ky, border, lo, hi, 0, false, (cudaStream_t)stream, 1.0f, 0);
 }
 
 int mie_unsharp(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t n, int h, int w,
                 int64_t src_stride_n, int64_t src_stride_h, int64_t dst_stride_n, int64_t dst_stride_h,
                 const float* wx, int kx, const float* wy, int ky, int border, float lo, float hi, void* stream) {
     return gauss_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n,
-                      dst_stride_h, wx, kx, wy, ky, border, lo, hi, 1, false, (cudaStream_t)stream);
+                      dst_stride_h, wx, kx, wy, ky, border, lo, hi, 1, false, (cudaStream_t)stream, 1.0f, 0);
+}
+
+int mie_unsharp_amount(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t n, int h, int w,
+                       int64_t src_stride_n, int64_t src_stride_h, int64_t dst_stride_n, int64_t dst_stride_h,
+                       const float* wx, int kx, const float* wy, int ky, int border, float amount, int clip, float lo,
+                       float hi, void* stream) {
+    return gauss_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n,
+                      dst_stride_h, wx, kx, wy, ky, border, lo, hi, 1, false, (cudaStream_t)stream, amount,
+                      clip ? 1 : 0);
 }
 
 }  // extern "C"

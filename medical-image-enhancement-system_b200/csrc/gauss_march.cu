@@ -152,7 +152,7 @@ bool gauss_march_ok(const void* src, const void* dst, int sd, int dd, int h, int
     if (off) return false;
     if (kx != 9 || ky != 9) return false;
     if (w % 128 != 0 || w > 1024 || h % kTile != 0) return false;
-    if (border == MIE_BORDER_CIRCULAR) return false;
+    if (border == MIE_BORDER_CIRCULAR || border == MIE_BORDER_SYMMETRIC) return false;
     if (dd != sd && dd != MIE_F32) return false;
     if (!default_range_of(sd, lo, hi) || !default_range_of(dd, lo, hi)) return false;
     if (((uintptr_t)src % 16) || ((ssn * esz[sd]) % 16) || ((ssh * esz[sd]) % 16)) return false;

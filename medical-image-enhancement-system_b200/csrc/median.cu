@@ -507,13 +507,13 @@ median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
             if (active) {
                 if (x0 == 0) {                      // pixel -1 sits in the high half
                     left = border == MIE_BORDER_REFLECT ? (v.x & 0xFFFF0000u)
-                         : border == MIE_BORDER_REPLICATE ? (v.x << 16) : 0u;
+                         : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? (v.x << 16) : 0u;
                 } else if (lane == 0) {
                     left = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
                 }
                 if (x0 + 8 == w) {                  // pixel w sits in the low half
                     right = border == MIE_BORDER_REFLECT ? (v.w & 0xFFFFu)
-                          : border == MIE_BORDER_REPLICATE ? (v.w >> 16) : 0u;
+                          : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? (v.w >> 16) : 0u;
                 } else if (lane == 31) {
                     right = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
                 }
@@ -620,7 +620,8 @@ int mie_median2d(const void* src, void* dst, int dtype, int64_t n, int h, int w,
                  void* stream) {
     int rc = check_planes(src, dst, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h);
     if (rc) return rc;
-    if (border != MIE_BORDER_CONSTANT && border != MIE_BORDER_REPLICATE && border != MIE_BORDER_REFLECT)
+    if (border != MIE_BORDER_CONSTANT && border != MIE_BORDER_REPLICATE && border != MIE_BORDER_REFLECT &&
+        border != MIE_BORDER_SYMMETRIC)
         return MIE_E_BORDER;
     if (ky <= 0 || kx <= 0 || !(ky & 1) || !(kx & 1)) return MIE_E_KERNEL;
     if (n == 0) return MIE_OK;

@@ -75,6 +75,12 @@ __host__ __device__ __forceinline__ int border_index(int i, int n, int mode) {
             int m = i % n;
             return m < 0 ? m + n : m;
         }
+        case MIE_BORDER_SYMMETRIC: {   // period 2n: 0..n-1, n-1..0
+            int p = 2 * n;
+            int m = i % p;
+            if (m < 0) m += p;
+            return m < n ? m : p - 1 - m;
+        }
         default:
             return -1;
     }

@@ -32,7 +32,7 @@
 #define MIE_CLONES
 #endif
 
-enum { B_CONSTANT = 0, B_REFLECT = 1, B_REPLICATE = 2, B_CIRCULAR = 3 };
+enum { B_CONSTANT = 0, B_REFLECT = 1, B_REPLICATE = 2, B_CIRCULAR = 3, B_SYMMETRIC = 4 };
 enum { DT_U8 = 0, DT_U16 = 1, DT_I16 = 2, DT_F32 = 3 };
 
 /* Source index for coordinate i on an axis of length n; -1 = constant (zero). */
@@ -49,6 +49,12 @@ static inline int border_index(int i, int n, int mode) {
     if (mode == B_CIRCULAR) {
         int m = i % n;
         return m < 0 ? m + n : m;
+    }
+    if (mode == B_SYMMETRIC) { /* scipy.ndimage 'reflect': d c b a | a b c d | d c b a */
+        int p = 2 * n;
+        int m = i % p;
+        if (m < 0) m += p;
+        return m < n ? m : p - 1 - m;
     }
     return -1;
 }
@@ -94,7 +100,7 @@ void orc_from01(const float* in, int dtype, int64_t count, float lo, float hi, v
  * Accumulation: acc = w[0]*x[0]; acc = fmaf(w[t], x[t], acc), t = 1..K-1.          */
 MIE_CLONES
 static void sep_plane(const float* in, float* out, float* tmp, int h, int w, const float* wx, int kx,
-                      const float* wy, int ky, int border, int unsharp) {
+                      const float* wy, int ky, int border, int unsharp, float amount, int clip) {
     const int rx = kx / 2, ry = ky / 2;
     for (int y = 0; y < h; ++y) {
         const float* row = in + (size_t)y * w;
@@ -118,15 +124,25 @@ static void sep_plane(const float* in, float* out, float* tmp, int h, int w, con
             }
             if (unsharp) {
                 float c = in[(size_t)y * w + x];
-                acc = c + (c - acc);
+                acc = fmaf(amount, c - acc, c); /* amount == 1: c + (c - acc), kornia's unsharp_mask */
+                if (clip) acc = fminf(fmaxf(acc, 0.0f), 1.0f);
             }
             out[(size_t)y * w + x] = acc;
         }
     }
 }
 
+/* skimage.filters.unsharp_mask(image, radius, amount): x + amount (x - blur), optionally clipped to [0,1]. */
+int orc_gaussian2d_ex(const float* in, float* out, int64_t n, int h, int w, const float* wx, int kx, const float* wy,
+                      int ky, int border, int unsharp, float amount, int clip);
+
 int orc_gaussian2d(const float* in, float* out, int64_t n, int h, int w, const float* wx, int kx, const float* wy,
                    int ky, int border, int unsharp) {
+    return orc_gaussian2d_ex(in, out, n, h, w, wx, kx, wy, ky, border, unsharp, 1.0f, 0);
+}
+
+int orc_gaussian2d_ex(const float* in, float* out, int64_t n, int h, int w, const float* wx, int kx, const float* wy,
+                      int ky, int border, int unsharp, float amount, int clip) {
     int err = 0;
 #pragma omp parallel
     {
@@ -137,7 +153,8 @@ int orc_gaussian2d(const float* in, float* out, int64_t n, int h, int w, const f
         } else {
 #pragma omp for schedule(dynamic, 1)
             for (int64_t i = 0; i < n; ++i)
-                sep_plane(in + (size_t)i * h * w, out + (size_t)i * h * w, tmp, h, w, wx, kx, wy, ky, border, unsharp);
+                sep_plane(in + (size_t)i * h * w, out + (size_t)i * h * w, tmp, h, w, wx, kx, wy, ky, border, unsharp,
+                          amount, clip);
             free(tmp);
         }
     }
