@@ -8,7 +8,9 @@
 // sequence as oracle/mie_oracle.c:mie_exp, so the result is reproducible bit for
 // bit and stays within 2 ulp of exp().  This op is FMA-pipe bound (81 taps x ~20
 // instructions), not HBM bound.
-#include "mie_common.cuh"
+#include <cstdlib>
+
+#include "chain_fast.cuh"
 
 #define MIE_HAVE_BILATERAL 1
 
@@ -20,9 +22,14 @@ struct SpaceW {
     float w[kBilMaxK * kBilMaxK];
 };
 
+// Same values as oracle/mie_oracle.c:mie_exp, bit for bit, without the conversion-pipe instructions
+// (FRND / F2I run at 16 lanes per clock): rint(t) = (t + 1.5*2^23) - 1.5*2^23 for |t| < 2^22, the integer
+// n sits in the low mantissa bits of the intermediate sum, and p * 2^n (exact: p in [0.7, 1.42] and
+// n >= -126 only when p > 1.39, so no subnormals) is an exponent-field addition on the integer pipe.
 __device__ __forceinline__ float mie_exp(float a) {
     a = fminf(fmaxf(a, -87.0f), 88.0f);
-    const float n = rintf(__fmul_rn(a, 1.44269504088896341f));
+    const float u = __fadd_rn(__fmul_rn(a, 1.44269504088896341f), 12582912.0f);
+    const float n = __fsub_rn(u, 12582912.0f);
     float r = __fmaf_rn(n, -0.693145751953125f, a);
     r = __fmaf_rn(n, -1.42860682030941723e-6f, r);
     float p = 1.3888889225e-3f;
@@ -32,8 +39,7 @@ __device__ __forceinline__ float mie_exp(float a) {
     p = __fmaf_rn(p, r, 0.5f);
     p = __fmaf_rn(p, r, 1.0f);
     p = __fmaf_rn(p, r, 1.0f);
-    const float s = __int_as_float(((int)n + 127) << 23);
-    return __fmul_rn(p, s);
+    return __uint_as_float(__float_as_uint(p) + (__float_as_uint(u) << 23));
 }
 
 // 32x32 output tile per block, 4 pixels per thread (rows ly, ly+8, ly+16, ly+24).
@@ -85,6 +91,145 @@ bilateral_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t s
     }
 }
 
+// ---------------------------------------------------------------- packed variant, compile-time window
+// The generic kernel above is ISSUE bound (95 % of the issue slots busy, FMA pipe 70 %: ncu,
+// profiles/r1_ncu_full_bilateral_generic.txt): 27 instructions per pixel-tap.  This variant processes the
+// four pixels of a thread as two f32x2 pairs: every arithmetic step of the weight (difference, square,
+// scale, the exp range reduction and polynomial, the spatial weight, both accumulations) is ONE packed
+// instruction per pair — same per-lane IEEE rounding, so the result is bit-identical — and the window
+// loops are unrolled at compile time.  Per pixel-tap: 6.5 packed + 2 scalar FMA-pipe instructions, 1 LDS,
+// 1 FMNMX, 1 exponent-field add: ~12 issue slots instead of 27; the FMA pipe becomes the limiter.
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_dup(float v) { return f2_pack(v, v); }
+
+struct ExpConsts {
+    f32x2 magic, ln2hi, ln2lo, c6, c5, c4, c3, c2, one;
+};
+__device__ __forceinline__ ExpConsts exp_consts() {
+    ExpConsts k;
+    k.magic = f2_dup(12582912.0f);
+    k.ln2hi = f2_dup(-0.693145751953125f); k.ln2lo = f2_dup(-1.42860682030941723e-6f);
+    k.c6 = f2_dup(1.3888889225e-3f); k.c5 = f2_dup(8.3333337680e-3f); k.c4 = f2_dup(4.1666667908e-2f);
+    k.c3 = f2_dup(1.6666667163e-1f); k.c2 = f2_dup(0.5f); k.one = f2_dup(1.0f);
+    return k;
+}
+// ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 — also __fadd2_rn(__fmul2_rn(..)), also with
+// -fmad=false, also when the product is written fma(a, b, -0) — into one FFMA2, i.e. one rounding instead
+// of two, which the scalar __fmul_rn / __fadd_rn sequence of mie_exp never does.  So the two products that
+// feed an addition (a * log2e before the magic add, ws * exp before den + w) are SCALAR multiplies on the
+// halves, which are unpacked there anyway (clamp / exponent-field add); everything else is packed.
+//
+// ws * mie_exp(a) on both halves for a NON-POSITIVE (or NaN) argument a = coef * d^2: after max(a, -87)
+// (which also replaces NaN) the scalar function's upper clamp min(a, 88) is the identity and is skipped.
+__device__ __forceinline__ f32x2 weight_x2(f32x2 a, float ws, const ExpConsts& k) {
+    float a0, a1;
+    f2_unpack(a, a0, a1);
+    a0 = fmaxf(a0, -87.0f);
+    a1 = fmaxf(a1, -87.0f);
+    a = f2_pack(a0, a1);
+    const f32x2 u = f2_add(f2_pack(__fmul_rn(a0, 1.44269504088896341f), __fmul_rn(a1, 1.44269504088896341f)), k.magic);
+    const f32x2 n = f2_sub(u, k.magic);
+    f32x2 r = f2_fma(n, k.ln2hi, a);
+    r = f2_fma(n, k.ln2lo, r);
+    f32x2 p = f2_fma(k.c6, r, k.c5);
+    p = f2_fma(p, r, k.c4);
+    p = f2_fma(p, r, k.c3);
+    p = f2_fma(p, r, k.c2);
+    p = f2_fma(p, r, k.one);
+    p = f2_fma(p, r, k.one);
+    float p0, p1, u0, u1;
+    f2_unpack(p, p0, p1);
+    f2_unpack(u, u0, u1);
+    const float e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(u0) << 23));
+    const float e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(u1) << 23));
+    return f2_pack(__fmul_rn(ws, e0), __fmul_rn(ws, e1));
+}
+
+struct SpaceW2 {   // spatial weights, row-major K x K
+    float w[81];
+};
+
+template <typename SrcT, typename DstT, int K>
+__global__ void __launch_bounds__(256)
+bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                        int64_t dsh, int h, int w, int tiles_x, int tiles_y, float coef, int border, float lo,
+                        float rg, SpaceW2 sw) {
+    constexpr int T = 32, R = K / 2, EW = T + 2 * R, EH = T + 2 * R, PITCH = EW | 1;
+    __shared__ float smem[EH * PITCH];
+    const int64_t tile = blockIdx.x;
+    const int tx0 = (int)(tile % tiles_x) * T, ty0 = (int)((tile / tiles_x) % tiles_y) * T;
+    const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
+    const SrcT* plane = src + n * ssn;
+    for (int i = threadIdx.x; i < EH * EW; i += 256) {
+        const int r = i / EW, c = i - r * EW;
+        const int sy = border_index(ty0 - R + r, h, border), sx = border_index(tx0 - R + c, w, border);
+        smem[r * PITCH + c] = (sy < 0 || sx < 0) ? 0.0f : Px<SrcT>::to01(plane[(int64_t)sy * ssh + sx], lo, rg);
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
+    const float* base = smem + ly0 * PITCH + lx;          // window origin of pixel (ly0, lx)
+    const ExpConsts kc = exp_consts();
+    const f32x2 coef2 = f2_dup(coef);
+    // pairs: (rows ly0, ly0 + 8) and (rows ly0 + 16, ly0 + 24)
+    const f32x2 ctrA = f2_pack(base[R * PITCH + R], base[(8 + R) * PITCH + R]);
+    const f32x2 ctrB = f2_pack(base[(16 + R) * PITCH + R], base[(24 + R) * PITCH + R]);
+    f32x2 numA = f2_dup(0.0f), denA = numA, numB = numA, denB = numA;
+#pragma unroll
+    for (int dy = 0; dy < K; ++dy) {
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+            const float ws = sw.w[dy * K + dx];
+            const float* p = base + dy * PITCH + dx;
+            const f32x2 vA = f2_pack(p[0], p[8 * PITCH]);
+            const f32x2 vB = f2_pack(p[16 * PITCH], p[24 * PITCH]);
+            const f32x2 dA = f2_sub(vA, ctrA), dB = f2_sub(vB, ctrB);
+            const f32x2 wA = weight_x2(f2_mul(coef2, f2_mul(dA, dA)), ws, kc);
+            const f32x2 wB = weight_x2(f2_mul(coef2, f2_mul(dB, dB)), ws, kc);
+            numA = f2_fma(wA, vA, numA); denA = f2_add(denA, wA);
+            numB = f2_fma(wB, vB, numB); denB = f2_add(denB, wB);
+        }
+    }
+    float num[4], den[4];
+    f2_unpack(numA, num[0], num[1]); f2_unpack(numB, num[2], num[3]);
+    f2_unpack(denA, den[0], den[1]); f2_unpack(denB, den[2], den[3]);
+    const int x = tx0 + lx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = ty0 + ly0 + 8 * k;
+        if (y < h && x < w)
+            dst[n * dsn + (int64_t)y * dsh + x] = Px<DstT>::from01(__fdiv_rn(num[k], den[k]), lo, rg);
+    }
+}
+
+template <typename SrcT, typename DstT>
+static int launch_bilateral_packed(int k, const void* src, void* dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                                   int64_t dsh, int h, int w, int tiles_x, int tiles_y, unsigned blocks, float coef,
+                                   int border, float lo, float rg, const float* wspace, cudaStream_t st) {
+    SpaceW2 sw;
+    for (int i = 0; i < 81; ++i) sw.w[i] = i < k * k ? wspace[i] : 0.f;
+#define MIE_BIL(K_)                                                                                          \
+    case K_:                                                                                                 \
+        bilateral_packed_kernel<SrcT, DstT, K_><<<blocks, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, dsn, \
+                                                                        dsh, h, w, tiles_x, tiles_y, coef, border,  \
+                                                                        lo, rg, sw);                             \
+        break;
+    switch (k) {
+        MIE_BIL(3) MIE_BIL(5) MIE_BIL(7) MIE_BIL(9)
+        default: return -1;
+    }
+#undef MIE_BIL
+    return check_launch();
+}
+
 int bilateral_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
                    int64_t dsn, int64_t dsh, const float* wspace, int ky, int kx, float sigma_color, int border,
                    float lo, float hi, cudaStream_t st) {
@@ -105,6 +250,12 @@ int bilateral_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h,
     const int tiles_x = ceil_div(w, 32), tiles_y = ceil_div(h, 32);
     const int64_t blocks = n * tiles_x * tiles_y;
     if (blocks > 2147483647LL) return MIE_E_SHAPE;
+    static const bool no_packed = [] { const char* e = getenv("MIE_BILATERAL_NO_PACKED"); return e && e[0] == '1'; }();
+    if (!no_packed && ky == kx && ky >= 3 && ky <= 9) {   // square 3 / 5 / 7 / 9 windows: packed, fully unrolled kernel
+        MIE_DISPATCH_SRC_DST(sd, dd, return (launch_bilateral_packed<SrcT, DstT>(
+                                         ky, src, dst, ssn, ssh, dsn, dsh, h, w, tiles_x, tiles_y, (unsigned)blocks,
+                                         coef, border, lo, hi - lo, wspace, st)));
+    }
     const int ew = 32 + 2 * (kx / 2), eh = 32 + 2 * (ky / 2);
     const size_t smem = (size_t)eh * (ew | 1) * 4;
     MIE_DISPATCH_SRC_DST(sd, dd, (bilateral_kernel<SrcT, DstT><<<(unsigned)blocks, 256, smem, st>>>(
