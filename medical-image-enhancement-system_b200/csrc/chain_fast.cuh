@@ -100,7 +100,7 @@ struct Fast<uint16_t> {
     }
     // rint(clamp(y,0,1)*65535) sits in the low 16 mantissa bits of the returned float's bit pattern
     static __device__ __forceinline__ uint32_t quant(float y) {
-        const float c = fminf(fmaxf(y, 0.0f), 1.0f);
+        const float c = __saturatef(y);   // == fminf(fmaxf(y, 0), 1) incl. NaN -> 0; folds into the producer as .SAT
         return __float_as_uint(__fadd_rn(__fmul_rn(c, 65535.0f), 8388608.0f));
     }
     static __device__ __forceinline__ void store4(uint16_t* p, const float* y) {
@@ -165,7 +165,7 @@ struct Fast<uint8_t> {
         cvt4(b.x, x); cvt4(b.y, x + 4);
     }
     static __device__ __forceinline__ uint32_t quant(float y) {  // value in the low byte of the bit pattern
-        const float c = fminf(fmaxf(y, 0.0f), 1.0f);
+        const float c = __saturatef(y);   // == fminf(fmaxf(y, 0), 1) incl. NaN -> 0; folds into the producer as .SAT
         return __float_as_uint(__fadd_rn(__fmul_rn(c, 255.0f), 8388608.0f));
     }
     static __device__ __forceinline__ void store4(uint8_t* p, const float* y) {

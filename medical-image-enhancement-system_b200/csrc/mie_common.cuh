@@ -36,7 +36,7 @@ struct PxInt {
         return __fdiv_rn(__fsub_rn((float)v, lo), rg);
     }
     static __device__ __forceinline__ T from01(float y, float lo, float rg) {
-        float c = fminf(fmaxf(y, 0.0f), 1.0f);
+        float c = __saturatef(y);   // == fminf(fmaxf(y, 0), 1) incl. NaN -> 0
         float q = __fadd_rn(rintf(__fmul_rn(c, rg)), lo);
         q = fminf(fmaxf(q, (float)LO), (float)HI);
         return (T)__float2int_rn(q);

@@ -74,6 +74,27 @@ def test_clahe_hist_and_luts_bit_exact(dev, kind, dtype):
         assert (np.diff(l.astype(np.int32), axis=-1) >= 0).all()
 
 
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.int16, np.float32])
+def test_clahe_many_tiles_warp_per_tile_kernel(dev, dtype):
+    """Jobs with >= 592 tiles take the warp-per-tile LUT kernel (smaller ones the block-per-tile latency
+    variant): 32-pixel tiles (4 chunks per row), 64-pixel tiles, and 24-pixel tiles (3 chunks: the generic
+    index loop)."""
+    import mie_b200 as M
+    import oracle as O
+
+    for shape, grid in [((12, 1, 256, 256), (8, 8)), ((10, 1, 512, 512), (8, 8)), ((20, 1, 192, 192), (8, 8)),
+                        ((3, 1, 1024, 512), (16, 16))]:
+        x = images("U", shape, dtype, seed=21)
+        x01 = O.to01(x)
+        h_ref = O.clahe_hist(x01, grid)
+        l_ref = O.clahe_luts(x01, 2.0, grid)
+        xt = gpu(x, dev)
+        assert np.array_equal(cpu(M.clahe_histograms(xt, grid)).reshape(h_ref.shape), h_ref), shape
+        assert np.array_equal(cpu(M.clahe_luts(xt, 2.0, grid)).reshape(l_ref.shape), l_ref), shape
+        ref = O.equalize_clahe(x01, 2.0, grid)
+        assert np.array_equal(cpu(M.equalize_clahe(xt, 2.0, grid, out_dtype=torch.float32)), ref), shape
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.uint16, np.uint8, np.int16])
 def test_clahe_apply_teacher_forced(dev, dtype):
     import mie_b200 as M
