@@ -204,8 +204,8 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
     __syncthreads();
 
     const uint8_t* iplane = a.idx + n * (int64_t)h * W + 4 * tid;
-    // raw[p % 8][j] = index word of row 2p + j, loaded 4..5 row pairs ahead of its use (one register
-    // per row, so depth is cheap here)
+    // raw[p % 8][j] = index word of row 2p + j, loaded 6..7 row pairs ahead of its use (one register
+    // per row, so depth is cheap here; at 4..5 pairs one use still showed 6 % long-scoreboard stalls)
     uint32_t raw[8][2];
     auto fetch_pairs = [&](const int p, const int slot) {
         const int4 o = *reinterpret_cast<const int4*>(s_off + 2 * p);
@@ -220,6 +220,7 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
     };
     fetch_pairs(0, 0);
     fetch_pairs(2, 2);
+    fetch_pairs(4, 4);
 
     // cells of this thread's columns: column cell (4t + 32) / 64; row cell 0 (rows above the tile
     // centre line ty0 + 32, i.e. band rows < 36) or 1.  Shared-window byte addresses: lookup = LEA + LDS.64.
@@ -251,7 +252,7 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
 
 #pragma unroll
     for (int p = 0; p < kMPro; ++p) {
-        if (p % 2 == 0) fetch_pairs(p + 4, (p + 4) % 8);
+        if (p % 2 == 0) fetch_pairs(p + 6, (p + 6) % 8);
         float x0[4], x1[4];
         clahe_pair(p, p % 8, x0, x1);
         float* buf = s_buf + (p % 4) * pbuf;
@@ -263,7 +264,7 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
 #pragma unroll
         for (int q = 0; q < kMUnroll; ++q) {
             const int p = p0 + q;
-            if (q % 2 == 0) fetch_pairs(p + 4, (kMPro + q + 4) % 8);
+            if (q % 2 == 0) fetch_pairs(p + 6, (kMPro + q + 6) % 8);
             float x0[4], x1[4];
             clahe_pair(p, (kMPro + q) % 8, x0, x1);
             float* buf = s_buf + (q % 4) * pbuf;

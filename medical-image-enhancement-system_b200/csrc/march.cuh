@@ -15,11 +15,11 @@ constexpr int kMPairs = kMRows / 2;        // 36 row pairs
 constexpr int kMPro = kMR;                 // prologue: 4 row pairs (8 rows) that produce no output
 constexpr int kMRing = 16;                 // register-ring slots (row s lives in slot s % 16)
 constexpr int kMUnroll = kMRing / 2;       // main loop: 8 row pairs per iteration
-constexpr int kMOffRows = kMRows + 8;      // rows covered by the source-offset table (incl. over-fetch)
+constexpr int kMOffRows = kMRows + 12;     // rows covered by the source-offset table (incl. over-fetch)
 constexpr int kHistPitch = 264;            // 257 slots (256 = value 1.0 / ignored pixels), padded
 static_assert((kMPairs - kMPro) % kMUnroll == 0, "main loop must tile the band");
 
-// Source row of band row r (|overshoot| <= 4 + 8 < h, so one reflection suffices).
+// Source row of band row r (|overshoot| <= 4 + 12 < h, so one reflection suffices).
 // -1 = outside the image with a constant border.
 template <int BORDER>
 __device__ __forceinline__ int march_src_row(int r, int h) {
