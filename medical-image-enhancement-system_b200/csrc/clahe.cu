@@ -11,13 +11,13 @@ namespace mie {
 // clahe_fast.cu
 bool clahe_lut_fast_ok(const ClaheGeom& g, int sd, const void* src, int64_t ssn, int64_t ssh, float lo, float hi);
 int launch_clahe_lut_fast(const void* src, int sd, int64_t n, int64_t ssn, int64_t ssh, const ClaheGeom& g,
-                          const LutParams& lp, uint32_t* hist, uint8_t* luts, cudaStream_t st);
+                          const LutParams& lp, uint32_t* hist, uint8_t* luts, float lo, float hi, cudaStream_t st);
 size_t clahe_cells_bytes(int64_t n, int gh, int gw);
 bool clahe_apply_fast_ok(const ClaheGeom& g, int sd, int dd, const void* src, const void* dst, int64_t ssn,
                          int64_t ssh, int64_t dsn, int64_t dsh, float lo, float hi);
 int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t n, int64_t ssn, int64_t ssh,
                             int64_t dsn, int64_t dsh, const ClaheGeom& g, const uint8_t* luts, void* cells,
-                            cudaStream_t st);
+                            float lo, float hi, cudaStream_t st);
 
 // ---------------------------------------------------------------- LUT kernel
 template <typename SrcT, int SEM>
@@ -158,7 +158,7 @@ int clahe_luts_impl(const void* src, int sd, int64_t n, int h, int w, int64_t ss
     const LutParams lp = make_lut_params(g, clip_limit, semantics);
     const float rg = hi - lo;
     if (semantics == MIE_CLAHE_KORNIA && clahe_lut_fast_ok(g, sd, src, ssn, ssh, lo, hi))
-        return launch_clahe_lut_fast(src, sd, n, ssn, ssh, g, lp, hist, luts, st);
+        return launch_clahe_lut_fast(src, sd, n, ssn, ssh, g, lp, hist, luts, lo, hi, st);
     MIE_DISPATCH_SRC(sd, return launch_lut<SrcT>(src, n, ssn, ssh, g, lo, rg, lp, semantics, hist, luts, st));
     return MIE_OK;
 }
@@ -257,7 +257,8 @@ int mie_clahe(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t 
                                 dst_stride_h, lo, hi))
             return launch_clahe_apply_fast(src, dst, src_dtype, dst_dtype, n, src_stride_n, src_stride_h, dst_stride_n,
                                            dst_stride_h, g, (const uint8_t*)workspace,
-                                           (uint8_t*)workspace + clahe_lut_region(n, gh, gw), (cudaStream_t)stream);
+                                           (uint8_t*)workspace + clahe_lut_region(n, gh, gw), lo, hi,
+                                           (cudaStream_t)stream);
     }
     return clahe_apply_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n,
                             dst_stride_h, gh, gw, semantics, lo, hi, (const uint8_t*)workspace, (cudaStream_t)stream);

@@ -9,7 +9,7 @@
 //     threads own 4 consecutive columns (64-bit loads / stores), no divides, no F2I.
 #include <cstdlib>
 
-#include "chain_fast.cuh"
+#include "window.cuh"
 
 namespace mie {
 
@@ -19,11 +19,11 @@ namespace mie {
 // instructions per pixel, 7.6 of them in the pixel loop).  So a warp owns a whole tile — 128 pixels per
 // lane for 64x64 tiles — with its own 257-slot histogram, no block-level synchronisation at all, and
 // builds the LUT as soon as its own tile is done while the other warps of the block keep counting.
-template <typename SrcT>
+template <typename SrcT, bool WIN>
 __global__ void __launch_bounds__(256)
 clahe_lut_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, LutParams lp,
-                      uint32_t* __restrict__ hist_out, uint8_t* __restrict__ lut_out, int64_t tiles) {
-    constexpr bool INT = sizeof(SrcT) != 4;  // integer pixels map into [0, 1]: no range tests
+                      uint32_t* __restrict__ hist_out, uint8_t* __restrict__ lut_out, int64_t tiles, WinCvt cv) {
+    constexpr bool INT = sizeof(SrcT) != 4 && !WIN;  // default-range integer pixels map into [0, 1]: no range tests
     __shared__ __align__(16) int s_all[8][kBins + 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -38,7 +38,7 @@ clahe_lut_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, Cl
     const int chunks = g.tw >> 3;              // 8-pixel chunks per tile row
     auto count8 = [&](int r, int c) {
         float x[8];
-        Fast<SrcT>::load8(base + (int64_t)r * ssh + 8 * c, x);
+        PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (INT) hist_add_le1(h32, x[k]);
@@ -70,11 +70,11 @@ clahe_lut_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, Cl
 // ---------------------------------------------------------------- histogram -> LUT, one BLOCK per tile
 // Latency variant for small jobs (a single 512x512 slice has 64 tiles: one warp per tile would leave
 // most of the machine idle): 256 threads share one tile histogram, warp 0 builds the LUT.
-template <typename SrcT>
+template <typename SrcT, bool WIN>
 __global__ void __launch_bounds__(256)
 clahe_lut_block_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, LutParams lp,
-                       uint32_t* __restrict__ hist_out, uint8_t* __restrict__ lut_out) {
-    constexpr bool INT = sizeof(SrcT) != 4;
+                       uint32_t* __restrict__ hist_out, uint8_t* __restrict__ lut_out, WinCvt cv) {
+    constexpr bool INT = sizeof(SrcT) != 4 && !WIN;
     __shared__ __align__(16) int s_hist[kBins + 8];
     const int tid = threadIdx.x;
     for (int i = tid; i < kBins + 8; i += 256) s_hist[i] = 0;
@@ -89,7 +89,7 @@ clahe_lut_block_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, C
     for (int i = tid; i < total; i += 256) {
         const int r = i / chunks, c = i - r * chunks;
         float x[8];
-        Fast<SrcT>::load8(base + (int64_t)r * ssh + 8 * c, x);
+        PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             if (INT) hist_add_le1(h32, x[k]);
@@ -134,10 +134,10 @@ __device__ __forceinline__ float axis_weight(int y, int T) {
     return __fdiv_rn((float)(T - 1 - r), (float)(T - 1));
 }
 
-template <typename SrcT, typename DstT>
+template <typename SrcT, typename DstT, bool WIN>
 __global__ void __launch_bounds__(1024)
-clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells) {
-    constexpr bool INT = sizeof(SrcT) != 4;
+clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells, WinCvt cv) {
+    constexpr bool INT = sizeof(SrcT) != 4 && !WIN;
     extern __shared__ __align__(16) uint2 s_tab[];   // (gw + 1) x 256 entries: one row of cells
     const ClaheGeom g = a.g;
     const int tid = threadIdx.x, T = blockDim.x;
@@ -163,26 +163,18 @@ clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells) {
 #pragma unroll 4
     for (int r = 0; r < a.rows_per_block; ++r) {
         float x[4], y[4];
-        Fast<SrcT>::load4(sp + (int64_t)r * a.ssh, x);
+        PixIO<SrcT, WIN>::load4(sp + (int64_t)r * a.ssh, x, cv);
         const float wyv = s_wy[r];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint32_t bits = INT ? fast_idx_bits_le1(x[k]) : fast_idx_bits<false>(x[k]);
             y[k] = clahe_px(lds64_(tb + (__byte_perm(bits, 0u, 0x4440) << 3)), wxv[k], wyv);
         }
-        Fast<DstT>::store4(dp + (int64_t)r * a.dsh, y);
+        PixIO<DstT, WIN>::store4(dp + (int64_t)r * a.dsh, y, cv);
     }
 }
 
 // ---------------------------------------------------------------- host side
-static bool default_range_c(int dtype, float lo, float hi) {
-    switch (dtype) {
-        case MIE_U8: return lo == 0.0f && hi == 255.0f;
-        case MIE_U16: return lo == 0.0f && hi == 65535.0f;
-        case MIE_I16: return lo == -32768.0f && hi == 32767.0f;
-        default: return true;
-    }
-}
 static const int kEsz[4] = {1, 2, 2, 4};
 static bool fast_disabled() {
     static const bool off = [] { const char* e = getenv("MIE_CLAHE_NO_FAST"); return e && e[0] == '1'; }();
@@ -192,26 +184,33 @@ static bool fast_disabled() {
 bool clahe_lut_fast_ok(const ClaheGeom& g, int sd, const void* src, int64_t ssn, int64_t ssh, float lo, float hi) {
     if (fast_disabled()) return false;
     if (g.hp != g.h || g.wp != g.w || (g.tw & 7)) return false;
-    if (!default_range_c(sd, lo, hi)) return false;
+    WinCvt cv;
+    if (range_mode(sd, lo, hi, &cv) < 0) return false;
     if (((uintptr_t)src % 16) || ((ssn * kEsz[sd]) % 16) || ((ssh * kEsz[sd]) % 16)) return false;
     if (((int64_t)g.tw * kEsz[sd]) % 16) return false;   // tile origins 16-byte aligned for load8
     return true;
 }
 
 int launch_clahe_lut_fast(const void* src, int sd, int64_t n, int64_t ssn, int64_t ssh, const ClaheGeom& g,
-                          const LutParams& lp, uint32_t* hist, uint8_t* luts, cudaStream_t st) {
+                          const LutParams& lp, uint32_t* hist, uint8_t* luts, float lo, float hi, cudaStream_t st) {
     const int64_t tiles = n * g.gh * g.gw;
     if (tiles == 0) return MIE_OK;
     if (tiles > 2147483647LL) return MIE_E_SHAPE;
-    if (tiles < 4 * 148) {   // small job: spread every tile over a whole block
-        MIE_DISPATCH_SRC(sd, (clahe_lut_block_kernel<SrcT><<<(unsigned)tiles, 256, 0, st>>>((const SrcT*)src, ssn, ssh, g, lp,
-                                                                                         hist, luts)));
-        return check_launch();
-    }
+    WinCvt cv = {};
+    const int mode = range_mode(sd, lo, hi, &cv);
+    if (mode < 0) return MIE_E_UNSUPPORTED;   // callers test clahe_lut_fast_ok first
     const int wpb = 8;
     const int64_t blocks = (tiles + wpb - 1) / wpb;
-    MIE_DISPATCH_SRC(sd, (clahe_lut_fast_kernel<SrcT><<<(unsigned)blocks, 32 * wpb, 0, st>>>((const SrcT*)src, ssn, ssh, g,
-                                                                                          lp, hist, luts, tiles)));
+#define MIE_LUT_FAST(WIN_)                                                                                        \
+    if (tiles < 4 * 148) /* small job: spread every tile over a whole block */                                   \
+        clahe_lut_block_kernel<SrcT, WIN_><<<(unsigned)tiles, 256, 0, st>>>((const SrcT*)src, ssn, ssh, g, lp, hist,  \
+                                                                         luts, cv);                               \
+    else                                                                                                          \
+        clahe_lut_fast_kernel<SrcT, WIN_><<<(unsigned)blocks, 32 * wpb, 0, st>>>((const SrcT*)src, ssn, ssh, g, lp,   \
+                                                                              hist, luts, tiles, cv)
+    if (mode == 1) { MIE_DISPATCH_SRC(sd, MIE_LUT_FAST(true)); }
+    else { MIE_DISPATCH_SRC(sd, MIE_LUT_FAST(false)); }
+#undef MIE_LUT_FAST
     return check_launch();
 }
 
@@ -222,7 +221,8 @@ bool clahe_apply_fast_ok(const ClaheGeom& g, int sd, int dd, const void* src, co
     if (fast_disabled()) return false;
     if (g.hp != g.h || g.wp != g.w || (g.tw & 7) || (g.w & 3) || g.w > 4096 || g.gw > 32) return false;
     if (dd != sd && dd != MIE_F32) return false;
-    if (!default_range_c(sd, lo, hi) || !default_range_c(dd, lo, hi)) return false;
+    WinCvt cv;
+    if (range_mode(sd, lo, hi, &cv) < 0) return false;
     if (((uintptr_t)src % 16) || ((ssn * kEsz[sd]) % 16) || ((ssh * kEsz[sd]) % 16)) return false;
     if (((uintptr_t)dst % 16) || ((dsn * kEsz[dd]) % 16) || ((dsh * kEsz[dd]) % 16)) return false;
     return true;
@@ -231,8 +231,11 @@ bool clahe_apply_fast_ok(const ClaheGeom& g, int sd, int dd, const void* src, co
 // luts -> cell tables (in `cells`, clahe_cells_bytes) -> interpolation
 int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t n, int64_t ssn, int64_t ssh,
                             int64_t dsn, int64_t dsh, const ClaheGeom& g, const uint8_t* luts, void* cells,
-                            cudaStream_t st) {
+                            float lo, float hi, cudaStream_t st) {
     if (n == 0) return MIE_OK;
+    WinCvt cv = {};
+    const int mode = range_mode(sd, lo, hi, &cv);
+    if (mode < 0) return MIE_E_UNSUPPORTED;   // callers test clahe_apply_fast_ok first
     int rc = launch_pack_cells(luts, cells, n, g.gh, g.gw, st);
     if (rc) return rc;
     ApplyFastArgs a;
@@ -246,10 +249,11 @@ int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t 
     const int64_t blocks = n * a.blocks_per_image;
     if (blocks > 2147483647LL) return MIE_E_SHAPE;
     const size_t smem = (size_t)(g.gw + 1) * kBins * 8;
-#define MIE_APPLY_FAST                                                                                     \
-    MIE_ENSURE_SMEM((clahe_apply_fast_kernel<SrcT, DstT>), 80 * 1024);                                     \
-    clahe_apply_fast_kernel<SrcT, DstT><<<(unsigned)blocks, g.w / 4, smem, st>>>(a, (const uint2*)cells)
-    MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST);
+#define MIE_APPLY_FAST(WIN_)                                                                               \
+    MIE_ENSURE_SMEM((clahe_apply_fast_kernel<SrcT, DstT, WIN_>), 80 * 1024);                               \
+    clahe_apply_fast_kernel<SrcT, DstT, WIN_><<<(unsigned)blocks, g.w / 4, smem, st>>>(a, (const uint2*)cells, cv)
+    if (mode == 1) { MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST(true)); }
+    else { MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST(false)); }
 #undef MIE_APPLY_FAST
     return check_launch();
 }

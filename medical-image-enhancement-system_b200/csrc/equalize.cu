@@ -11,7 +11,7 @@
 // apply.
 #include <cstdlib>
 
-#include "chain_fast.cuh"
+#include "window.cuh"
 
 namespace mie {
 
@@ -116,10 +116,10 @@ equalize_apply_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int6
 // stores, the divide-free pixel conversion of chain_fast.cuh, one ATOMS.POPC.INC per pixel into a single
 // block histogram, and — because lut[trunc(v)] takes only 256 values — a per-block table of the 256
 // possible OUTPUT codes, so a pixel costs one conversion, one shared-memory lookup and a pack.
-template <typename SrcT>
+template <typename SrcT, bool WIN>
 __global__ void __launch_bounds__(256)
 equalize_hist_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, int h, int w, int rows_per_block,
-                          EqPlaneState* __restrict__ state) {
+                          EqPlaneState* __restrict__ state, WinCvt cv) {
     __shared__ __align__(16) int s_hist[kBins + 8];
     const int tid = threadIdx.x;
     for (int i = tid; i < kBins + 8; i += 256) s_hist[i] = 0;
@@ -132,9 +132,12 @@ equalize_hist_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh
     for (int i = tid; i < total; i += 256) {
         const int r = i / chunks, c = i - r * chunks;
         float x[8];
-        Fast<SrcT>::load8(base + (int64_t)r * ssh + 8 * c, x);
+        PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) hist_add_le1(h32, div255(__fmul_rn(x[k], 255.0f)));  // eq_bin, x in [0,1]
+        for (int k = 0; k < 8; ++k) {
+            if (WIN) hist_add(s_hist, eq_bin(__fmul_rn(x[k], 255.0f)));                   // pixels outside the window: ignored
+            else hist_add_le1(h32, div255(__fmul_rn(x[k], 255.0f)));                      // eq_bin, x in [0,1]
+        }
     }
     __syncthreads();
     int hv = s_hist[tid];
@@ -164,11 +167,11 @@ __device__ __forceinline__ void eq_store8(float* p, const float* s_out, const ui
     *reinterpret_cast<float4*>(p + 4) = make_float4(s_out[i[4]], s_out[i[5]], s_out[i[6]], s_out[i[7]]);
 }
 
-template <typename SrcT, typename DstT>
+template <typename SrcT, typename DstT, bool WIN>
 __global__ void __launch_bounds__(256)
 equalize_apply_fast_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh,
                            int64_t dsn, int64_t dsh, int h, int w, int rows_per_block, float lo, float rg,
-                           const EqPlaneState* __restrict__ state) {
+                           const EqPlaneState* __restrict__ state, WinCvt cv) {
     __shared__ __align__(16) DstT s_out[kBins];
     const int tid = threadIdx.x;
     const int64_t n = blockIdx.y;
@@ -186,16 +189,17 @@ equalize_apply_fast_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst,
             const int r = i / chunks, c = i - r * chunks;
             float x[8];
             uint32_t idx[8];
-            Fast<SrcT>::load8(sp + (int64_t)r * ssh + 8 * c, x);
+            PixIO<SrcT, WIN>::load8(sp + (int64_t)r * ssh + 8 * c, x, cv);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) idx[k] = fast_idx_bits_le1(x[k]) & 0xFFu;   // trunc(x*255)
+            for (int k = 0; k < 8; ++k)   // trunc(clamp(x*255, 0, 255))
+                idx[k] = (WIN ? fast_idx_bits<false>(x[k]) : fast_idx_bits_le1(x[k])) & 0xFFu;
             eq_store8(dp + (int64_t)r * dsh + 8 * c, s_out, idx);
         }
     } else {   // step == 0 (e.g. a constant plane): v/255 goes back unchanged
         for (int i = tid; i < total; i += 256) {
             const int r = i / chunks, c = i - r * chunks;
             float x[8];
-            Fast<SrcT>::load8(sp + (int64_t)r * ssh + 8 * c, x);
+            PixIO<SrcT, WIN>::load8(sp + (int64_t)r * ssh + 8 * c, x, cv);
             DstT* o = dp + (int64_t)r * dsh + 8 * c;
 #pragma unroll
             for (int k = 0; k < 8; ++k) o[k] = Px<DstT>::from01(div255(__fmul_rn(x[k], 255.0f)), lo, rg);
@@ -203,19 +207,12 @@ equalize_apply_fast_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst,
     }
 }
 
-static bool eq_default_range(int dtype, float lo, float hi) {
-    switch (dtype) {
-        case MIE_U8: return lo == 0.0f && hi == 255.0f;
-        case MIE_U16: return lo == 0.0f && hi == 65535.0f;
-        case MIE_I16: return lo == -32768.0f && hi == 32767.0f;
-        default: return false;   // float planes may hold values outside [0,1]: generic kernels
-    }
-}
 static bool equalize_fast_ok(int sd, int dd, const void* src, const void* dst, int w, int64_t ssn, int64_t ssh,
                              int64_t dsn, int64_t dsh, float lo, float hi) {
     static const bool off = [] { const char* e = getenv("MIE_EQUALIZE_NO_FAST"); return e && e[0] == '1'; }();
     static const int esz[4] = {1, 2, 2, 4};
-    if (off || (w & 7) || !eq_default_range(sd, lo, hi)) return false;
+    WinCvt cv;
+    if (off || (w & 7) || sd == MIE_F32 || range_mode(sd, lo, hi, &cv) < 0) return false;   // float planes: generic kernels
     const int sa = 8 * esz[sd], da = dd == MIE_F32 ? 16 : 8 * esz[dd];
     if (((uintptr_t)src % sa) || ((ssn * esz[sd]) % sa) || ((ssh * esz[sd]) % sa)) return false;
     if (((uintptr_t)dst % da) || ((dsn * esz[dd]) % da) || ((dsh * esz[dd]) % da)) return false;
@@ -255,19 +252,29 @@ int mie_equalize(const void* src, void* dst, int src_dtype, int dst_dtype, int64
         if (rows < 8) rows = 8;
         if (rows > 64) rows = 64;
         dim3 grid((unsigned)ceil_div(h, rows), (unsigned)n);
+        WinCvt cv = {};
+        const bool win = range_mode(src_dtype, lo, hi, &cv) == 1;
+#define MIE_EQ_HIST(T_)                                                                                            \
+    if (win) equalize_hist_fast_kernel<T_, true><<<grid, 256, 0, st>>>((const T_*)src, src_stride_n, src_stride_h, h, w, rows, state, cv); \
+    else equalize_hist_fast_kernel<T_, false><<<grid, 256, 0, st>>>((const T_*)src, src_stride_n, src_stride_h, h, w, rows, state, cv)
         switch (src_dtype) {
-            case MIE_U8: equalize_hist_fast_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)src, src_stride_n, src_stride_h, h, w, rows, state); break;
-            case MIE_U16: equalize_hist_fast_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, src_stride_n, src_stride_h, h, w, rows, state); break;
-            default: equalize_hist_fast_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)src, src_stride_n, src_stride_h, h, w, rows, state); break;
+            case MIE_U8: MIE_EQ_HIST(uint8_t); break;
+            case MIE_U16: MIE_EQ_HIST(uint16_t); break;
+            default: MIE_EQ_HIST(int16_t); break;
         }
+#undef MIE_EQ_HIST
         rc = check_launch();
         if (rc) return rc;
         equalize_lut_kernel<<<(unsigned)n, 256, 0, st>>>(state);
         rc = check_launch();
         if (rc) return rc;
-        MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, (equalize_apply_fast_kernel<SrcT, DstT><<<grid, 256, 0, st>>>(
-                                                       (const SrcT*)src, (DstT*)dst, src_stride_n, src_stride_h,
-                                                       dst_stride_n, dst_stride_h, h, w, rows, lo, rg, state)));
+#define MIE_EQ_APPLY(WIN_)                                                                                  \
+    equalize_apply_fast_kernel<SrcT, DstT, WIN_><<<grid, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, src_stride_n, \
+                                                                      src_stride_h, dst_stride_n, dst_stride_h, h, \
+                                                                      w, rows, lo, rg, state, cv)
+        if (win) { MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, MIE_EQ_APPLY(true)); }
+        else { MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, MIE_EQ_APPLY(false)); }
+#undef MIE_EQ_APPLY
         return check_launch();
     }
     // enough blocks per plane to fill the machine when n is small, few enough to keep global atomics rare

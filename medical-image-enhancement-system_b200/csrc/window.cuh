@@ -1,0 +1,152 @@
+// window.cuh — integer value_range windows for the tuned kernels: the divide-free windowed pixel conversion
+// (device) and its exhaustive host-side verification.  See the comment on WinCvt.
+#pragma once
+
+#include <cmath>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "chain_fast.cuh"
+
+namespace mie {
+
+// ---------------------------------------------------------------- integer windows (value_range)
+// x01 = (float(v) - lo) / (hi - lo) for an integer window [lo, hi] inside the dtype's range (e.g. the HU
+// window -1024 .. 3071 of int16 CT data) without I2F and without an IEEE divide:
+//   a  = uint_as_float(0x4B000000 | (v + bias)) - (2^23 + bias + lo)          exact: float(v) - lo
+//   q0 = a * r;  x01 = fma(fma(-rg, q0, a), r, q0)        with r = RN(1 / rg) (Markstein's correction)
+// The host checks this against the IEEE quotient for EVERY code of the dtype (65 536 at most) the first
+// time a window is used and caches the verdict; a window that fails keeps the generic kernels.  Pixels
+// outside the window land outside [0, 1]: not counted by the histogram (torch.histc rule), clamped by the
+// lookup — the float-input rules, so windowed kernels take the float code path after the conversion.
+// Back: rint(clamp(y, 0, 1) * rg) + lo as an integer add on the mantissa of (c * rg + 2^23).
+struct WinCvt {
+    float in_magic, r, neg_rg, rg;
+    int lo_out;
+};
+
+template <typename T, bool WIN>
+struct PixIO {   // WIN == false: the default-range conversions of chain_fast.cuh
+    static __device__ __forceinline__ void load8(const T* p, float* x, const WinCvt&) { Fast<T>::load8(p, x); }
+    static __device__ __forceinline__ void load4(const T* p, float* x, const WinCvt&) { Fast<T>::load4(p, x); }
+    static __device__ __forceinline__ void store4(T* p, const float* y, const WinCvt&) { Fast<T>::store4(p, y); }
+};
+__device__ __forceinline__ float win_one(uint32_t mant_bits, const WinCvt& c) {
+    const float a = __fsub_rn(__uint_as_float(mant_bits), c.in_magic);
+    const float q0 = __fmul_rn(a, c.r);
+    return __fmaf_rn(__fmaf_rn(c.neg_rg, q0, a), c.r, q0);
+}
+__device__ __forceinline__ uint32_t win_quant(float y, const WinCvt& c) {   // low bits = rint(clamp(y) * rg) + lo
+    return __float_as_uint(__fadd_rn(__fmul_rn(__saturatef(y), c.rg), 8388608.0f)) + (uint32_t)c.lo_out;
+}
+template <>
+struct PixIO<uint16_t, true> {
+    static __device__ __forceinline__ void cvt2(uint32_t w, float* x, const WinCvt& c) {
+        x[0] = win_one(__byte_perm(w, 0x4B000000u, 0x7610), c);
+        x[1] = win_one(__byte_perm(w, 0x4B000000u, 0x7632), c);
+    }
+    static __device__ __forceinline__ void load8(const uint16_t* p, float* x, const WinCvt& c) {
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p));
+        cvt2(b.x, x, c); cvt2(b.y, x + 2, c); cvt2(b.z, x + 4, c); cvt2(b.w, x + 6, c);
+    }
+    static __device__ __forceinline__ void load4(const uint16_t* p, float* x, const WinCvt& c) {
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
+        cvt2(b.x, x, c); cvt2(b.y, x + 2, c);
+    }
+    static __device__ __forceinline__ void store4(uint16_t* p, const float* y, const WinCvt& c) {
+        uint2 o;
+        o.x = __byte_perm(win_quant(y[0], c), win_quant(y[1], c), 0x5410);
+        o.y = __byte_perm(win_quant(y[2], c), win_quant(y[3], c), 0x5410);
+        *reinterpret_cast<uint2*>(p) = o;
+    }
+};
+template <>
+struct PixIO<int16_t, true> {   // v + 32768 by flipping the sign bit; the bias is part of in_magic
+    static __device__ __forceinline__ void load8(const int16_t* p, float* x, const WinCvt& c) {
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p));
+        PixIO<uint16_t, true>::cvt2(b.x ^ 0x80008000u, x, c); PixIO<uint16_t, true>::cvt2(b.y ^ 0x80008000u, x + 2, c);
+        PixIO<uint16_t, true>::cvt2(b.z ^ 0x80008000u, x + 4, c); PixIO<uint16_t, true>::cvt2(b.w ^ 0x80008000u, x + 6, c);
+    }
+    static __device__ __forceinline__ void load4(const int16_t* p, float* x, const WinCvt& c) {
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
+        PixIO<uint16_t, true>::cvt2(b.x ^ 0x80008000u, x, c); PixIO<uint16_t, true>::cvt2(b.y ^ 0x80008000u, x + 2, c);
+    }
+    static __device__ __forceinline__ void store4(int16_t* p, const float* y, const WinCvt& c) {
+        PixIO<uint16_t, true>::store4(reinterpret_cast<uint16_t*>(p), y, c);   // two's complement low halves
+    }
+};
+template <>
+struct PixIO<uint8_t, true> {
+    static __device__ __forceinline__ void cvt4(uint32_t w, float* x, const WinCvt& c) {
+        x[0] = win_one(__byte_perm(w, 0x4B000000u, 0x7650), c);
+        x[1] = win_one(__byte_perm(w, 0x4B000000u, 0x7651), c);
+        x[2] = win_one(__byte_perm(w, 0x4B000000u, 0x7652), c);
+        x[3] = win_one(__byte_perm(w, 0x4B000000u, 0x7653), c);
+    }
+    static __device__ __forceinline__ void load8(const uint8_t* p, float* x, const WinCvt& c) {
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
+        cvt4(b.x, x, c); cvt4(b.y, x + 4, c);
+    }
+    static __device__ __forceinline__ void load4(const uint8_t* p, float* x, const WinCvt& c) {
+        cvt4(__ldg(reinterpret_cast<const uint32_t*>(p)), x, c);
+    }
+    static __device__ __forceinline__ void store4(uint8_t* p, const float* y, const WinCvt& c) {
+        *reinterpret_cast<uint32_t*>(p) = pack_low_bytes(win_quant(y[0], c), win_quant(y[1], c), win_quant(y[2], c),
+                                                         win_quant(y[3], c));
+    }
+};
+template <>
+struct PixIO<float, true> : PixIO<float, false> {};
+
+// ---------------------------------------------------------------- host side
+inline bool default_range_c(int dtype, float lo, float hi) {
+    switch (dtype) {
+        case MIE_U8: return lo == 0.0f && hi == 255.0f;
+        case MIE_U16: return lo == 0.0f && hi == 65535.0f;
+        case MIE_I16: return lo == -32768.0f && hi == 32767.0f;
+        default: return true;
+    }
+}
+
+// 0 = the dtype's default range (or float pixels), 1 = integer window usable by the windowed kernels
+// (*cv filled in), -1 = neither.  The exhaustive check runs once per (dtype, lo, hi).
+inline int range_mode(int dtype, float lo, float hi, WinCvt* cv) {
+    if (default_range_c(dtype, lo, hi)) return 0;
+    static const int kLo[3] = {0, 0, -32768}, kHi[3] = {255, 65535, 32767}, kBias[3] = {0, 0, 32768};
+    if (dtype < MIE_U8 || dtype > MIE_I16) return -1;
+    if (lo != std::floor(lo) || hi != std::floor(hi) || !(hi > lo)) return -1;
+    if (lo < (float)kLo[dtype] || hi > (float)kHi[dtype]) return -1;   // outputs stay inside the dtype: no final clamp
+    const float rg = hi - lo;
+    WinCvt c;
+    c.in_magic = 8388608.0f + (float)kBias[dtype] + lo;
+    c.r = 1.0f / rg; c.neg_rg = -rg; c.rg = rg; c.lo_out = (int)lo;
+    static std::mutex mu;
+    static std::map<std::tuple<int, float, float>, bool> verdicts;
+    bool ok;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto key = std::make_tuple(dtype, lo, hi);
+        auto it = verdicts.find(key);
+        if (it == verdicts.end()) {
+            ok = true;
+            for (int v = kLo[dtype]; v <= kHi[dtype] && ok; ++v) {
+                volatile float exact = ((float)v - lo) / rg;                       // Px<T>::to01
+                volatile float a = (8388608.0f + (float)(v + kBias[dtype])) - c.in_magic;
+                volatile float q0 = a * c.r;
+                volatile float rem = std::fmaf(c.neg_rg, q0, a);
+                volatile float q = std::fmaf(rem, c.r, q0);
+                float e = exact, f = q;
+                ok = (e == f) && (std::signbit(e) == std::signbit(f) || e != 0.0f);
+            }
+            verdicts[key] = ok;
+        } else {
+            ok = it->second;
+        }
+    }
+    if (!ok) return -1;
+    *cv = c;
+    return 1;
+}
+
+}  // namespace mie

@@ -163,6 +163,21 @@ def test_equalize_bit_exact(dev, dtype):
     assert np.array_equal(cpu(M.equalize(gpu(c, dev))), c)
 
 
+@pytest.mark.parametrize("case", [(np.int16, (-1024.0, 3071.0)), (np.uint16, (0.0, 4095.0)), (np.uint8, (10.0, 200.0))])
+def test_equalize_integer_windows(dev, case):
+    """value_range windows on the tuned kernels (windowed conversion, csrc/window.cuh): pixels outside the
+    window are ignored by the histogram and clamped by the lookup."""
+    import mie_b200 as M
+    import oracle as O
+
+    dtype, vr = case
+    for shape in [(3, 1, 64, 80), (2, 1, 512, 512)]:
+        x = rand(dtype, shape, 12)
+        ref = O.equalize(O.to01(x, vr))
+        assert np.array_equal(cpu(M.equalize(gpu(x, dev), value_range=vr, out_dtype=torch.float32)), ref)
+        assert np.array_equal(cpu(M.equalize(gpu(x, dev), value_range=vr)), O.from01(ref, dtype, vr))
+
+
 def test_equalize_matches_torchvision_uint8(dev):
     tvf = pytest.importorskip("torchvision.transforms.v2.functional")
     import mie_b200 as M
