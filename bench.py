@@ -244,7 +244,12 @@ def run_ours(args):
     # ---- per-kernel durations (CUDA events on the launching stream), same inputs, same workspace
     kern = {}
     if fused:
-        for name, mask in (("chain_a_kernel", 1), ("chain_b_kernel", 2)):
+        # stage A / stage B of the fused chain (include/mie.h: MIE_CHAIN_STAGE_A / _B).  On the workload's
+        # geometry (path 2, W % 128 == 0) these are the marching kernels of csrc/chain_march.cu; stage B is
+        # the tiny cell-table packing launch plus chain_b.
+        stage_names = (("chain_a_march_kernel", 1), ("chain_pack_cells_kernel+chain_b_march_kernel", 2)) if path == 2 \
+            else (("chain_a_kernel", 1), ("chain_b_kernel", 2))
+        for name, mask in stage_names:
             g = mie_b200.ChainPlan(x, cfg, out=y, workspace=ws, stages=mask)
             for _ in range(3):
                 g.replay()
@@ -306,7 +311,9 @@ def run_ours(args):
             traffic = None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                    traffic = json.load(f).get(dom)
+                    tj = json.load(f)
+                parts = [tj.get(k) for k in dom.split("+")]
+                traffic = sum(parts) if all(v is not None for v in parts) else None
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
