@@ -16,6 +16,8 @@
 // sums in registers) and accumulates the weighted shifted pixel — ~35 instructions per pixel and shift
 // instead of ~110 for the direct 36-term patch distance.  exp() is ex2.approx (MUFU): the result is
 // within the north star's fp32 tolerance (rel 1e-5) of the float64 oracle, not bit-exact.
+#include <cstdlib>
+
 #include "mie_common.cuh"
 
 namespace mie {
@@ -112,6 +114,103 @@ nlm_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, in
     }
 }
 
+// ---------------------------------------------------------------- marching variant (no barriers per shift)
+// The tile kernel above synchronises the block twice per shift (1 058 barriers per tile for d = 11) and keeps
+// only 148 of its 256 threads busy while the horizontal sums are formed: ~59 issue slots per pixel and shift.
+// Here a warp works alone on a band of BH output rows x VL = 33 - 2o output columns: lane l owns the column
+// of squared differences c = x0 - o + 1 + l, the horizontal box sum over columns c .. c + 2o - 1 is three
+// shuffle-adds (s2 = d + d[+1]; s4 = s2 + s2[+2]; s6 = s4 + s2[+4] for o = 3), the vertical box sum is the sum
+// of a register ring of the last 2o row sums, and the BH accumulator pairs (num, den) of the lane's output
+// column stay in registers across all (2d+1)^2 shifts.  After the neighbourhood is staged in shared memory
+// (read-only from then on) there is not a single barrier; ~23 instructions per lane and row step, 84 % of the
+// lanes and BH / (BH + 2o - 1) of the row steps produce an output.
+template <int O>
+__device__ __forceinline__ float nlm_hsum(float d2) {
+    const float s2 = d2 + __shfl_down_sync(0xffffffffu, d2, 1);
+    if (O == 1) return s2;
+    const float s4 = s2 + __shfl_down_sync(0xffffffffu, s2, 2);
+    if (O == 2) return s4;
+    if (O == 3) return s4 + __shfl_down_sync(0xffffffffu, s2, 4);
+    return s4 + __shfl_down_sync(0xffffffffu, s4, 4);
+}
+__device__ __forceinline__ float nlm_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int O> struct NlmMarch {
+    static constexpr int box = 2 * O, VL = 33 - box, BH = 32, TWB = 2 * VL, THB = 4 * BH;
+    static constexpr int RMAX = O + kNlmMaxD, PITCH = (TWB + 2 * RMAX) | 1;
+};
+
+template <typename SrcT, typename DstT, int O>
+__global__ void __launch_bounds__(256, 2)
+nlm_march_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                 int64_t dsh, NlmArgs a) {
+    using G = NlmMarch<O>;
+    constexpr int box = G::box, VL = G::VL, BH = G::BH, PITCH = G::PITCH;
+    extern __shared__ __align__(16) float S[];
+    const int d = a.d, R = O + d;
+    const int EW = G::TWB + 2 * R, EH = G::THB + 2 * R;
+    const int64_t tile = blockIdx.x;
+    const int tx0 = (int)(tile % a.tiles_x) * G::TWB, ty0 = (int)((tile / a.tiles_x) % a.tiles_y) * G::THB;
+    const int64_t n = tile / ((int64_t)a.tiles_x * a.tiles_y);
+    const SrcT* plane = src + n * ssn;
+    for (int i = threadIdx.x; i < EH * EW; i += 256) {
+        const int r = i / EW, c = i - r * EW;
+        const int sy = border_index(ty0 - R + r, a.h, MIE_BORDER_REFLECT);
+        const int sx = border_index(tx0 - R + c, a.w, MIE_BORDER_REFLECT);
+        S[r * PITCH + c] = Px<SrcT>::to01(plane[(int64_t)sy * ssh + sx], a.lo, a.rg);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int x0 = (warp & 1) * VL, y0 = (warp >> 1) * BH;                 // the warp's outputs, tile coordinates
+    const float* pbase = S + (R + y0 - O + 1) * PITCH + (R + x0 - O + 1 + lane);   // difference row 0, column c
+    const float* cbase = S + (R + y0) * PITCH + (R + x0 + lane);                   // output row 0, output column
+    const float k2 = -1.4426950408889634f * a.inv_h2s2;                    // weight = 2^(k2 * max(D - var, 0))
+    const float cut = -5.0f * 1.4426950408889634f;                         // distance 5 on that scale
+    float num[BH], den[BH];
+#pragma unroll
+    for (int j = 0; j < BH; ++j) {                                         // zero shift: D = 0, weight 2 (upstream quirk)
+        const float c = cbase[j * PITCH];
+        num[j] = c + c; den[j] = 2.0f;
+    }
+    for (int ty = -d; ty <= d; ++ty) {
+        for (int tx = -d; tx <= d; ++tx) {
+            if (ty == 0 && tx == 0) continue;
+            const int toff = ty * PITCH + tx;
+            const float* q = pbase + toff;
+            const float* cq = cbase + toff;
+            float hs[box];
+#pragma unroll
+            for (int s = 0; s < BH + box - 1; ++s) {
+                const float df = pbase[s * PITCH] - q[s * PITCH];
+                hs[s % box] = nlm_hsum<O>(df * df);
+                if (s >= box - 1) {
+                    const int j = s - (box - 1);
+                    float V = hs[0];
+#pragma unroll
+                    for (int k = 1; k < box; ++k) V += hs[k];
+                    const float e = fmaxf(V - a.var_term, 0.0f) * k2;
+                    const float wgt = e >= cut ? nlm_ex2(e) : 0.0f;     // branch-free: select, not a divergent region
+                    num[j] = fmaf(wgt, cq[j * PITCH], num[j]);
+                    den[j] += wgt;
+                }
+            }
+        }
+    }
+    const int x = tx0 + x0 + lane;
+    if (lane < VL && x < a.w) {
+#pragma unroll
+        for (int j = 0; j < BH; ++j) {
+            const int y = ty0 + y0 + j;
+            if (y < a.h) dst[n * dsn + (int64_t)y * dsh + x] = Px<DstT>::from01(num[j] / den[j], a.lo, a.rg);
+        }
+    }
+}
+
 int nlm_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
              int64_t dsn, int64_t dsh, int patch_size, int patch_distance, float hpar, float sigma, float lo, float hi,
              cudaStream_t st) {
@@ -133,6 +232,28 @@ int nlm_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w
     a.inv_h2s2 = (float)(1.0 / ((double)hpar * hpar * s * s));
     a.var_term = (float)((double)(2 * o) * (2 * o) * 2.0 * (double)sigma * sigma);
     a.lo = lo; a.rg = hi - lo;
+    static const bool no_march = [] { const char* e = getenv("MIE_NLM_NO_MARCH"); return e && e[0] == '1'; }();
+    if (!no_march) {
+#define MIE_NLM_MARCH(O_)                                                                                      \
+    {                                                                                                          \
+        using G = NlmMarch<O_>;                                                                                \
+        a.tiles_x = ceil_div(w, G::TWB); a.tiles_y = ceil_div(h, G::THB);                                      \
+        const int64_t mblocks = n * a.tiles_x * a.tiles_y;                                                     \
+        if (mblocks > 2147483647LL) return MIE_E_SHAPE;                                                        \
+        const size_t msmem = (size_t)(G::THB + 2 * (O_ + patch_distance)) * G::PITCH * 4;                      \
+        MIE_ENSURE_SMEM((nlm_march_kernel<SrcT, DstT, O_>), (G::THB + 2 * G::RMAX) * G::PITCH * 4);            \
+        nlm_march_kernel<SrcT, DstT, O_><<<(unsigned)mblocks, 256, msmem, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, \
+                                                                              dsn, dsh, a);                    \
+    }
+        switch (o) {
+            case 1: MIE_DISPATCH_SRC_DST(sd, dd, MIE_NLM_MARCH(1)); break;
+            case 2: MIE_DISPATCH_SRC_DST(sd, dd, MIE_NLM_MARCH(2)); break;
+            case 3: MIE_DISPATCH_SRC_DST(sd, dd, MIE_NLM_MARCH(3)); break;
+            default: MIE_DISPATCH_SRC_DST(sd, dd, MIE_NLM_MARCH(4)); break;
+        }
+#undef MIE_NLM_MARCH
+        return check_launch();
+    }
     const int64_t blocks = n * a.tiles_x * a.tiles_y;
     if (blocks > 2147483647LL) return MIE_E_SHAPE;
     const int E = kNlmTile + 2 * (o + patch_distance);
