@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--d", type=int, default=512)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="time eager calls instead of the captured SlabPlan")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -40,7 +41,11 @@ def main():
     slab = torch.from_numpy(vol[z0:z1].copy()).to(dev)
     vr = None   # integer <-> [0,1] mapping = the full dtype range (an HU window is an option)
 
+    plan = None if args.eager else M.SlabPlan(slab, 2.0, (8, 8), value_range=vr)
+
     def step():
+        if plan is not None:
+            return plan.replay()
         return M.median3d_clahe_slab(slab, 2.0, (8, 8), value_range=vr)
 
     for _ in range(3):
@@ -74,8 +79,10 @@ def main():
         vox = args.d * 512 * 512
         t = float(ms.item())
         print(json.dumps({"config": f"C3 median3d 3x3x3 + per-slice CLAHE, {args.d}x512x512 i16, {world} z-slab(s)",
-                          "n_gpus": world, "ms": round(t, 4), "mvoxel_s": round(vox / t / 1e3, 1), "scaling": "strong",
+                          "n_gpus": world, "ms": round(t, 4), "mvoxel_s": round(vox / t / 1e3, 1), "scaling": "strong", "launch": "eager" if args.eager else "CUDA graph (SlabPlan)",
                           "halo_bytes_per_face": 512 * 512 * 2, "bit_identical_to_unsharded": same}), flush=True)
+    if plan is not None:
+        plan.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

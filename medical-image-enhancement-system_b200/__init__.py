@@ -12,7 +12,7 @@ from .enhance import clahe16_luts, clahe_apply, clahe_histograms, clahe_luts, eq
 from .filters import bilateral_blur, denoise_nl_means, gaussian_blur2d, get_gaussian_kernel1d, median, median_blur, unsharp_mask
 from .loader import HostSlicePipeline, enhance_chain_host
 from .metrics import mae, mse, psnr, rmse, ssim
-from .volume import exchange_z_halos, median3d_clahe_slab, shard_range, start_z_halo_exchange
+from .volume import SlabPlan, exchange_z_halos, median3d_clahe_slab, shard_range, start_z_halo_exchange
 
 __version__ = "0.1.0"
 
@@ -23,5 +23,5 @@ __all__ = [
     "ChainConfig", "ChainPlan", "enhance_chain", "chain_workspace_bytes",
     "HostSlicePipeline", "enhance_chain_host",
     "mse", "rmse", "psnr", "ssim", "mae",
-    "shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab",
+    "shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab", "SlabPlan",
 ]

@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab", "world_info"]
+__all__ = ["shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab", "SlabPlan", "world_info"]
 
 
 def world_info(group=None):
@@ -108,3 +108,44 @@ def median3d_clahe_slab(slab: torch.Tensor, clip_limit: float = 2.0, grid_size: 
         median(slab[0:1], out=med[0:1], mode=mode, halo_lo=halo_lo, halo_hi=slab[1])
         median(slab[d - 1:d], out=med[d - 1:d], mode=mode, halo_lo=slab[d - 2], halo_hi=halo_hi)
     return equalize_clahe(med.unsqueeze(1), clip_limit, grid_size, value_range=value_range).squeeze(1)
+
+
+class SlabPlan:
+    """median3d_clahe_slab on a FIXED slab buffer, captured once into a CUDA graph — the halo send / recv
+    (NCCL supports stream capture), the three median launches, the CLAHE launches and the allocations they
+    make — and replayed per volume: at 8 GPUs a 64-plane slab needs ~0.1 ms of kernels, and a dozen eager
+    launches plus the Python around them cost several times that.
+
+        plan = SlabPlan(slab)            # warm-up call (creates the NCCL pair communicators) + capture
+        slab.copy_(next_volume_part)     # refill the same buffer
+        out = plan.replay()              # this rank's part of the result (owned by the plan)
+
+    Every rank of the group must build the plan and replay it the same number of times."""
+
+    def __init__(self, slab: torch.Tensor, clip_limit: float = 2.0, grid_size: tuple = (8, 8), *,
+                 mode: str = "nearest", value_range=None, group=None):
+        if not slab.is_cuda or slab.dim() != 3 or not slab.is_contiguous():
+            raise ValueError("SlabPlan needs a contiguous (D, H, W) CUDA slab")
+        self.slab = slab
+        self._args = (clip_limit, grid_size)
+        self._kw = dict(mode=mode, value_range=value_range, group=group)
+        with torch.cuda.device(slab.device):
+            median3d_clahe_slab(slab, *self._args, **self._kw)       # eager: NCCL communicators, lazy inits
+            torch.cuda.synchronize(slab.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = median3d_clahe_slab(slab, *self._args, **self._kw)
+            torch.cuda.synchronize(slab.device)
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.out
+
+    def close(self) -> None:
+        """Release the captured graph.  Call it (on every rank) before destroy_process_group(): a live graph
+        that holds captured NCCL operations makes the process-group teardown hang."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.slab.device)
+            self.graph.reset()
+            self.graph = None
+            self.out = None

@@ -36,6 +36,13 @@ def _worker(rank, world, port, out_dir):
         slab = torch.from_numpy(vol[z0:z1].copy()).to(dev)
         out = M.median3d_clahe_slab(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0))
         np.save(os.path.join(out_dir, f"vol{rank}.npy"), out.cpu().numpy())
+        # the same step captured into a CUDA graph (NCCL halo exchange included) and replayed on new data
+        plan = M.SlabPlan(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0))
+        assert torch.equal(plan.replay(), out)
+        vol2 = synthetic.phantom_volume((37, 128, 192), np.int16, seed=7)
+        slab.copy_(torch.from_numpy(vol2[z0:z1].copy()).to(dev))
+        np.save(os.path.join(out_dir, f"vol2_{rank}.npy"), plan.replay().cpu().numpy())
+        plan.close()
         x = synthetic.phantom((10, 1, 256, 256), np.uint16, seed=6)
         s0, s1 = M.shard_range(10, world, rank)
         y = M.enhance_chain(torch.from_numpy(x[s0:s1].copy()).to(dev), M.ChainConfig(grid_size=(4, 4)))
@@ -60,6 +67,10 @@ def test_sharded_results_equal_single_gpu(tmp_path, world):
     ref = M.median3d_clahe_slab(torch.from_numpy(vol).to(dev), 2.0, (2, 3), value_range=(-1024.0, 3071.0)).cpu().numpy()
     got = np.concatenate([np.load(tmp_path / f"vol{r}.npy") for r in range(world)])
     assert np.array_equal(got, ref)
+    vol2 = synthetic.phantom_volume((37, 128, 192), np.int16, seed=7)
+    ref2 = M.median3d_clahe_slab(torch.from_numpy(vol2).to(dev), 2.0, (2, 3), value_range=(-1024.0, 3071.0)).cpu().numpy()
+    got2 = np.concatenate([np.load(tmp_path / f"vol2_{r}.npy") for r in range(world)])
+    assert np.array_equal(got2, ref2)
     x = synthetic.phantom((10, 1, 256, 256), np.uint16, seed=6)
     refc = M.enhance_chain(torch.from_numpy(x).to(dev), M.ChainConfig(grid_size=(4, 4))).cpu().numpy()
     gotc = np.concatenate([np.load(tmp_path / f"chain{r}.npy") for r in range(world)])
