@@ -324,7 +324,7 @@ def run_ours(args):
                     "kernels_ms": {k: round(v, 4) for k, v in kern.items()}}
         step_gbs = ALG_BYTES_PER_PIXEL * PIXELS / (ms_step * 1e-3) / 1e9
         cpu = None
-        if world == 1 or rank == 0:
+        if world == 1:   # the CPU baseline is a rank-0, N = 1 figure (the reference arm times it at every N)
             mpx, cores, desc = cpu_chain_sample(sample_slices=32, reps=5, budget_s=20.0)
             cpu = {"value": round(mpx, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
         line = {

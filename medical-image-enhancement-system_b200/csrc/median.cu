@@ -299,6 +299,7 @@ __device__ __forceinline__ P select27_sorted(const P* A, const P* B, const P* C)
 template <typename T> struct PackedOf;
 template <> struct PackedOf<uint16_t> { using type = PackedU16; };
 template <> struct PackedOf<int16_t> { using type = PackedS16; };
+template <> struct PackedOf<uint8_t> { using type = PackedU16; };   // 8-bit pixels widened to 16-bit lanes on load
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -468,7 +469,7 @@ median3d_direct_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t s
     else median3d_direct_body<T, true>(src, dst, ssd, ssh, dsd, dsh, d, h, w, x, y, z0, z1, halo_lo, halo_hi, rep);
 }
 
-// ---------------------------------------------------------------- 2-D 3x3, 16-bit pixels, marching rows
+// ---------------------------------------------------------------- 2-D 3x3, 8 / 16-bit pixels, marching rows
 // A lane owns 8 consecutive columns (one 128-bit load per row = four packed pixel pairs) and marches
 // down a band of rows with the last three rows in registers; the pair to the left / right comes from the
 // neighbouring lane by shuffle (from global memory or the border rule at the ends of the warp's 256-column
@@ -501,7 +502,15 @@ median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
         uint32_t left = 0u, right = 0u;
         if (sy >= 0) {                              // uniform
             const T* row = plane + (int64_t)sy * ssh;
-            if (active) v = __ldg(reinterpret_cast<const uint4*>(row + x0));
+            if (active) {
+                if constexpr (sizeof(T) == 1) {     // 8 bytes -> four (pixel, pixel) words of 16-bit lanes
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + x0));
+                    v.x = __byte_perm(raw.x, 0u, 0x4140); v.y = __byte_perm(raw.x, 0u, 0x4342);
+                    v.z = __byte_perm(raw.y, 0u, 0x4140); v.w = __byte_perm(raw.y, 0u, 0x4342);
+                } else {
+                    v = __ldg(reinterpret_cast<const uint4*>(row + x0));
+                }
+            }
             left = __shfl_up_sync(0xffffffffu, v.w, 1);
             right = __shfl_down_sync(0xffffffffu, v.x, 1);
             if (active) {
@@ -509,13 +518,15 @@ median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
                     left = border == MIE_BORDER_REFLECT ? (v.x & 0xFFFF0000u)
                          : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? (v.x << 16) : 0u;
                 } else if (lane == 0) {
-                    left = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
+                    if constexpr (sizeof(T) == 1) left = (uint32_t)__ldg(row + x0 - 1) << 16;
+                    else left = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
                 }
                 if (x0 + 8 == w) {                  // pixel w sits in the low half
                     right = border == MIE_BORDER_REFLECT ? (v.w & 0xFFFFu)
                           : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? (v.w >> 16) : 0u;
                 } else if (lane == 31) {
-                    right = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
+                    if constexpr (sizeof(T) == 1) right = (uint32_t)__ldg(row + x0 + 8);
+                    else right = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
                 }
             }
         }
@@ -552,7 +563,13 @@ median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
                     const P c = pmin(maxlo, medmi), d = pmax(maxlo, medmi);
                     o[k] = pmax(c, pmin(d, minhi)).v;
                 }
-                if (active) *reinterpret_cast<uint4*>(oplane + (int64_t)y * dsh + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+                if (active) {
+                    if constexpr (sizeof(T) == 1)
+                        *reinterpret_cast<uint2*>(oplane + (int64_t)y * dsh + x0) =
+                            make_uint2(__byte_perm(o[0], o[1], 0x6420), __byte_perm(o[2], o[3], 0x6420));
+                    else
+                        *reinterpret_cast<uint4*>(oplane + (int64_t)y * dsh + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
             }
         }
     }
@@ -564,8 +581,9 @@ static int try_median3x3_packed(const void* src, void* dst, int64_t n, int h, in
                                 int64_t dsn, int64_t dsh, int border, cudaStream_t st) {
     static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
     if (off || (w & 7) || h < 2) return -1;
-    if (((uintptr_t)src % 16) || ((ssn * 2) % 16) || ((ssh * 2) % 16)) return -1;
-    if (((uintptr_t)dst % 16) || ((dsn * 2) % 16) || ((dsh * 2) % 16)) return -1;
+    constexpr int esz = (int)sizeof(T), al = 8 * esz;   // one 8-pixel vector per lane and row
+    if (((uintptr_t)src % al) || ((ssn * esz) % al) || ((ssh * esz) % al)) return -1;
+    if (((uintptr_t)dst % al) || ((dsn * esz) % al) || ((dsh * esz) % al)) return -1;
     const int strips = ceil_div(w, 256);
     int rows = 32;                                 // 2 halo rows per band: 6 % extra loads
     while (rows > 8 && n * strips * ceil_div(h, rows) < 8 * 148 * 4) rows >>= 1;   // small jobs: more warps
@@ -626,10 +644,12 @@ int mie_median2d(const void* src, void* dst, int dtype, int64_t n, int h, int w,
     if (ky <= 0 || kx <= 0 || !(ky & 1) || !(kx & 1)) return MIE_E_KERNEL;
     if (n == 0) return MIE_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (ky == 3 && kx == 3 && (dtype == MIE_U16 || dtype == MIE_I16)) {
+    if (ky == 3 && kx == 3 && dtype != MIE_F32) {
         rc = dtype == MIE_U16 ? try_median3x3_packed<uint16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
                                                                dst_stride_n, dst_stride_h, border, st)
-                              : try_median3x3_packed<int16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
+           : dtype == MIE_I16 ? try_median3x3_packed<int16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
+                                                              dst_stride_n, dst_stride_h, border, st)
+                              : try_median3x3_packed<uint8_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
                                                               dst_stride_n, dst_stride_h, border, st);
         if (rc >= 0) return rc;
     }
