@@ -19,7 +19,7 @@ namespace mie {
 // instructions per pixel, 7.6 of them in the pixel loop).  So a warp owns a whole tile — 128 pixels per
 // lane for 64x64 tiles — with its own 257-slot histogram, no block-level synchronisation at all, and
 // builds the LUT as soon as its own tile is done while the other warps of the block keep counting.
-template <typename SrcT, bool WIN>
+template <typename SrcT, bool WIN, bool IDX>
 __global__ void __launch_bounds__(256)
 clahe_lut_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, LutParams lp,
                       uint32_t* __restrict__ hist_out, uint8_t* __restrict__ lut_out, int64_t tiles, WinCvt cv) {
@@ -37,12 +37,19 @@ clahe_lut_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, Cl
     const uint32_t h32 = hist_base32(s_hist);
     const int chunks = g.tw >> 3;              // 8-pixel chunks per tile row
     auto count8 = [&](int r, int c) {
-        float x[8];
-        PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
+        if constexpr (IDX) {   // default-range integers: the bin is an integer function of the code (window.cuh)
+            uint32_t u[8];
+            Codes<SrcT>::load8(base + (int64_t)r * ssh + 8 * c, u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (INT) hist_add_le1(h32, x[k]);
-            else hist_add_nobranch(s_hist, fast_bin<false>(x[k]));
+            for (int k = 0; k < 8; ++k) hist_add_nobranch(s_hist, (int)Codes<SrcT>::bin(u[k]));
+        } else {
+            float x[8];
+            PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (INT) hist_add_le1(h32, x[k]);
+                else hist_add_nobranch(s_hist, fast_bin<false>(x[k]));
+            }
         }
     };
     if (chunks <= 32 && (32 % chunks) == 0) {  // a warp covers 32 / chunks whole rows per step
@@ -70,7 +77,7 @@ clahe_lut_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, Cl
 // ---------------------------------------------------------------- histogram -> LUT, one BLOCK per tile
 // Latency variant for small jobs (a single 512x512 slice has 64 tiles: one warp per tile would leave
 // most of the machine idle): 256 threads share one tile histogram, warp 0 builds the LUT.
-template <typename SrcT, bool WIN>
+template <typename SrcT, bool WIN, bool IDX>
 __global__ void __launch_bounds__(256)
 clahe_lut_block_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, LutParams lp,
                        uint32_t* __restrict__ hist_out, uint8_t* __restrict__ lut_out, WinCvt cv) {
@@ -88,12 +95,19 @@ clahe_lut_block_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, C
     const int total = chunks * g.th;
     for (int i = tid; i < total; i += 256) {
         const int r = i / chunks, c = i - r * chunks;
-        float x[8];
-        PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
+        if constexpr (IDX) {
+            uint32_t u[8];
+            Codes<SrcT>::load8(base + (int64_t)r * ssh + 8 * c, u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (INT) hist_add_le1(h32, x[k]);
-            else hist_add_nobranch(s_hist, fast_bin<false>(x[k]));
+            for (int k = 0; k < 8; ++k) hist_add_nobranch(s_hist, (int)Codes<SrcT>::bin(u[k]));
+        } else {
+            float x[8];
+            PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (INT) hist_add_le1(h32, x[k]);
+                else hist_add_nobranch(s_hist, fast_bin<false>(x[k]));
+            }
         }
     }
     __syncthreads();
@@ -134,7 +148,7 @@ __device__ __forceinline__ float axis_weight(int y, int T) {
     return __fdiv_rn((float)(T - 1 - r), (float)(T - 1));
 }
 
-template <typename SrcT, typename DstT, bool WIN>
+template <typename SrcT, typename DstT, bool WIN, bool IDX>
 __global__ void __launch_bounds__(1024)
 clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells, WinCvt cv) {
     constexpr bool INT = sizeof(SrcT) != 4 && !WIN;
@@ -162,13 +176,21 @@ clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells, WinCvt
     __syncthreads();
 #pragma unroll 4
     for (int r = 0; r < a.rows_per_block; ++r) {
-        float x[4], y[4];
-        PixIO<SrcT, WIN>::load4(sp + (int64_t)r * a.ssh, x, cv);
+        float y[4];
         const float wyv = s_wy[r];
+        if constexpr (IDX) {   // default-range integers: the lookup index is an integer function of the code
+            uint32_t u[4];
+            Codes<SrcT>::load4(sp + (int64_t)r * a.ssh, u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t bits = INT ? fast_idx_bits_le1(x[k]) : fast_idx_bits<false>(x[k]);
-            y[k] = clahe_px(lds64_(tb + (__byte_perm(bits, 0u, 0x4440) << 3)), wxv[k], wyv);
+            for (int k = 0; k < 4; ++k) y[k] = clahe_px(lds64_(tb + (Codes<SrcT>::index(u[k]) << 3)), wxv[k], wyv);
+        } else {
+            float x[4];
+            PixIO<SrcT, WIN>::load4(sp + (int64_t)r * a.ssh, x, cv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t bits = INT ? fast_idx_bits_le1(x[k]) : fast_idx_bits<false>(x[k]);
+                y[k] = clahe_px(lds64_(tb + (__byte_perm(bits, 0u, 0x4440) << 3)), wxv[k], wyv);
+            }
         }
         PixIO<DstT, WIN>::store4(dp + (int64_t)r * a.dsh, y, cv);
     }
@@ -176,6 +198,10 @@ clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells, WinCvt
 
 // ---------------------------------------------------------------- host side
 static const int kEsz[4] = {1, 2, 2, 4};
+static bool int_rules_disabled() {   // MIE_CLAHE_NO_INT_RULES=1: keep the float conversion of the input (A/B tests)
+    static const bool off = [] { const char* e = getenv("MIE_CLAHE_NO_INT_RULES"); return e && e[0] == '1'; }();
+    return off;
+}
 static bool fast_disabled() {
     static const bool off = [] { const char* e = getenv("MIE_CLAHE_NO_FAST"); return e && e[0] == '1'; }();
     return off;
@@ -201,15 +227,16 @@ int launch_clahe_lut_fast(const void* src, int sd, int64_t n, int64_t ssn, int64
     if (mode < 0) return MIE_E_UNSUPPORTED;   // callers test clahe_lut_fast_ok first
     const int wpb = 8;
     const int64_t blocks = (tiles + wpb - 1) / wpb;
-#define MIE_LUT_FAST(WIN_)                                                                                        \
+#define MIE_LUT_FAST(WIN_, IDX_)                                                                                  \
     if (tiles < 4 * 148) /* small job: spread every tile over a whole block */                                   \
-        clahe_lut_block_kernel<SrcT, WIN_><<<(unsigned)tiles, 256, 0, st>>>((const SrcT*)src, ssn, ssh, g, lp, hist,  \
-                                                                         luts, cv);                               \
+        clahe_lut_block_kernel<SrcT, WIN_, IDX_><<<(unsigned)tiles, 256, 0, st>>>((const SrcT*)src, ssn, ssh, g, lp,  \
+                                                                               hist, luts, cv);                   \
     else                                                                                                          \
-        clahe_lut_fast_kernel<SrcT, WIN_><<<(unsigned)blocks, 32 * wpb, 0, st>>>((const SrcT*)src, ssn, ssh, g, lp,   \
-                                                                              hist, luts, tiles, cv)
-    if (mode == 1) { MIE_DISPATCH_SRC(sd, MIE_LUT_FAST(true)); }
-    else { MIE_DISPATCH_SRC(sd, MIE_LUT_FAST(false)); }
+        clahe_lut_fast_kernel<SrcT, WIN_, IDX_><<<(unsigned)blocks, 32 * wpb, 0, st>>>((const SrcT*)src, ssn, ssh, g, \
+                                                                                    lp, hist, luts, tiles, cv)
+    if (mode == 1) { MIE_DISPATCH_SRC(sd, MIE_LUT_FAST(true, false)); }
+    else if (sd != MIE_F32 && int_rules_ok(sd) && !int_rules_disabled()) { MIE_DISPATCH_SRC(sd, MIE_LUT_FAST(false, true)); }
+    else { MIE_DISPATCH_SRC(sd, MIE_LUT_FAST(false, false)); }
 #undef MIE_LUT_FAST
     return check_launch();
 }
@@ -249,11 +276,12 @@ int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t 
     const int64_t blocks = n * a.blocks_per_image;
     if (blocks > 2147483647LL) return MIE_E_SHAPE;
     const size_t smem = (size_t)(g.gw + 1) * kBins * 8;
-#define MIE_APPLY_FAST(WIN_)                                                                               \
-    MIE_ENSURE_SMEM((clahe_apply_fast_kernel<SrcT, DstT, WIN_>), 80 * 1024);                               \
-    clahe_apply_fast_kernel<SrcT, DstT, WIN_><<<(unsigned)blocks, g.w / 4, smem, st>>>(a, (const uint2*)cells, cv)
-    if (mode == 1) { MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST(true)); }
-    else { MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST(false)); }
+#define MIE_APPLY_FAST(WIN_, IDX_)                                                                         \
+    MIE_ENSURE_SMEM((clahe_apply_fast_kernel<SrcT, DstT, WIN_, IDX_>), 80 * 1024);                         \
+    clahe_apply_fast_kernel<SrcT, DstT, WIN_, IDX_><<<(unsigned)blocks, g.w / 4, smem, st>>>(a, (const uint2*)cells, cv)
+    if (mode == 1) { MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST(true, false)); }
+    else if (sd != MIE_F32 && int_rules_ok(sd) && !int_rules_disabled()) { MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST(false, true)); }
+    else { MIE_DISPATCH_SRC_DST(sd, dd, MIE_APPLY_FAST(false, false)); }
 #undef MIE_APPLY_FAST
     return check_launch();
 }

@@ -116,7 +116,7 @@ equalize_apply_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int6
 // stores, the divide-free pixel conversion of chain_fast.cuh, one ATOMS.POPC.INC per pixel into a single
 // block histogram, and — because lut[trunc(v)] takes only 256 values — a per-block table of the 256
 // possible OUTPUT codes, so a pixel costs one conversion, one shared-memory lookup and a pack.
-template <typename SrcT, bool WIN>
+template <typename SrcT, bool WIN, bool IDX>
 __global__ void __launch_bounds__(256)
 equalize_hist_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh, int h, int w, int rows_per_block,
                           EqPlaneState* __restrict__ state, WinCvt cv) {
@@ -131,12 +131,19 @@ equalize_hist_fast_kernel(const SrcT* __restrict__ src, int64_t ssn, int64_t ssh
     const int chunks = w >> 3, total = chunks * (y1 - y0);
     for (int i = tid; i < total; i += 256) {
         const int r = i / chunks, c = i - r * chunks;
-        float x[8];
-        PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
+        if constexpr (IDX) {   // default-range integers: eq_bin is an integer function of the code (window.cuh)
+            uint32_t u[8];
+            Codes<SrcT>::load8(base + (int64_t)r * ssh + 8 * c, u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            if (WIN) hist_add(s_hist, eq_bin(__fmul_rn(x[k], 255.0f)));                   // pixels outside the window: ignored
-            else hist_add_le1(h32, div255(__fmul_rn(x[k], 255.0f)));                      // eq_bin, x in [0,1]
+            for (int k = 0; k < 8; ++k) hist_add_nobranch(s_hist, (int)Codes<SrcT>::bin(u[k]));
+        } else {
+            float x[8];
+            PixIO<SrcT, WIN>::load8(base + (int64_t)r * ssh + 8 * c, x, cv);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (WIN) hist_add(s_hist, eq_bin(__fmul_rn(x[k], 255.0f)));               // pixels outside the window: ignored
+                else hist_add_le1(h32, div255(__fmul_rn(x[k], 255.0f)));                  // eq_bin, x in [0,1]
+            }
         }
     }
     __syncthreads();
@@ -167,7 +174,7 @@ __device__ __forceinline__ void eq_store8(float* p, const float* s_out, const ui
     *reinterpret_cast<float4*>(p + 4) = make_float4(s_out[i[4]], s_out[i[5]], s_out[i[6]], s_out[i[7]]);
 }
 
-template <typename SrcT, typename DstT, bool WIN>
+template <typename SrcT, typename DstT, bool WIN, bool IDX>
 __global__ void __launch_bounds__(256)
 equalize_apply_fast_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh,
                            int64_t dsn, int64_t dsh, int h, int w, int rows_per_block, float lo, float rg,
@@ -187,12 +194,18 @@ equalize_apply_fast_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst,
 #pragma unroll 2
         for (int i = tid; i < total; i += 256) {
             const int r = i / chunks, c = i - r * chunks;
-            float x[8];
             uint32_t idx[8];
-            PixIO<SrcT, WIN>::load8(sp + (int64_t)r * ssh + 8 * c, x, cv);
+            if constexpr (IDX) {
+                Codes<SrcT>::load8(sp + (int64_t)r * ssh + 8 * c, idx);
 #pragma unroll
-            for (int k = 0; k < 8; ++k)   // trunc(clamp(x*255, 0, 255))
-                idx[k] = (WIN ? fast_idx_bits<false>(x[k]) : fast_idx_bits_le1(x[k])) & 0xFFu;
+                for (int k = 0; k < 8; ++k) idx[k] = Codes<SrcT>::index(idx[k]);
+            } else {
+                float x[8];
+                PixIO<SrcT, WIN>::load8(sp + (int64_t)r * ssh + 8 * c, x, cv);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)   // trunc(clamp(x*255, 0, 255))
+                    idx[k] = (WIN ? fast_idx_bits<false>(x[k]) : fast_idx_bits_le1(x[k])) & 0xFFu;
+            }
             eq_store8(dp + (int64_t)r * dsh + 8 * c, s_out, idx);
         }
     } else {   // step == 0 (e.g. a constant plane): v/255 goes back unchanged
@@ -254,9 +267,12 @@ int mie_equalize(const void* src, void* dst, int src_dtype, int dst_dtype, int64
         dim3 grid((unsigned)ceil_div(h, rows), (unsigned)n);
         WinCvt cv = {};
         const bool win = range_mode(src_dtype, lo, hi, &cv) == 1;
+        static const bool no_int = [] { const char* e = getenv("MIE_EQUALIZE_NO_INT_RULES"); return e && e[0] == '1'; }();
+        const bool idx = !win && !no_int && int_rules_ok(src_dtype);
 #define MIE_EQ_HIST(T_)                                                                                            \
-    if (win) equalize_hist_fast_kernel<T_, true><<<grid, 256, 0, st>>>((const T_*)src, src_stride_n, src_stride_h, h, w, rows, state, cv); \
-    else equalize_hist_fast_kernel<T_, false><<<grid, 256, 0, st>>>((const T_*)src, src_stride_n, src_stride_h, h, w, rows, state, cv)
+    if (win) equalize_hist_fast_kernel<T_, true, false><<<grid, 256, 0, st>>>((const T_*)src, src_stride_n, src_stride_h, h, w, rows, state, cv); \
+    else if (idx) equalize_hist_fast_kernel<T_, false, true><<<grid, 256, 0, st>>>((const T_*)src, src_stride_n, src_stride_h, h, w, rows, state, cv); \
+    else equalize_hist_fast_kernel<T_, false, false><<<grid, 256, 0, st>>>((const T_*)src, src_stride_n, src_stride_h, h, w, rows, state, cv)
         switch (src_dtype) {
             case MIE_U8: MIE_EQ_HIST(uint8_t); break;
             case MIE_U16: MIE_EQ_HIST(uint16_t); break;
@@ -268,12 +284,13 @@ int mie_equalize(const void* src, void* dst, int src_dtype, int dst_dtype, int64
         equalize_lut_kernel<<<(unsigned)n, 256, 0, st>>>(state);
         rc = check_launch();
         if (rc) return rc;
-#define MIE_EQ_APPLY(WIN_)                                                                                  \
-    equalize_apply_fast_kernel<SrcT, DstT, WIN_><<<grid, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, src_stride_n, \
-                                                                      src_stride_h, dst_stride_n, dst_stride_h, h, \
-                                                                      w, rows, lo, rg, state, cv)
-        if (win) { MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, MIE_EQ_APPLY(true)); }
-        else { MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, MIE_EQ_APPLY(false)); }
+#define MIE_EQ_APPLY(WIN_, IDX_)                                                                            \
+    equalize_apply_fast_kernel<SrcT, DstT, WIN_, IDX_><<<grid, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, src_stride_n, \
+                                                                            src_stride_h, dst_stride_n, dst_stride_h, \
+                                                                            h, w, rows, lo, rg, state, cv)
+        if (win) { MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, MIE_EQ_APPLY(true, false)); }
+        else if (idx) { MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, MIE_EQ_APPLY(false, true)); }
+        else { MIE_DISPATCH_SRC_DST(src_dtype, dst_dtype, MIE_EQ_APPLY(false, false)); }
 #undef MIE_EQ_APPLY
         return check_launch();
     }

@@ -99,6 +99,63 @@ struct PixIO<uint8_t, true> {
 template <>
 struct PixIO<float, true> : PixIO<float, false> {};
 
+// ---------------------------------------------------------------- integer rules for the default range
+// For integer pixels with the dtype's default range, the kornia histogram bin floor(x01 * 256) and lookup
+// index trunc(x01 * 255) (and equalize's floor(RN(RN(x01 * 255) / 255) * 256)) are pure integer functions
+// of the code u = v - dtype_min:
+//     16-bit:  bin = u >> 8,   index = u / 257 = (u * 65281) >> 24        8-bit:  bin = index = u
+// (the float roundings never cross an integer boundary).  int_rules_ok() checks this against the float
+// formulas for every code on the host before the first launch, so the standalone CLAHE / equalize kernels
+// need no float conversion of their INPUT at all.
+template <typename T> struct Codes;
+template <> struct Codes<uint16_t> {
+    static __device__ __forceinline__ void load8(const uint16_t* p, uint32_t* u) {
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(p));
+        u[0] = b.x & 0xFFFFu; u[1] = b.x >> 16; u[2] = b.y & 0xFFFFu; u[3] = b.y >> 16;
+        u[4] = b.z & 0xFFFFu; u[5] = b.z >> 16; u[6] = b.w & 0xFFFFu; u[7] = b.w >> 16;
+    }
+    static __device__ __forceinline__ void load4(const uint16_t* p, uint32_t* u) {
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
+        u[0] = b.x & 0xFFFFu; u[1] = b.x >> 16; u[2] = b.y & 0xFFFFu; u[3] = b.y >> 16;
+    }
+    static __device__ __forceinline__ uint32_t bin(uint32_t u) { return u >> 8; }
+    static __device__ __forceinline__ uint32_t index(uint32_t u) { return (u * 65281u) >> 24; }
+};
+template <> struct Codes<int16_t> {
+    static __device__ __forceinline__ void load8(const int16_t* p, uint32_t* u) {
+        uint4 b = __ldg(reinterpret_cast<const uint4*>(p));
+        b.x ^= 0x80008000u; b.y ^= 0x80008000u; b.z ^= 0x80008000u; b.w ^= 0x80008000u;   // v + 32768
+        u[0] = b.x & 0xFFFFu; u[1] = b.x >> 16; u[2] = b.y & 0xFFFFu; u[3] = b.y >> 16;
+        u[4] = b.z & 0xFFFFu; u[5] = b.z >> 16; u[6] = b.w & 0xFFFFu; u[7] = b.w >> 16;
+    }
+    static __device__ __forceinline__ void load4(const int16_t* p, uint32_t* u) {
+        uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
+        b.x ^= 0x80008000u; b.y ^= 0x80008000u;
+        u[0] = b.x & 0xFFFFu; u[1] = b.x >> 16; u[2] = b.y & 0xFFFFu; u[3] = b.y >> 16;
+    }
+    static __device__ __forceinline__ uint32_t bin(uint32_t u) { return u >> 8; }
+    static __device__ __forceinline__ uint32_t index(uint32_t u) { return (u * 65281u) >> 24; }
+};
+template <> struct Codes<uint8_t> {
+    static __device__ __forceinline__ void load8(const uint8_t* p, uint32_t* u) {
+        const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
+        u[0] = b.x & 0xFFu; u[1] = (b.x >> 8) & 0xFFu; u[2] = (b.x >> 16) & 0xFFu; u[3] = b.x >> 24;
+        u[4] = b.y & 0xFFu; u[5] = (b.y >> 8) & 0xFFu; u[6] = (b.y >> 16) & 0xFFu; u[7] = b.y >> 24;
+    }
+    static __device__ __forceinline__ void load4(const uint8_t* p, uint32_t* u) {
+        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(p));
+        u[0] = b & 0xFFu; u[1] = (b >> 8) & 0xFFu; u[2] = (b >> 16) & 0xFFu; u[3] = b >> 24;
+    }
+    static __device__ __forceinline__ uint32_t bin(uint32_t u) { return u; }
+    static __device__ __forceinline__ uint32_t index(uint32_t u) { return u; }
+};
+template <> struct Codes<float> {   // never used (IDX kernels are integer-only); keeps the dispatch macros compiling
+    static __device__ __forceinline__ void load8(const float*, uint32_t* u) { for (int k = 0; k < 8; ++k) u[k] = 0; }
+    static __device__ __forceinline__ void load4(const float*, uint32_t* u) { for (int k = 0; k < 4; ++k) u[k] = 0; }
+    static __device__ __forceinline__ uint32_t bin(uint32_t) { return 0; }
+    static __device__ __forceinline__ uint32_t index(uint32_t) { return 0; }
+};
+
 // ---------------------------------------------------------------- host side
 inline bool default_range_c(int dtype, float lo, float hi) {
     switch (dtype) {
@@ -147,6 +204,37 @@ inline int range_mode(int dtype, float lo, float hi, WinCvt* cv) {
     if (!ok) return -1;
     *cv = c;
     return 1;
+}
+
+// Exhaustive host check of the integer rules above against the float formulas of the kernels / the oracle
+// (IEEE float ops on the host are the ops the kernels reproduce).  Evaluated once.
+inline bool int_rules_ok(int dtype) {
+    static const bool ok16 = [] {
+        for (int u = 0; u < 65536; ++u) {
+            volatile float x = (float)u / 65535.0f;
+            volatile float b = x * 256.0f, i = x * 255.0f;
+            volatile float g = (float)i / 255.0f;
+            volatile float eb = g * 256.0f;
+            int bin = (int)std::floor((float)b); if (bin > 255) bin = 255;
+            int ebin = (int)std::floor((float)eb); if (ebin > 255) ebin = 255;
+            const int idx = (int)std::floor((float)i);
+            if (bin != (u >> 8) || ebin != (u >> 8) || idx != (int)(((unsigned)u * 65281u) >> 24)) return false;
+        }
+        return true;
+    }();
+    static const bool ok8 = [] {
+        for (int u = 0; u < 256; ++u) {
+            volatile float x = (float)u / 255.0f;
+            volatile float b = x * 256.0f, i = x * 255.0f;
+            volatile float g = (float)i / 255.0f;
+            volatile float eb = g * 256.0f;
+            int bin = (int)std::floor((float)b); if (bin > 255) bin = 255;
+            int ebin = (int)std::floor((float)eb); if (ebin > 255) ebin = 255;
+            if (bin != u || ebin != u || (int)std::floor((float)i) != u) return false;
+        }
+        return true;
+    }();
+    return dtype == MIE_U8 ? ok8 : (dtype == MIE_U16 || dtype == MIE_I16) ? ok16 : false;
 }
 
 }  // namespace mie

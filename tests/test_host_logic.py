@@ -171,3 +171,24 @@ def test_median27_selection_network():
         s = [np.sort(v[9 * k:9 * k + 9], axis=0) for k in range(3)]
         got = _select27_sorted(list(s[0]), list(s[1]), list(s[2]))
         assert np.array_equal(got, np.sort(v, axis=0)[13])
+
+
+# ---------------------------------------------------------------------------- integer bin / index rules
+def test_integer_bin_and_index_rules_for_default_ranges():
+    """csrc/window.cuh (Codes<T>): for default-range integer pixels the kornia histogram bin floor(x*256), the
+    lookup index trunc(x*255) and equalize's bin floor(RN(RN(x*255)/255)*256) are integer functions of the code:
+    16-bit: bin = u >> 8, index = u // 257 = (u * 65281) >> 24;  8-bit: bin = index = u.  Exhaustive check
+    against the float32 formulas (the library repeats it in C before the first launch)."""
+    f32 = np.float32
+    for bits, rng in ((16, 65535), (8, 255)):
+        u = np.arange(rng + 1, dtype=np.int64)
+        x = (u.astype(f32) / f32(rng)).astype(f32)
+        b = np.minimum(np.floor((x * f32(256)).astype(f32)), 255).astype(np.int64)
+        v = (x * f32(255)).astype(f32)
+        idx = np.floor(v).astype(np.int64)
+        eb = np.minimum(np.floor(((v / f32(255)).astype(f32) * f32(256)).astype(f32)), 255).astype(np.int64)
+        if bits == 16:
+            assert np.array_equal(b, u >> 8) and np.array_equal(eb, u >> 8)
+            assert np.array_equal(idx, u // 257) and np.array_equal(idx, (u * 65281) >> 24)
+        else:
+            assert np.array_equal(b, u) and np.array_equal(eb, u) and np.array_equal(idx, u)
