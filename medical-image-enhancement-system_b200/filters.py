@@ -197,6 +197,11 @@ def median(image: torch.Tensor, footprint=None, out=None, mode: str = "nearest",
     dst = out if out is not None else torch.empty_like(x)
     if out is not None and (out.shape != x.shape or out.dtype != x.dtype or not out.is_contiguous()):
         raise ValueError("out must be a contiguous tensor of the input's shape and dtype")
+    if out is not None and out.untyped_storage().data_ptr() == x.untyped_storage().data_ptr():
+        lo, hi = max(out.data_ptr(), x.data_ptr()), min(out.data_ptr() + out.numel() * out.element_size(),
+                                                        x.data_ptr() + x.numel() * x.element_size())
+        if lo < hi:
+            raise ValueError("out must not overlap the input: the median kernels read neighbours they have not written yet")
     with torch.cuda.device(x.device):
         if x.dim() == 2:
             h, w = x.shape
