@@ -18,7 +18,7 @@ import torch
 
 from .chain import ChainConfig, chain_workspace_bytes, enhance_chain
 
-__all__ = ["HostSlicePipeline", "pin", "enhance_chain_host"]
+__all__ = ["HostSlicePipeline", "HostVolumePipeline", "pin", "enhance_chain_host", "median3d_clahe_host"]
 
 
 def pin(t: torch.Tensor) -> torch.Tensor:
@@ -136,3 +136,88 @@ def enhance_chain_host(src: torch.Tensor, config: ChainConfig = ChainConfig(), *
         out = torch.empty_like(src).pin_memory()
     pipe = HostSlicePipeline(device, src.shape[-2:], src.dtype, chunk=min(chunk, max(int(src.shape[0]), 1)), config=config)
     return pipe.run(src, out)
+
+
+class HostVolumePipeline:
+    """BASELINE.json config 3 for a HOST-resident volume: (D, H, W) int16 / uint16 / uint8 planes are streamed
+    through the GPU in z-chunks — 3x3x3 median (skimage.filters.median semantics) followed by per-slice CLAHE
+    — with the upload of chunk k+1, the kernels of chunk k and the download of chunk k-1 overlapping on three
+    streams.  A chunk is uploaded together with its two neighbouring planes, which serve as the median's z-halo
+    exactly like the planes a neighbouring rank would send (volume.py), so the result is bit-identical to
+    processing the whole volume on the device.
+
+        pipe = HostVolumePipeline("cuda:0", (512, 512), torch.int16, chunk=64)
+        pipe.run(vol_host_pinned, out_host_pinned)
+    """
+
+    def __init__(self, device, plane_shape, dtype, chunk: int = 64, depth: int = 3, clip_limit: float = 2.0,
+                 grid_size: tuple = (8, 8), mode: str = "nearest", value_range=None):
+        self.device = torch.device(device)
+        self.h, self.w = int(plane_shape[-2]), int(plane_shape[-1])
+        self.chunk, self.depth = int(chunk), int(depth)
+        self.clip_limit, self.grid_size, self.mode, self.value_range = float(clip_limit), tuple(grid_size), mode, value_range
+        with torch.cuda.device(self.device):
+            self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream() for _ in range(3))
+            # chunk planes plus one halo plane on either side
+            self.x = [torch.empty((self.chunk + 2, self.h, self.w), dtype=dtype, device=self.device) for _ in range(depth)]
+            self.y = [None] * depth
+            self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_comp = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+
+    def run(self, src: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+        """src, dst: host tensors (D, H, W), ideally pinned (see pin()).  Returns dst once it is complete."""
+        from .enhance import equalize_clahe
+        from .filters import median
+
+        if src.is_cuda or dst.is_cuda:
+            raise ValueError("HostVolumePipeline takes host tensors")
+        if src.dim() != 3 or src.shape != dst.shape or src.shape[1:] != (self.h, self.w):
+            raise ValueError("expected (D, H, W) volumes of the pipeline's plane shape")
+        d = int(src.shape[0])
+        caller = torch.cuda.current_stream(self.device)
+        for st in (self.s_in, self.s_comp, self.s_out):
+            st.wait_stream(caller)
+        used = [False] * self.depth
+        for i, z0 in enumerate(range(0, d, self.chunk)):
+            z1 = min(z0 + self.chunk, d)
+            m, k = z1 - z0, i % self.depth
+            a, b = max(z0 - 1, 0), min(z1 + 1, d)          # planes uploaded: the chunk and its z-neighbours
+            off = z0 - a                                   # 1 when a lower halo plane is present
+            with torch.cuda.stream(self.s_in):
+                if used[k]:
+                    self.s_in.wait_event(self.ev_comp[k])
+                self.x[k][:b - a].copy_(src[a:b], non_blocking=True)
+                self.ev_in[k].record(self.s_in)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(self.ev_in[k])
+                if used[k]:
+                    self.s_comp.wait_event(self.ev_out[k])
+                buf = self.x[k]
+                med = median(buf[off:off + m], mode=self.mode, halo_lo=buf[0] if off else None,
+                             halo_hi=buf[off + m] if z1 < d else None)
+                self.y[k] = equalize_clahe(med.unsqueeze(1), self.clip_limit, self.grid_size,
+                                           value_range=self.value_range).squeeze(1)
+                self.y[k].record_stream(self.s_out)
+                self.ev_comp[k].record(self.s_comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_comp[k])
+                dst[z0:z1].copy_(self.y[k], non_blocking=True)
+                self.ev_out[k].record(self.s_out)
+            used[k] = True
+        self.s_out.synchronize()
+        self.s_comp.synchronize()
+        return dst
+
+
+def median3d_clahe_host(vol: torch.Tensor, clip_limit: float = 2.0, grid_size: tuple = (8, 8), *, out: torch.Tensor = None,
+                        device="cuda", chunk: int = 64, mode: str = "nearest", value_range=None) -> torch.Tensor:
+    """One-call convenience: 3x3x3 median + per-slice CLAHE of a host-resident (D, H, W) volume on `device`."""
+    if vol.is_cuda:
+        raise ValueError("median3d_clahe_host takes host tensors; use median3d_clahe_slab for device tensors")
+    vol = pin(vol)
+    if out is None:
+        out = torch.empty_like(vol).pin_memory()
+    pipe = HostVolumePipeline(device, vol.shape[-2:], vol.dtype, chunk=min(chunk, max(int(vol.shape[0]), 1)),
+                              clip_limit=clip_limit, grid_size=grid_size, mode=mode, value_range=value_range)
+    return pipe.run(vol, out)
