@@ -188,8 +188,8 @@ int mie_median3d(const void* src, void* dst, int dtype, int d, int h, int w,
  * Replaces kornia.filters.bilateral_blur(input, kernel_size, sigma_color,
  * sigma_space, border_type, color_distance_type) for single-channel planes
  * (SURVEY.md §8(a) A7).  wspace: ky*kx HOST floats (outer product of the
- * normalised 1-D Gaussians).  Weight = wspace * mie_exp(coef * d*d),
- * coef = fp32(-0.5 / sigma_color^2), accumulated in row-major tap order
+ * normalised 1-D Gaussians).  Weight = wspace * 2^(c2 * (d*d)) with the fixed-sequence exp2 of
+ * csrc/bilateral.cu:mie_exp2n, c2 = fp32(-0.5 log2(e) / sigma_color^2), accumulated in row-major tap order
  * (num = fma(w, v, num); den += w), out = num / den.  ky, kx odd <= 15.           */
 int mie_bilateral(const void* src, void* dst, int src_dtype, int dst_dtype,
                   int64_t n, int h, int w,

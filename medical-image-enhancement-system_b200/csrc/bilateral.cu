@@ -3,11 +3,11 @@
 // §8(a) A7, Appendix B2):  w = space[dy,dx] * exp(-0.5/sigma_color^2 * (v-c)^2),
 // out = sum(w*v) / sum(w), full ky x kx window, padding by border_type.
 //
-// The colour weight uses mie_exp(): range reduction by ln2 (two-constant
-// Cody-Waite) and a degree-6 polynomial, all explicit fp32 fma — the same
-// sequence as oracle/mie_oracle.c:mie_exp, so the result is reproducible bit for
-// bit and stays within 2 ulp of exp().  This op is FMA-pipe bound (81 taps x ~20
-// instructions), not HBM bound.
+// The colour weight is 2^t with t = c2 * d^2, c2 = fp32(-0.5 log2(e) / sigma_color^2), evaluated by
+// mie_exp2n(): clamp, n = rint(t) by the 1.5 * 2^23 trick (no FRND / F2I), f = t - n, a degree-5
+// polynomial for 2^f (max rel err 1.7e-7) and an exponent-field add — the same sequence as
+// oracle/mie_oracle.c:mie_exp2n, so the result is reproducible bit for bit.  This op is FMA-pipe bound
+// (81 taps x 14 FMA-pipe operations), not HBM bound.
 #include <cstdlib>
 
 #include "chain_fast.cuh"
@@ -22,23 +22,17 @@ struct SpaceW {
     float w[kBilMaxK * kBilMaxK];
 };
 
-// Same values as oracle/mie_oracle.c:mie_exp, bit for bit, without the conversion-pipe instructions
-// (FRND / F2I run at 16 lanes per clock): rint(t) = (t + 1.5*2^23) - 1.5*2^23 for |t| < 2^22, the integer
-// n sits in the low mantissa bits of the intermediate sum, and p * 2^n (exact: p in [0.7, 1.42] and
-// n >= -126 only when p > 1.39, so no subnormals) is an exponent-field addition on the integer pipe.
-__device__ __forceinline__ float mie_exp(float a) {
-    a = fminf(fmaxf(a, -87.0f), 88.0f);
-    const float u = __fadd_rn(__fmul_rn(a, 1.44269504088896341f), 12582912.0f);
+__device__ __forceinline__ float mie_exp2n(float t) {
+    t = fmaxf(t, -125.0f);
+    const float u = __fadd_rn(t, 12582912.0f);
     const float n = __fsub_rn(u, 12582912.0f);
-    float r = __fmaf_rn(n, -0.693145751953125f, a);
-    r = __fmaf_rn(n, -1.42860682030941723e-6f, r);
-    float p = 1.3888889225e-3f;
-    p = __fmaf_rn(p, r, 8.3333337680e-3f);
-    p = __fmaf_rn(p, r, 4.1666667908e-2f);
-    p = __fmaf_rn(p, r, 1.6666667163e-1f);
-    p = __fmaf_rn(p, r, 0.5f);
-    p = __fmaf_rn(p, r, 1.0f);
-    p = __fmaf_rn(p, r, 1.0f);
+    const float f = __fsub_rn(t, n);
+    float p = 0.0013264685403555632f;
+    p = __fmaf_rn(p, f, 0.009671504609286785f);
+    p = __fmaf_rn(p, f, 0.05550733953714371f);
+    p = __fmaf_rn(p, f, 0.24022242426872253f);
+    p = __fmaf_rn(p, f, 0.6931470036506653f);
+    p = __fmaf_rn(p, f, 1.0f);
     return __uint_as_float(__float_as_uint(p) + (__float_as_uint(u) << 23));
 }
 
@@ -77,7 +71,7 @@ bilateral_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t s
             for (int k = 0; k < 4; ++k) {
                 const float v = smem[(ly0 + 8 * k + dy) * pitch + lx + dx];
                 const float dv = __fsub_rn(v, ctr[k]);
-                const float wgt = __fmul_rn(ws, mie_exp(__fmul_rn(coef, __fmul_rn(dv, dv))));
+                const float wgt = __fmul_rn(ws, mie_exp2n(__fmul_rn(coef, __fmul_rn(dv, dv))));
                 num[k] = __fmaf_rn(wgt, v, num[k]);
                 den[k] = __fadd_rn(den[k], wgt);
             }
@@ -97,8 +91,8 @@ bilateral_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t s
 // four pixels of a thread as two f32x2 pairs: every arithmetic step of the weight (difference, square,
 // scale, the exp range reduction and polynomial, the spatial weight, both accumulations) is ONE packed
 // instruction per pair — same per-lane IEEE rounding, so the result is bit-identical — and the window
-// loops are unrolled at compile time.  Per pixel-tap: 6.5 packed + 2 scalar FMA-pipe instructions, 1 LDS,
-// 1 FMNMX, 1 exponent-field add: ~12 issue slots instead of 27; the FMA pipe becomes the limiter.
+// loops are unrolled at compile time.  Per pixel-tap: 6.5 packed + 1 scalar FMA-pipe instructions, 1 LDS,
+// 1 FMNMX, 1 exponent-field add: ~10.5 issue slots instead of 27; the FMA pipe becomes the limiter.
 __device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
     f32x2 d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -112,40 +106,37 @@ __device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
 __device__ __forceinline__ f32x2 f2_dup(float v) { return f2_pack(v, v); }
 
 struct ExpConsts {
-    f32x2 magic, ln2hi, ln2lo, c6, c5, c4, c3, c2, one;
+    f32x2 magic, c5, c4, c3, c2, c1, one;
 };
 __device__ __forceinline__ ExpConsts exp_consts() {
     ExpConsts k;
     k.magic = f2_dup(12582912.0f);
-    k.ln2hi = f2_dup(-0.693145751953125f); k.ln2lo = f2_dup(-1.42860682030941723e-6f);
-    k.c6 = f2_dup(1.3888889225e-3f); k.c5 = f2_dup(8.3333337680e-3f); k.c4 = f2_dup(4.1666667908e-2f);
-    k.c3 = f2_dup(1.6666667163e-1f); k.c2 = f2_dup(0.5f); k.one = f2_dup(1.0f);
+    k.c5 = f2_dup(0.0013264685403555632f); k.c4 = f2_dup(0.009671504609286785f);
+    k.c3 = f2_dup(0.05550733953714371f); k.c2 = f2_dup(0.24022242426872253f);
+    k.c1 = f2_dup(0.6931470036506653f); k.one = f2_dup(1.0f);
     return k;
 }
 // ptxas (CUDA 12.9) contracts mul.rn.f32x2 + add.rn.f32x2 — also __fadd2_rn(__fmul2_rn(..)), also with
 // -fmad=false, also when the product is written fma(a, b, -0) — into one FFMA2, i.e. one rounding instead
-// of two, which the scalar __fmul_rn / __fadd_rn sequence of mie_exp never does.  So the two products that
-// feed an addition (a * log2e before the magic add, ws * exp before den + w) are SCALAR multiplies on the
-// halves, which are unpacked there anyway (clamp / exponent-field add); everything else is packed.
+// of two, which the scalar __fmul_rn / __fadd_rn sequence of the oracle never does.  Here the packed product
+// c2 * d^2 passes through the scalar clamp before the magic add, and the product that feeds den + w
+// (ws * 2^t) is a SCALAR multiply on the halves, which are unpacked there anyway (exponent-field add).
 //
-// ws * mie_exp(a) on both halves for a NON-POSITIVE (or NaN) argument a = coef * d^2: after max(a, -87)
-// (which also replaces NaN) the scalar function's upper clamp min(a, 88) is the identity and is skipped.
-__device__ __forceinline__ f32x2 weight_x2(f32x2 a, float ws, const ExpConsts& k) {
-    float a0, a1;
-    f2_unpack(a, a0, a1);
-    a0 = fmaxf(a0, -87.0f);
-    a1 = fmaxf(a1, -87.0f);
-    a = f2_pack(a0, a1);
-    const f32x2 u = f2_add(f2_pack(__fmul_rn(a0, 1.44269504088896341f), __fmul_rn(a1, 1.44269504088896341f)), k.magic);
+// ws * mie_exp2n(t) on both halves of t = c2 * d^2.
+__device__ __forceinline__ f32x2 weight_x2(f32x2 t, float ws, const ExpConsts& k) {
+    float t0, t1;
+    f2_unpack(t, t0, t1);
+    t0 = fmaxf(t0, -125.0f);
+    t1 = fmaxf(t1, -125.0f);
+    t = f2_pack(t0, t1);
+    const f32x2 u = f2_add(t, k.magic);
     const f32x2 n = f2_sub(u, k.magic);
-    f32x2 r = f2_fma(n, k.ln2hi, a);
-    r = f2_fma(n, k.ln2lo, r);
-    f32x2 p = f2_fma(k.c6, r, k.c5);
-    p = f2_fma(p, r, k.c4);
-    p = f2_fma(p, r, k.c3);
-    p = f2_fma(p, r, k.c2);
-    p = f2_fma(p, r, k.one);
-    p = f2_fma(p, r, k.one);
+    const f32x2 f = f2_sub(t, n);
+    f32x2 p = f2_fma(k.c5, f, k.c4);
+    p = f2_fma(p, f, k.c3);
+    p = f2_fma(p, f, k.c2);
+    p = f2_fma(p, f, k.c1);
+    p = f2_fma(p, f, k.one);
     float p0, p1, u0, u1;
     f2_unpack(p, p0, p1);
     f2_unpack(u, u0, u1);
@@ -246,7 +237,7 @@ int bilateral_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h,
     if (n == 0) return MIE_OK;
     SpaceW sw;
     for (int i = 0; i < kBilMaxK * kBilMaxK; ++i) sw.w[i] = i < ky * kx ? wspace[i] : 0.0f;
-    const float coef = (float)(-0.5 / ((double)sigma_color * (double)sigma_color));
+    const float coef = (float)(-0.5 * 1.4426950408889634 / ((double)sigma_color * (double)sigma_color));   // log2 domain
     const int tiles_x = ceil_div(w, 32), tiles_y = ceil_div(h, 32);
     const int64_t blocks = n * tiles_x * tiles_y;
     if (blocks > 2147483647LL) return MIE_E_SHAPE;

@@ -60,6 +60,7 @@ class _Sig:
     orc_median2d = ([_p, _p, _i64, _i, _i, _i, _i, _i], _i)
     orc_median3d = ([_p, _p, _i, _i, _i, _p, _p, _i], _i)
     orc_exp = ([_p, _p, _i64], None)
+    orc_exp2n = ([_p, _p, _i64], None)
     orc_bilateral = ([_p, _p, _i64, _i, _i, _p, _i, _i, _f, _i], _i)
     orc_equalize = ([_p, _p, _i64, _i, _i], _i)
 
@@ -338,6 +339,14 @@ def median3d(vol, mode="nearest", halo_lo=None, halo_hi=None) -> np.ndarray:
     _check(lib().orc_median3d(_ptr(x), _ptr(out), d, h, w, None if lo is None else _ptr(lo),
                               None if hi is None else _ptr(hi), border))
     return out.astype(vol.dtype)
+
+
+def mie_exp2n(t) -> np.ndarray:
+    """2^t for t <= 0 as the bilateral filter evaluates it (oracle/mie_oracle.c:mie_exp2n)."""
+    t = np.ascontiguousarray(t, np.float32)
+    out = np.empty_like(t)
+    lib().orc_exp2n(_ptr(t), _ptr(out), t.size)
+    return out
 
 
 def mie_exp(a) -> np.ndarray:

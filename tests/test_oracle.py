@@ -239,6 +239,19 @@ def test_equalize_oracle_against_torchvision_uint8_and_twin():
 
 
 # ---------------------------------------------------------------------------- A7 bilateral
+def test_mie_exp2n_accuracy():
+    """The base-2 exponential of the bilateral colour weight: max rel err 1.7e-7 on [-125, 0], exact at 0,
+    clamped below -125, NaN -> 2^-125 (never a NaN weight)."""
+    import oracle as O
+
+    t = np.linspace(-125.0, 0.0, 500001).astype(np.float32)
+    got = O.mie_exp2n(t).astype(np.float64)
+    assert np.abs(got / np.exp2(t.astype(np.float64)) - 1.0).max() < 2.5e-7
+    assert O.mie_exp2n(np.zeros(1, np.float32))[0] == 1.0
+    lo = O.mie_exp2n(np.array([-125.0, -126.0, -1e30, -np.inf, np.nan], np.float32))
+    assert np.all(lo == np.float32(2.0 ** -125))
+
+
 def test_mie_exp_accuracy():
     a = -np.abs(np.random.default_rng(8).normal(0, 8, 200000)).astype(np.float32)
     a = np.concatenate([a, np.array([0.0, -1e-8, -87.0, -100.0, -0.5], np.float32)])
