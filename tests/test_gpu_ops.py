@@ -308,3 +308,35 @@ def test_nlm_argument_errors(dev):
         M.denoise_nl_means(x, patch_size=11)
     with pytest.raises((ValueError, RuntimeError)):
         M.denoise_nl_means(torch.zeros((1, 1, 12, 12), device=dev))      # padding would exceed the image
+
+
+# ---------------------------------------------------------------------------- edge cases of the newer entry points
+def test_edge_cases_metrics_windows_host_volume(dev):
+    import mie_b200 as M
+    from mie_b200 import skimage_compat as S
+
+    # single-pixel-high / single-plane inputs
+    a = gpu(rand(np.uint16, (1, 1, 1, 64), 1), dev)
+    assert M.mse(a, a) == 0.0 and M.psnr(a, a) == float("inf")
+    with pytest.raises(ValueError):
+        M.ssim(a, a)                                     # 11x11 window does not fit a 1x64 image
+    assert M.ssim(a, a, ws=1)[0] == pytest.approx(1.0, abs=1e-12)
+    # value_range windows that the tuned kernels cannot take (non-integer bounds) still work (generic kernels)
+    x = gpu(rand(np.int16, (2, 1, 64, 64), 2), dev)
+    import oracle as O
+    vr = (-1000.5, 2999.25)
+    ref = O.from01(O.equalize_clahe(O.to01(cpu(x), vr), 2.0, (2, 2)), np.int16, vr)
+    assert np.array_equal(cpu(M.equalize_clahe(x, 2.0, (2, 2), value_range=vr)), ref)
+    ref = O.from01(O.equalize(O.to01(cpu(x), vr)), np.int16, vr)
+    assert np.array_equal(cpu(M.equalize(x, value_range=vr)), ref)
+    # host volume of a single plane, and of fewer planes than a chunk
+    for d in (1, 2, 5):
+        vol = rand(np.int16, (d, 64, 64), 3)
+        got = M.median3d_clahe_host(torch.from_numpy(vol), 2.0, (2, 2), device=dev, chunk=4)
+        assert np.array_equal(got.numpy(), cpu(M.median3d_clahe_slab(gpu(vol, dev), 2.0, (2, 2)))), d
+    # skimage signatures on (H, W) input keep the rank
+    img = gpu(rand(np.uint16, (40, 56), 4), dev)
+    assert S.gaussian(img, 1.0).shape == (40, 56) and S.unsharp_mask(img, 1.0, 1.0).shape == (40, 56)
+    # median(out=) must not alias the input
+    with pytest.raises(ValueError):
+        M.median(img, out=img)
