@@ -575,12 +575,150 @@ median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
     }
 }
 
+// ---------------------------------------------------------------- 2-D 5x5, 8 / 16-bit pixels, marching rows
+// Same schedule as the 3x3 kernel (8 columns per lane, neighbours by shuffle, five rows in registers).
+// Per row the five vertical samples of every packed word are sorted once (9 compare-exchanges, shared by
+// the five windows that contain the column; the x-1 / x+1 shifted columns are byte permutes of the sorted
+// words).  The window is then a 5x5 matrix with sorted columns; sorting its ROWS keeps the columns sorted,
+// so element (r, c) has (r+1)(c+1)-1 samples below and (5-r)(5-c)-1 above: 13 or more on either side rules
+// it out.  Six entries drop out on each side and the median of 25 is the median (rank 6) of the remaining 13
+// — five sorted runs of 2, 3, 3, 3, 2 — found by three small merges (3 + 6 + 8 compare-exchanges) and
+// rank_r(W u Y) = min(w_r, min_{i+j=r-1} max(w_i, y_j)).  Unused halves of the row sorts are dead code.
+// Verified on 0/1 inputs and random ties: tests/test_host_logic.py::test_median25_selection_network.
+template <typename P>
+__device__ __forceinline__ void sort5(P& a, P& b, P& c, P& d, P& e) {
+    cswap(a, d); cswap(b, e); cswap(a, c); cswap(b, d); cswap(a, b); cswap(c, e); cswap(b, c); cswap(d, e); cswap(c, d);
+}
+// col[c][r]: column c of the window (c = 0..4), vertical rank r (0..4)
+template <typename P>
+__device__ __forceinline__ P select25_sorted_columns(const P (&A)[5], const P (&B)[5], const P (&C)[5],
+                                                     const P (&D)[5], const P (&E)[5]) {
+    P R[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        R[r][0] = A[r]; R[r][1] = B[r]; R[r][2] = C[r]; R[r][3] = D[r]; R[r][4] = E[r];
+        sort5(R[r][0], R[r][1], R[r][2], R[r][3], R[r][4]);
+    }
+    // candidates: R0[3..4], R1[2..4], R2[1..3], R3[0..2], R4[0..1]
+    P xz[4] = {R[0][3], R[0][4], R[4][0], R[4][1]};
+    cswap(xz[0], xz[2]); cswap(xz[1], xz[3]); cswap(xz[1], xz[2]);                        // merge 2 + 2
+    P y[6] = {R[1][2], R[1][3], R[1][4], R[3][0], R[3][1], R[3][2]};
+    cswap(y[0], y[3]); cswap(y[1], y[4]); cswap(y[1], y[3]); cswap(y[2], y[5]); cswap(y[2], y[3]); cswap(y[3], y[4]);   // 3 + 3
+    P w[7] = {xz[0], xz[1], xz[2], xz[3], R[2][1], R[2][2], R[2][3]};
+    cswap(w[0], w[4]); cswap(w[1], w[4]); cswap(w[1], w[5]); cswap(w[2], w[5]); cswap(w[3], w[6]); cswap(w[3], w[4]);
+    cswap(w[2], w[3]); cswap(w[4], w[5]);                                                 // merge 4 + 3
+    P m = w[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) m = pmin(m, pmax(w[i], y[5 - i]));
+    return m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+median5x5_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                        int64_t dsh, int64_t nplanes, int h, int w, int strips, int bands, int rows_per_band,
+                        int border) {
+    using P = typename PackedOf<T>::type;
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int strip = (int)(wg % strips), band = (int)((wg / strips) % bands);
+    const int64_t n = wg / ((int64_t)strips * bands);
+    if (n >= nplanes) return;                      // warp-uniform
+    const int x0 = strip * 256 + lane * 8;
+    const bool active = x0 < w;
+    const int y0 = band * rows_per_band, y1 = min(y0 + rows_per_band, h);
+    const T* plane = src + n * ssn;
+    T* oplane = dst + n * dsn;
+
+    // six packed words of image row y: [pixels x0-2, x0-1 | four own pairs | pixels x0+8, x0+9]
+    auto load_row = [&](int y, P* r) {
+        const int sy = border_index(y, h, border);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t left = 0u, right = 0u;
+        if (sy >= 0) {                              // uniform
+            const T* row = plane + (int64_t)sy * ssh;
+            if (active) {
+                if constexpr (sizeof(T) == 1) {
+                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + x0));
+                    v.x = __byte_perm(raw.x, 0u, 0x4140); v.y = __byte_perm(raw.x, 0u, 0x4342);
+                    v.z = __byte_perm(raw.y, 0u, 0x4140); v.w = __byte_perm(raw.y, 0u, 0x4342);
+                } else {
+                    v = __ldg(reinterpret_cast<const uint4*>(row + x0));
+                }
+            }
+            left = __shfl_up_sync(0xffffffffu, v.w, 1);
+            right = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (active) {
+                if (x0 == 0) {                      // pixels -2 (low half), -1 (high half)
+                    left = border == MIE_BORDER_REFLECT ? __byte_perm(v.x, v.y, 0x3254)        // (px 2, px 1)
+                         : border == MIE_BORDER_SYMMETRIC ? __byte_perm(v.x, 0u, 0x1032)       // (px 1, px 0)
+                         : border == MIE_BORDER_REPLICATE ? __byte_perm(v.x, 0u, 0x1010) : 0u; // (px 0, px 0)
+                } else if (lane == 0) {
+                    if constexpr (sizeof(T) == 1)
+                        left = __byte_perm((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(row + x0 - 2)), 0u, 0x4140);
+                    else
+                        left = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
+                }
+                if (x0 + 8 == w) {                  // pixels w (low half), w + 1 (high half)
+                    right = border == MIE_BORDER_REFLECT ? __byte_perm(v.w, v.z, 0x7610)       // (px w-2, px w-3)
+                          : border == MIE_BORDER_SYMMETRIC ? __byte_perm(v.w, 0u, 0x1032)      // (px w-1, px w-2)
+                          : border == MIE_BORDER_REPLICATE ? __byte_perm(v.w, 0u, 0x3232) : 0u;// (px w-1, px w-1)
+                } else if (lane == 31) {
+                    if constexpr (sizeof(T) == 1)
+                        right = __byte_perm((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(row + x0 + 8)), 0u, 0x4140);
+                    else
+                        right = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
+                }
+            }
+        }
+        r[0].v = left; r[1].v = v.x; r[2].v = v.y; r[3].v = v.z; r[4].v = v.w; r[5].v = right;
+    };
+
+    P ring[5][6];
+    load_row(y0 - 2, ring[0]);
+    load_row(y0 - 1, ring[1]);
+    load_row(y0, ring[2]);
+    load_row(y0 + 1, ring[3]);
+    for (int yb = y0; yb < y1; yb += 5) {
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            const int y = yb + u;
+            if (y < y1) {                           // uniform
+                load_row(y + 2, ring[(u + 4) % 5]);
+                P s[6][5];                          // vertically sorted samples of every word
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) s[c][r] = ring[r][c];
+                    sort5(s[c][0], s[c][1], s[c][2], s[c][3], s[c][4]);
+                }
+                P bt[5][5];                         // bt[j] = words j, j+1 shifted by one pixel: (hi of j, lo of j+1)
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) bt[j][r].v = __byte_perm(s[j][r].v, s[j + 1][r].v, 0x5432);
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    o[k] = select25_sorted_columns(s[k], bt[k], s[k + 1], bt[k + 1], s[k + 2]).v;
+                if (active) {
+                    if constexpr (sizeof(T) == 1)
+                        *reinterpret_cast<uint2*>(oplane + (int64_t)y * dsh + x0) =
+                            make_uint2(__byte_perm(o[0], o[1], 0x6420), __byte_perm(o[2], o[3], 0x6420));
+                    else
+                        *reinterpret_cast<uint4*>(oplane + (int64_t)y * dsh + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+    }
+}
+
 // 0 = launched, < 0 = not applicable (caller falls back to the generic kernel), > 0 = CUDA error
 template <typename T>
 static int try_median3x3_packed(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
-                                int64_t dsn, int64_t dsh, int border, cudaStream_t st) {
+                                int64_t dsn, int64_t dsh, int border, cudaStream_t st, int k = 3) {
     static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
-    if (off || (w & 7) || h < 2) return -1;
+    if (off || (w & 7) || h < k - 1) return -1;
     constexpr int esz = (int)sizeof(T), al = 8 * esz;   // one 8-pixel vector per lane and row
     if (((uintptr_t)src % al) || ((ssn * esz) % al) || ((ssh * esz) % al)) return -1;
     if (((uintptr_t)dst % al) || ((dsn * esz) % al) || ((dsh * esz) % al)) return -1;
@@ -591,8 +729,12 @@ static int try_median3x3_packed(const void* src, void* dst, int64_t n, int h, in
     const int64_t warps = n * strips * bands;
     const int64_t blocks = (warps + 7) / 8;
     if (blocks > 2147483647LL) return MIE_E_SHAPE;
-    median3x3_packed_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)src, (T*)dst, ssn, ssh, dsn, dsh, n, h, w,
-                                                                strips, bands, rows, border);
+    if (k == 5)
+        median5x5_packed_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)src, (T*)dst, ssn, ssh, dsn, dsh, n, h, w,
+                                                                    strips, bands, rows, border);
+    else
+        median3x3_packed_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)src, (T*)dst, ssn, ssh, dsn, dsh, n, h, w,
+                                                                    strips, bands, rows, border);
     return check_launch();
 }
 
@@ -644,13 +786,13 @@ int mie_median2d(const void* src, void* dst, int dtype, int64_t n, int h, int w,
     if (ky <= 0 || kx <= 0 || !(ky & 1) || !(kx & 1)) return MIE_E_KERNEL;
     if (n == 0) return MIE_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (ky == 3 && kx == 3 && dtype != MIE_F32) {
+    if (ky == kx && (ky == 3 || ky == 5) && dtype != MIE_F32) {   // packed marching kernels (8 / 16-bit pixels)
         rc = dtype == MIE_U16 ? try_median3x3_packed<uint16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
-                                                               dst_stride_n, dst_stride_h, border, st)
+                                                               dst_stride_n, dst_stride_h, border, st, ky)
            : dtype == MIE_I16 ? try_median3x3_packed<int16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
-                                                              dst_stride_n, dst_stride_h, border, st)
+                                                              dst_stride_n, dst_stride_h, border, st, ky)
                               : try_median3x3_packed<uint8_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
-                                                              dst_stride_n, dst_stride_h, border, st);
+                                                              dst_stride_n, dst_stride_h, border, st, ky);
         if (rc >= 0) return rc;
     }
     MIE_DISPATCH_SRC(dtype, return dispatch_median2d<SrcT>(ky, kx, src, dst, n, h, w, src_stride_n, src_stride_h,

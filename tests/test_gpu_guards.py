@@ -62,10 +62,11 @@ def test_guards_median_equalize_clahe(dev, dtype):
         x = torch.from_numpy(_rand(dtype, (n, h, w), 1)).to(dev)
         # 2-D 3x3 median (packed marching kernel for 16-bit), every border rule
         for border in (0, 1, 2, 4):
-            g = Guarded(n * h * w * esz, dev)
-            _ffi.check(L.mie_median2d(x.data_ptr(), g.ptr, CODE[dtype], n, h, w, h * w, w, h * w, w, 3, 3, border,
-                                      _stream(dev)))
-            g.check(f"median2d {(n, h, w)} border {border}")
+            for k in (3, 5):
+                g = Guarded(n * h * w * esz, dev)
+                _ffi.check(L.mie_median2d(x.data_ptr(), g.ptr, CODE[dtype], n, h, w, h * w, w, h * w, w, k, k, border,
+                                          _stream(dev)))
+                g.check(f"median2d {k}x{k} {(n, h, w)} border {border}")
         # 3x3x3 median on the stack as a volume (direct kernel for even widths), both border rules
         for border in (0, 2):
             g = Guarded(n * h * w * esz, dev)

@@ -53,12 +53,16 @@ def test_median_blur_3x3_packed_kernel(dev, dtype):
     import mie_b200 as M
     import oracle as O
 
-    for shape in [(2, 1, 70, 48), (1, 1, 33, 512), (1, 2, 9, 264), (1, 1, 2, 8), (3, 1, 100, 1032), (1, 1, 67, 256)]:
+    for shape in [(2, 1, 70, 48), (1, 1, 33, 512), (1, 2, 9, 264), (1, 1, 2, 8), (3, 1, 100, 1032), (1, 1, 67, 256),
+                  (1, 1, 4, 8), (1, 1, 5, 16)]:
         x = rand(dtype, shape, 5)
         x[..., : shape[-2] // 2, :] //= (64 if dtype != np.uint8 else 8)  # many ties
-        for border in ("constant", "replicate", "reflect"):
-            got = cpu(M.median_blur(gpu(x, dev), 3, border_type=border))
-            assert np.array_equal(got, O.median_blur(x, 3, border)), (shape, border)
+        for k in (3, 5):   # both packed marching kernels
+            for border in ("constant", "replicate", "reflect", "symmetric"):
+                if border == "reflect" and k // 2 >= min(shape[-2:]):
+                    continue
+                got = cpu(M.median_blur(gpu(x, dev), k, border_type=border))
+                assert np.array_equal(got, O.median_blur(x, k, border)), (shape, k, border)
     # config-2 sized batch: first / last slices against the oracle, all slices against scipy on a sample
     from mie_b200 import synthetic
 
@@ -66,6 +70,9 @@ def test_median_blur_3x3_packed_kernel(dev, dtype):
     got = cpu(M.median_blur(gpu(x, dev), 3))
     for i in (0, 1, 127, 255):
         assert np.array_equal(got[i], O.median_blur(x[i:i + 1], 3, "constant")[0]), i
+    got5 = cpu(M.median_blur(gpu(x, dev), 5))
+    for i in (0, 200):
+        assert np.array_equal(got5[i], O.median_blur(x[i:i + 1], 5, "constant")[0]), i
 
 
 def test_median_blur_matches_scipy_and_cv2(dev):

@@ -192,3 +192,35 @@ def test_integer_bin_and_index_rules_for_default_ranges():
             assert np.array_equal(idx, u // 257) and np.array_equal(idx, (u * 65281) >> 24)
         else:
             assert np.array_equal(b, u) and np.array_equal(eb, u) and np.array_equal(idx, u)
+
+
+SORT5 = [(0, 3), (1, 4), (0, 2), (1, 3), (0, 1), (2, 4), (1, 2), (3, 4), (2, 3)]
+M22 = [(0, 2), (1, 3), (1, 2)]
+M33 = [(0, 3), (1, 4), (1, 3), (2, 5), (2, 3), (3, 4)]
+M43 = [(0, 4), (1, 4), (1, 5), (2, 5), (3, 6), (3, 4), (2, 3), (4, 5)]
+
+
+def _net(v, net):
+    v = list(v)
+    for i, j in net:
+        _cs(v, i, j)
+    return v
+
+
+def test_median25_selection_network():
+    """Python twin of select25_sorted_columns (csrc/median.cu): rank 12 of 25 from five vertically sorted
+    columns — row sorts, pruning to 13 candidates, three merges, rank_6(W u Y)."""
+    bits = ((np.arange(32)[:, None] >> np.arange(5)[None, :]) & 1).T.copy()
+    assert np.array_equal(np.stack(_net([bits[i].copy() for i in range(5)], SORT5)), np.sort(bits, axis=0))
+    rng = np.random.default_rng(1)
+    for hi in (2, 3, 7, 1000):
+        v = rng.integers(0, hi, (25, 20000))
+        cols = [np.sort(v[5 * c:5 * c + 5], axis=0) for c in range(5)]          # cols[c][r]
+        R = [_net([cols[c][r] for c in range(5)], SORT5) for r in range(5)]    # rows sorted horizontally
+        xz = _net([R[0][3], R[0][4], R[4][0], R[4][1]], M22)
+        y = _net([R[1][2], R[1][3], R[1][4], R[3][0], R[3][1], R[3][2]], M33)
+        w = _net(xz + [R[2][1], R[2][2], R[2][3]], M43)
+        m = w[6]
+        for i in range(6):
+            m = np.minimum(m, np.maximum(w[i], y[5 - i]))
+        assert np.array_equal(m, np.sort(v, axis=0)[12]), hi
