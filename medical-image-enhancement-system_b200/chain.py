@@ -16,7 +16,7 @@ from ._ffi import DTYPE_CODE, as_planes, check, lib, require_cuda, stream_ptr, v
 from .enhance import _check_clahe_args
 from .filters import _border, _check_kernel, _pair_float, _pair_int, get_gaussian_kernel1d
 
-__all__ = ["ChainConfig", "ChainPlan", "enhance_chain", "chain_workspace_bytes"]
+__all__ = ["ChainConfig", "ChainPlan", "ChainRing", "enhance_chain", "chain_workspace_bytes"]
 
 
 @dataclass(frozen=True)
@@ -128,3 +128,48 @@ class ChainPlan:
         else:
             self._direct()
         return self.out
+
+
+class ChainRing:
+    """Steady-state throughput over many independent batches.
+
+    One config-2 step is three launches whose block counts are not multiples of what the GPU holds at once
+    (2 048 bands are 2.8 waves of chain_a blocks and 3.5 waves of chain_b blocks), so the last, partial wave of
+    each kernel leaves SMs idle: 8 % / 13 % of the kernels' time.  A ring of independent ChainPlans (own input,
+    output and workspace — e.g. the slots of a loader's buffer ring) replayed round-robin on their own streams
+    lets the next batch's chain_a fill the SMs that the previous batch's chain_b tail no longer uses:
+    0.204 -> 0.189 ms per 256-slice batch with two plans (benchmarks/two_stream_probe.py).
+
+        ring = ChainRing([x0, x1])          # two batches in flight
+        ring.begin()
+        for k in range(steps):
+            ring.replay(k)                  # batch k % 2: fill ring.plans[k % 2].input first in a real loop
+        ring.join()                         # the caller's stream now waits for everything enqueued
+    """
+
+    def __init__(self, inputs, config: ChainConfig = ChainConfig(), *, outs=None, out_dtype=None):
+        if len(inputs) < 1:
+            raise ValueError("ChainRing needs at least one input batch")
+        self.device = inputs[0].device
+        outs = outs if outs is not None else [None] * len(inputs)
+        self.plans = [ChainPlan(x, config, out=o, out_dtype=out_dtype) for x, o in zip(inputs, outs)]
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(device=self.device) for _ in self.plans]
+
+    def begin(self) -> None:
+        """Order the ring's streams after everything already enqueued on the caller's current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            s.wait_stream(cur)
+
+    def replay(self, k: int) -> torch.Tensor:
+        """Enqueue the chain of slot k % len(plans) on that slot's stream; returns its output tensor (valid once
+        the slot's stream — or, after join(), the caller's stream — reaches this point)."""
+        i = k % len(self.plans)
+        with torch.cuda.stream(self.streams[i]):
+            return self.plans[i].replay()
+
+    def join(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
