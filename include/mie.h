@@ -244,7 +244,12 @@ int mie_ssim_sums(const void* a, const void* b, int dtype, int64_t n, int h, int
  * first / second launch of the fused path against the same workspace (used by
  * bench.py to time each kernel with CUDA events; MIE_E_UNSUPPORTED when the
  * geometry takes the unfused path).                                               */
-enum mie_chain_stages { MIE_CHAIN_STAGE_A = 1, MIE_CHAIN_STAGE_B = 2, MIE_CHAIN_ALL = 3 };
+enum mie_chain_stages {
+    MIE_CHAIN_STAGE_A = 1, MIE_CHAIN_STAGE_B = 2, MIE_CHAIN_ALL = 3,
+    /* schedule hints OR-ed into `stages` (tests / benchmarks): by default the marching kernels (one block per
+     * 64-row band) serve jobs of >= 222 bands and the tile kernels (one block per 64x64 tile) smaller ones */
+    MIE_CHAIN_PREFER_MARCH = 4, MIE_CHAIN_PREFER_TILES = 8
+};
 /* Which path (h, w, grid, kernel sizes) takes: 0 = stages run unfused (4 launches), 1 = generic
  * fused kernels (2 launches), 2 = tuned fused kernels for 64x64-pixel tiles and a 9-tap unsharp
  * (3 launches: chain_a, cell-table packing, chain_b; needs 16-byte aligned rows and the dtype's

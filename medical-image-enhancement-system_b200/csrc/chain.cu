@@ -275,7 +275,10 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     ClaheGeom g;
     rc = make_clahe_geom(h, w, gh, gw, MIE_CLAHE_KORNIA, &g);
     if (rc) return rc;
-    if (stages < MIE_CHAIN_STAGE_A || stages > MIE_CHAIN_ALL) return MIE_E_UNSUPPORTED;
+    if (stages & ~(MIE_CHAIN_ALL | MIE_CHAIN_PREFER_MARCH | MIE_CHAIN_PREFER_TILES)) return MIE_E_UNSUPPORTED;
+    const int hints = stages & (MIE_CHAIN_PREFER_MARCH | MIE_CHAIN_PREFER_TILES);
+    stages &= MIE_CHAIN_ALL;
+    if (stages < MIE_CHAIN_STAGE_A) return MIE_E_UNSUPPORTED;
     if (n == 0) return MIE_OK;
     if (!workspace) return MIE_E_NULL;
     if (workspace_bytes < mie_chain_workspace_bytes(n, h, w, gh, gw)) return MIE_E_WORKSPACE;
@@ -317,7 +320,13 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     b.lo = lo; b.rg = hi - lo;
     if (n * (int64_t)b.tiles_x * b.tiles_y > 2147483647LL) return MIE_E_SHAPE;
     if (fast) {
-        const bool march = march_chain_ok(g, kgx, kux) && !g_disable_march &&
+        // The marching kernels run one block per 64-row band: unbeatable once the bands fill the machine, but a
+        // single 512x512 slice is 8 blocks walking 72 rows each (30.8 us for the step against 12.3 us with one
+        // block per 64x64 tile).  Measured crossover on B200: ~24 slices of 512x512 (benchmarks/
+        // chain_latency_probe.py), i.e. about 1.5 band-blocks per SM.
+        const bool enough_bands = n * (int64_t)g.gh >= 222;
+        const bool march = march_chain_ok(g, kgx, kux) && !g_disable_march && !(hints & MIE_CHAIN_PREFER_TILES) &&
+                           (enough_bands || (hints & MIE_CHAIN_PREFER_MARCH)) &&
                            (int64_t)h * src_stride_h * 4 < (1LL << 31);  // 32-bit source-row offsets
         if (stages & MIE_CHAIN_STAGE_A) {
             rc = march ? launch_chain_a_march(a, src_dtype, tgx, tgy, n, st)

@@ -129,9 +129,12 @@ def test_guards_bilateral_metrics_chain(dev, dtype):
         x = torch.from_numpy(_rand(dtype, (n, h, w), 5)).to(dev)
         g = Guarded(n * h * w * esz, dev)
         ws = Guarded(L.mie_chain_workspace_bytes(n, h, w, gh, gw), dev)
-        _ffi.check(L.mie_chain_gauss_clahe_unsharp(x.data_ptr(), g.ptr, CODE[dtype], CODE[dtype], n, h, w, h * w, w,
-                                                   h * w, w, taps.ctypes.data, 9, taps.ctypes.data, 9, gh, gw, 2.0,
-                                                   taps.ctypes.data, 9, taps.ctypes.data, 9, 1, lo, hi, 3, ws.ptr,
-                                                   ws.nbytes, _stream(dev)))
-        g.check(f"chain {(n, h, w)}")
-        ws.check(f"chain workspace {(n, h, w)}")
+        for stages in (3, 3 | 4, 3 | 8):   # default schedule, marching kernels, tile kernels
+            g = Guarded(n * h * w * esz, dev)
+            ws = Guarded(L.mie_chain_workspace_bytes(n, h, w, gh, gw), dev)
+            _ffi.check(L.mie_chain_gauss_clahe_unsharp(x.data_ptr(), g.ptr, CODE[dtype], CODE[dtype], n, h, w, h * w, w,
+                                                       h * w, w, taps.ctypes.data, 9, taps.ctypes.data, 9, gh, gw, 2.0,
+                                                       taps.ctypes.data, 9, taps.ctypes.data, 9, 1, lo, hi, stages,
+                                                       ws.ptr, ws.nbytes, _stream(dev)))
+            g.check(f"chain {(n, h, w)} stages {stages}")
+            ws.check(f"chain workspace {(n, h, w)} stages {stages}")

@@ -385,9 +385,12 @@ def test_chain_marching_kernels(dev, case, dtype):
         border, clip = case.get("border", "reflect"), case.get("clip", 2.0)
         cfg = M.ChainConfig(grid_size=case["grid"], border_type=border, clip_limit=clip)
         ref, st = O.chain_gauss_clahe_unsharp(x, 9, 1.0, clip, case["grid"], 9, 1.0, border, return_stages=True)
-        got = cpu(M.enhance_chain(gpu(x, dev), cfg))
+        # stages = ALL | PREFER_MARCH: small batches take the tile kernels by default (latency heuristic)
+        got = cpu(M.enhance_chain(gpu(x, dev), cfg, stages=3 | 4))
         assert np.array_equal(got, ref), (kind, int((got != ref).sum()))
-        gf = cpu(M.enhance_chain(gpu(x, dev), cfg, out_dtype=torch.float32))
+        assert np.array_equal(cpu(M.enhance_chain(gpu(x, dev), cfg)), ref)               # default schedule
+        assert np.array_equal(cpu(M.enhance_chain(gpu(x, dev), cfg, stages=3 | 8)), ref)  # tile kernels
+        gf = cpu(M.enhance_chain(gpu(x, dev), cfg, out_dtype=torch.float32, stages=3 | 4))
         assert np.array_equal(gf, st["unsharp"]), kind
 
 
