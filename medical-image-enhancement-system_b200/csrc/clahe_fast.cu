@@ -175,24 +175,24 @@ clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells, WinCvt
     DstT* dp = (DstT*)a.dst + n * a.dsn + (int64_t)y0 * a.dsh + x0;
     __syncthreads();
 #pragma unroll 4
-    for (int r = 0; r < a.rows_per_block; ++r) {
+    for (int r = 0; r < a.rows_per_block; ++r, sp += a.ssh, dp += a.dsh) {   // running row pointers: no 64-bit multiplies
         float y[4];
         const float wyv = s_wy[r];
         if constexpr (IDX) {   // default-range integers: the lookup index is an integer function of the code
             uint32_t u[4];
-            Codes<SrcT>::load4(sp + (int64_t)r * a.ssh, u);
+            Codes<SrcT>::load4(sp, u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) y[k] = clahe_px(lds64_(tb + (Codes<SrcT>::index(u[k]) << 3)), wxv[k], wyv);
+            for (int k = 0; k < 4; ++k) y[k] = clahe_px(lds64_(tb + Codes<SrcT>::entry_offset(u[k])), wxv[k], wyv);
         } else {
             float x[4];
-            PixIO<SrcT, WIN>::load4(sp + (int64_t)r * a.ssh, x, cv);
+            PixIO<SrcT, WIN>::load4(sp, x, cv);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const uint32_t bits = INT ? fast_idx_bits_le1(x[k]) : fast_idx_bits<false>(x[k]);
                 y[k] = clahe_px(lds64_(tb + (__byte_perm(bits, 0u, 0x4440) << 3)), wxv[k], wyv);
             }
         }
-        PixIO<DstT, WIN>::store4(dp + (int64_t)r * a.dsh, y, cv);
+        PixIO<DstT, WIN>::store4(dp, y, cv);
     }
 }
 

@@ -120,6 +120,8 @@ template <> struct Codes<uint16_t> {
     }
     static __device__ __forceinline__ uint32_t bin(uint32_t u) { return u >> 8; }
     static __device__ __forceinline__ uint32_t index(uint32_t u) { return (u * 65281u) >> 24; }
+    // byte offset of the 8-byte cell-table entry: the index is the top byte of the product (IMAD, PRMT, shift-add)
+    static __device__ __forceinline__ uint32_t entry_offset(uint32_t u) { return __byte_perm(u * 65281u, 0u, 0x4443) << 3; }
 };
 template <> struct Codes<int16_t> {
     static __device__ __forceinline__ void load8(const int16_t* p, uint32_t* u) {
@@ -135,6 +137,7 @@ template <> struct Codes<int16_t> {
     }
     static __device__ __forceinline__ uint32_t bin(uint32_t u) { return u >> 8; }
     static __device__ __forceinline__ uint32_t index(uint32_t u) { return (u * 65281u) >> 24; }
+    static __device__ __forceinline__ uint32_t entry_offset(uint32_t u) { return __byte_perm(u * 65281u, 0u, 0x4443) << 3; }
 };
 template <> struct Codes<uint8_t> {
     static __device__ __forceinline__ void load8(const uint8_t* p, uint32_t* u) {
@@ -148,12 +151,14 @@ template <> struct Codes<uint8_t> {
     }
     static __device__ __forceinline__ uint32_t bin(uint32_t u) { return u; }
     static __device__ __forceinline__ uint32_t index(uint32_t u) { return u; }
+    static __device__ __forceinline__ uint32_t entry_offset(uint32_t u) { return u << 3; }
 };
 template <> struct Codes<float> {   // never used (IDX kernels are integer-only); keeps the dispatch macros compiling
     static __device__ __forceinline__ void load8(const float*, uint32_t* u) { for (int k = 0; k < 8; ++k) u[k] = 0; }
     static __device__ __forceinline__ void load4(const float*, uint32_t* u) { for (int k = 0; k < 4; ++k) u[k] = 0; }
     static __device__ __forceinline__ uint32_t bin(uint32_t) { return 0; }
     static __device__ __forceinline__ uint32_t index(uint32_t) { return 0; }
+    static __device__ __forceinline__ uint32_t entry_offset(uint32_t) { return 0; }
 };
 
 // ---------------------------------------------------------------- host side
