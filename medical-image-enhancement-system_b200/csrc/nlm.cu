@@ -124,14 +124,20 @@ nlm_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, in
 // column stay in registers across all (2d+1)^2 shifts.  After the neighbourhood is staged in shared memory
 // (read-only from then on) there is not a single barrier; ~23 instructions per lane and row step, 84 % of the
 // lanes and BH / (BH + 2o - 1) of the row steps produce an output.
+// Box sum over lanes l - O + 1 .. l + O, landing on lane l itself (valid for lanes O - 1 .. 31 - O): the lane
+// that owns a column of squared differences also owns the output of that column, so the shifted centre pixel
+// I(p + t) it needs is the q value it loaded O row steps earlier — a register, not another shared-memory load.
 template <int O>
 __device__ __forceinline__ float nlm_hsum(float d2) {
-    const float s2 = d2 + __shfl_down_sync(0xffffffffu, d2, 1);
-    if (O == 1) return s2;
-    const float s4 = s2 + __shfl_down_sync(0xffffffffu, s2, 2);
-    if (O == 2) return s4;
-    if (O == 3) return s4 + __shfl_down_sync(0xffffffffu, s2, 4);
-    return s4 + __shfl_down_sync(0xffffffffu, s4, 4);
+    if (O == 1) return d2 + __shfl_down_sync(0xffffffffu, d2, 1);                        // l, l+1
+    if (O == 2) {
+        const float t = d2 + __shfl_up_sync(0xffffffffu, d2, 1);                          // l-1, l
+        return t + __shfl_down_sync(0xffffffffu, t, 2);                                   // l-1 .. l+2
+    }
+    const float s2 = d2 + __shfl_down_sync(0xffffffffu, d2, 1);                           // l, l+1
+    if (O == 3) return s2 + __shfl_up_sync(0xffffffffu, s2, 2) + __shfl_down_sync(0xffffffffu, s2, 2);   // l-2 .. l+3
+    const float s4 = s2 + __shfl_down_sync(0xffffffffu, s2, 2);                           // l .. l+3
+    return __shfl_up_sync(0xffffffffu, s4, 3) + __shfl_down_sync(0xffffffffu, s4, 1);     // l-3 .. l, l+1 .. l+4
 }
 __device__ __forceinline__ float nlm_ex2(float x) {
     float y;
@@ -167,8 +173,9 @@ nlm_march_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t s
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int x0 = (warp & 1) * VL, y0 = (warp >> 1) * BH;                 // the warp's outputs, tile coordinates
-    const float* pbase = S + (R + y0 - O + 1) * PITCH + (R + x0 - O + 1 + lane);   // difference row 0, column c
-    const float* cbase = S + (R + y0) * PITCH + (R + x0 + lane);                   // output row 0, output column
+    // lane l owns tile column x0 - (O - 1) + l: differences AND output (valid outputs: lanes O-1 .. O-2+VL)
+    const float* pbase = S + (R + y0 - O + 1) * PITCH + (R + x0 - O + 1 + lane);   // difference row 0, own column
+    const float* cbase = pbase + (O - 1) * PITCH;                                  // output row 0, own column
     const float k2 = -1.4426950408889634f * a.inv_h2s2;                    // weight = 2^(k2 * max(D - var, 0))
     const float cut = -5.0f * 1.4426950408889634f;                         // distance 5 on that scale
     float num[BH], den[BH];
@@ -182,27 +189,28 @@ nlm_march_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t s
             if (ty == 0 && tx == 0) continue;
             const int toff = ty * PITCH + tx;
             const float* q = pbase + toff;
-            const float* cq = cbase + toff;
-            float hs[box];
+            float hs[box], qr[O + 1];           // rings: row sums of the last 2O rows, q of the last O + 1 rows
 #pragma unroll
             for (int s = 0; s < BH + box - 1; ++s) {
-                const float df = pbase[s * PITCH] - q[s * PITCH];
+                const float qv = q[s * PITCH];
+                qr[s % (O + 1)] = qv;
+                const float df = pbase[s * PITCH] - qv;
                 hs[s % box] = nlm_hsum<O>(df * df);
                 if (s >= box - 1) {
-                    const int j = s - (box - 1);
+                    const int j = s - (box - 1);              // output row j: centre = difference row j + O - 1 = s - O
                     float V = hs[0];
 #pragma unroll
                     for (int k = 1; k < box; ++k) V += hs[k];
                     const float e = fmaxf(V - a.var_term, 0.0f) * k2;
                     const float wgt = e >= cut ? nlm_ex2(e) : 0.0f;     // branch-free: select, not a divergent region
-                    num[j] = fmaf(wgt, cq[j * PITCH], num[j]);
+                    num[j] = fmaf(wgt, qr[(s - O) % (O + 1)], num[j]);
                     den[j] += wgt;
                 }
             }
         }
     }
-    const int x = tx0 + x0 + lane;
-    if (lane < VL && x < a.w) {
+    const int x = tx0 + x0 - (O - 1) + lane;
+    if (lane >= O - 1 && lane < O - 1 + VL && x < a.w) {
 #pragma unroll
         for (int j = 0; j < BH; ++j) {
             const int y = ty0 + y0 + j;
