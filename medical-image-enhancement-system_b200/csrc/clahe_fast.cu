@@ -130,6 +130,7 @@ struct ApplyFastArgs {
     ClaheGeom g;
     int rows_per_block;   // divides th / 2
     int blocks_per_image;
+    const uint8_t* luts;  // non-null: the block packs its row of cell tables itself (small jobs: one launch less)
     float inv_tm1_y, inv_tm1_x;  // unused (weights use the exact division below)
 };
 
@@ -158,7 +159,20 @@ clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells, WinCvt
     const int64_t n = blockIdx.x / a.blocks_per_image;
     const int y0 = (int)(blockIdx.x % a.blocks_per_image) * a.rows_per_block;
     const int cy = (y0 + (g.th >> 1)) / g.th;        // cell row of all rows of this block
-    {
+    if (a.luts) {   // latency path: cell tables straight from the LUTs (same packing as chain_pack_cells_kernel)
+        const int jt = max(cy - 1, 0), jb = min(cy, g.gh - 1);
+        for (int gl = tid; gl < kBins; gl += T) {
+            const uint8_t* top = a.luts + (n * g.gh + jt) * (int64_t)g.gw * kBins + gl;
+            const uint8_t* bot = a.luts + (n * g.gh + jb) * (int64_t)g.gw * kBins + gl;
+            int tl = __ldg(top), bl = __ldg(bot);
+            for (int cx = 0; cx <= g.gw; ++cx) {
+                const int ir = min(cx, g.gw - 1);
+                const int tr = __ldg(top + ir * kBins), br = __ldg(bot + ir * kBins);
+                s_tab[cx * kBins + gl] = make_uint2(cell_word(tl - tr, tr), cell_word(bl - br, br));
+                tl = tr; bl = br;
+            }
+        }
+    } else {
         const uint4* s = reinterpret_cast<const uint4*>(cells + (n * (g.gh + 1) + cy) * (int64_t)(g.gw + 1) * kBins);
         uint4* d = reinterpret_cast<uint4*>(s_tab);
         for (int i = tid; i < (g.gw + 1) * kBins / 2; i += T) d[i] = __ldg(s + i);
@@ -263,9 +277,14 @@ int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t 
     WinCvt cv = {};
     const int mode = range_mode(sd, lo, hi, &cv);
     if (mode < 0) return MIE_E_UNSUPPORTED;   // callers test clahe_apply_fast_ok first
-    int rc = launch_pack_cells(luts, cells, n, g.gh, g.gw, st);
-    if (rc) return rc;
+    // small jobs are launch-latency bound (a single 512x512 slice: ~4 us per launch): skip the packing launch
+    const bool in_kernel_cells = n * (int64_t)g.gh * g.gw < 4 * 148;
+    if (!in_kernel_cells) {
+        int rc = launch_pack_cells(luts, cells, n, g.gh, g.gw, st);
+        if (rc) return rc;
+    }
     ApplyFastArgs a;
+    a.luts = in_kernel_cells ? luts : nullptr;
     a.src = src; a.dst = dst; a.ssn = ssn; a.ssh = ssh; a.dsn = dsn; a.dsh = dsh; a.g = g;
     int rows = g.th / 2;                        // rows of a block stay inside one cell row
     for (int d = 32; d >= 1; --d)
