@@ -131,7 +131,6 @@ struct ApplyFastArgs {
     int rows_per_block;   // divides th / 2
     int blocks_per_image;
     const uint8_t* luts;  // non-null: the block packs its row of cell tables itself (small jobs: one launch less)
-    float inv_tm1_y, inv_tm1_x;  // unused (weights use the exact division below)
 };
 
 __device__ __forceinline__ uint2 lds64_(uint32_t addr) {
@@ -291,7 +290,6 @@ int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t 
         if ((g.th / 2) % d == 0) { rows = d; break; }
     a.rows_per_block = rows;
     a.blocks_per_image = g.h / rows;
-    a.inv_tm1_y = a.inv_tm1_x = 0.f;
     const int64_t blocks = n * a.blocks_per_image;
     if (blocks > 2147483647LL) return MIE_E_SHAPE;
     const size_t smem = (size_t)(g.gw + 1) * kBins * 8;

@@ -1,5 +1,13 @@
 // median.cu — 2-D K x K and 3-D 3x3x3 median filters (pure selection, bit-exact).
 //
+// Kernels, fastest first:
+//   median3x3_packed_kernel / median5x5_packed_kernel  8 / 16-bit pixels, rows a multiple of 8 pixels: two pixels
+//       per lane on min/max.{u,s}16x2, marching rows in registers, neighbours by shuffle, no shared memory;
+//   median3d_direct_kernel   16-bit volumes of even width: sorted 9-lists of three planes in registers,
+//       rank 13 of 27 by column sorts + pruning + merges;
+//   median3d_packed_kernel   16-bit volumes of any width (planes staged in shared memory), same selection;
+//   median2d_kernel<KY,KX> / median3d_kernel   every other size / dtype: shared-memory tiles, forgetful selection.
+//
 // mie_median2d replaces kornia.filters.median_blur (zero padding, lower median ==
 // true median for odd window sizes) and skimage.filters.median on 2-D input
 // ('nearest' border); SURVEY.md §8(a) A5.
@@ -715,7 +723,7 @@ median5x5_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
 
 // 0 = launched, < 0 = not applicable (caller falls back to the generic kernel), > 0 = CUDA error
 template <typename T>
-static int try_median3x3_packed(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
+static int try_median_packed(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
                                 int64_t dsn, int64_t dsh, int border, cudaStream_t st, int k = 3) {
     static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
     if (off || (w & 7) || h < k - 1) return -1;
@@ -787,11 +795,11 @@ int mie_median2d(const void* src, void* dst, int dtype, int64_t n, int h, int w,
     if (n == 0) return MIE_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (ky == kx && (ky == 3 || ky == 5) && dtype != MIE_F32) {   // packed marching kernels (8 / 16-bit pixels)
-        rc = dtype == MIE_U16 ? try_median3x3_packed<uint16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
+        rc = dtype == MIE_U16 ? try_median_packed<uint16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
                                                                dst_stride_n, dst_stride_h, border, st, ky)
-           : dtype == MIE_I16 ? try_median3x3_packed<int16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
+           : dtype == MIE_I16 ? try_median_packed<int16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
                                                               dst_stride_n, dst_stride_h, border, st, ky)
-                              : try_median3x3_packed<uint8_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
+                              : try_median_packed<uint8_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
                                                               dst_stride_n, dst_stride_h, border, st, ky);
         if (rc >= 0) return rc;
     }
