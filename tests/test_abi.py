@@ -110,3 +110,39 @@ def test_host_side_argument_validation_of_the_abi():
     assert rc == -9
     rc = L.mie_clahe_luts(fake, 1, 1, 64, 64, 4096, 64, 8, 8, 2.0, 0, 5.0, 5.0, fake, None)
     assert rc == -10
+
+
+def test_newer_entry_points_reject_bad_arguments_before_any_launch():
+    """Argument validation of the metrics / skimage-signature / median / chain entry points runs on the host,
+    so it can be checked without a GPU (pointers are never dereferenced when validation fails)."""
+    import numpy as np
+    from mie_b200 import _ffi
+
+    L = _ffi.lib()
+    fake = 0x1000
+    w9 = np.ones(9, np.float32) / 9
+    # metrics: window larger than the image, unknown dtype, undersized workspace, n == 0 is a no-op
+    assert L.mie_ssim_sums(fake, fake, 1, 1, 8, 8, 64, 8, 64, 8, 11, 1.0, 1.0, fake, fake, 1 << 20, None) == -7
+    assert L.mie_ssim_sums(fake, fake, 1, 1, 64, 64, 4096, 64, 4096, 64, 17, 1.0, 1.0, fake, fake, 1 << 20, None) == -7
+    assert L.mie_sqdiff_sums(fake, fake, 7, 1, 8, 8, 64, 8, 64, 8, fake, fake, 1 << 20, None) == -2
+    assert L.mie_sqdiff_sums(fake, fake, 1, 1, 64, 64, 4096, 64, 4096, 64, fake, fake, 1, None) == -9
+    assert L.mie_sqdiff_sums(None, None, 1, 0, 64, 64, 4096, 64, 4096, 64, None, None, 0, None) == 0
+    assert L.mie_metric_workspace_bytes(2, 64, 64, 11) == 2 * 4 * 2 * 8      # 2 planes x (2x2 window tiles) x 2 doubles
+    assert L.mie_metric_workspace_bytes(2, 8, 8, 11) == 0                    # window does not fit
+    # unsharp with amount: symmetric border accepted by validation (fails later only on the null stream launch),
+    # unknown border rejected
+    assert L.mie_unsharp_amount(fake, fake, 3, 3, 1, 64, 64, 4096, 64, 4096, 64, w9.ctypes.data, 9, w9.ctypes.data, 9,
+                                9, 1.5, 1, 0.0, 1.0, None) == -8
+    assert L.mie_unsharp_amount(fake, fake, 3, 3, 0, 64, 64, 4096, 64, 4096, 64, w9.ctypes.data, 9, w9.ctypes.data, 9,
+                                4, 1.5, 1, 0.0, 1.0, None) == 0             # empty batch, symmetric border: fine
+    # median: even kernel, circular border
+    assert L.mie_median2d(fake, fake, 1, 1, 64, 64, 4096, 64, 4096, 64, 4, 4, 0, None) == -7
+    assert L.mie_median2d(fake, fake, 1, 1, 64, 64, 4096, 64, 4096, 64, 3, 3, 3, None) == -8
+    assert L.mie_median3d(fake, fake, 1, 4, 64, 64, 4096, 64, 4096, 64, None, None, 1, None) == -8   # reflect: not for volumes
+    # chain: unknown bits in the stages mask; schedule hints are legal
+    assert L.mie_chain_gauss_clahe_unsharp(fake, fake, 1, 1, 0, 512, 512, 262144, 512, 262144, 512, w9.ctypes.data, 9,
+                                           w9.ctypes.data, 9, 8, 8, 2.0, w9.ctypes.data, 9, w9.ctypes.data, 9, 1, 0.0,
+                                           65535.0, 16, fake, 0, None) == -11
+    assert L.mie_chain_gauss_clahe_unsharp(fake, fake, 1, 1, 0, 512, 512, 262144, 512, 262144, 512, w9.ctypes.data, 9,
+                                           w9.ctypes.data, 9, 8, 8, 2.0, w9.ctypes.data, 9, w9.ctypes.data, 9, 1, 0.0,
+                                           65535.0, 3 | 4, fake, 0, None) == 0
