@@ -208,8 +208,9 @@ __device__ __forceinline__ int fast_bin(float g) {
 // Bit pattern whose low byte is trunc(clamp(g*255, 0, 255)) (NaN -> 0).
 template <bool NONNEG>
 __device__ __forceinline__ uint32_t fast_idx_bits(float g) {
-    float f = fminf(__fmul_rn(g, 255.0f), 255.0f);
-    if (!NONNEG) f = fmaxf(f, 0.0f);
+    float f = __fmul_rn(g, 255.0f);
+    if (!NONNEG) f = fmaxf(f, 0.0f);     // first, so that NaN -> 0 as in fminf(fmaxf(f, 0), 255) (clahe.cuh, oracle)
+    f = fminf(f, 255.0f);
     return __float_as_uint(__fadd_rd(f, 8388608.0f));
 }
 

@@ -225,7 +225,7 @@ static bool equalize_fast_ok(int sd, int dd, const void* src, const void* dst, i
     static const bool off = [] { const char* e = getenv("MIE_EQUALIZE_NO_FAST"); return e && e[0] == '1'; }();
     static const int esz[4] = {1, 2, 2, 4};
     WinCvt cv;
-    if (off || (w & 7) || sd == MIE_F32 || range_mode(sd, lo, hi, &cv) < 0) return false;   // float planes: generic kernels
+    if (off || (w & 7) || range_mode(sd, lo, hi, &cv) < 0) return false;
     const int sa = 8 * esz[sd], da = dd == MIE_F32 ? 16 : 8 * esz[dd];
     if (((uintptr_t)src % sa) || ((ssn * esz[sd]) % sa) || ((ssh * esz[sd]) % sa)) return false;
     if (((uintptr_t)dst % da) || ((dsn * esz[dd]) % da) || ((dsh * esz[dd]) % da)) return false;
@@ -266,7 +266,9 @@ int mie_equalize(const void* src, void* dst, int src_dtype, int dst_dtype, int64
         if (rows > 64) rows = 64;
         dim3 grid((unsigned)ceil_div(h, rows), (unsigned)n);
         WinCvt cv = {};
-        const bool win = range_mode(src_dtype, lo, hi, &cv) == 1;
+        // float planes (kornia's native input) may hold values outside [0, 1] or NaN: they take the range-checked
+        // code path of the windowed kernels (PixIO<float, true> is a plain load)
+        const bool win = range_mode(src_dtype, lo, hi, &cv) == 1 || src_dtype == MIE_F32;
         static const bool no_int = [] { const char* e = getenv("MIE_EQUALIZE_NO_INT_RULES"); return e && e[0] == '1'; }();
         const bool idx = !win && !no_int && int_rules_ok(src_dtype);
 #define MIE_EQ_HIST(T_)                                                                                            \
@@ -276,7 +278,8 @@ int mie_equalize(const void* src, void* dst, int src_dtype, int dst_dtype, int64
         switch (src_dtype) {
             case MIE_U8: MIE_EQ_HIST(uint8_t); break;
             case MIE_U16: MIE_EQ_HIST(uint16_t); break;
-            default: MIE_EQ_HIST(int16_t); break;
+            case MIE_I16: MIE_EQ_HIST(int16_t); break;
+            default: MIE_EQ_HIST(float); break;
         }
 #undef MIE_EQ_HIST
         rc = check_launch();

@@ -165,6 +165,12 @@ def test_equalize_bit_exact(dev, dtype):
         assert np.array_equal(got, ref)
         if dtype != np.float32:
             assert np.array_equal(cpu(M.equalize(gpu(x, dev))), O.from01(ref, dtype))
+    if dtype == np.float32:   # values outside [0, 1] and NaN: ignored by the histogram, clamped by the lookup
+        x = rand(dtype, (2, 1, 64, 80), 13) * 1.6 - 0.3
+        x[0, 0, 5, 7:20] = np.nan
+        ref = O.equalize(x)
+        got = cpu(M.equalize(gpu(x, dev)))
+        assert np.array_equal(got, ref, equal_nan=True)
     # constant image: step == 0 -> returned unchanged
     c = np.full((1, 1, 32, 32), 77, np.uint8)
     assert np.array_equal(cpu(M.equalize(gpu(c, dev))), c)

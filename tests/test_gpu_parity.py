@@ -161,6 +161,30 @@ def test_clahe_integer_windows_take_the_tuned_kernels_bit_exactly(dev, case):
         assert np.array_equal(cpu(M.equalize_clahe(xt, 2.0, grid, value_range=vr)), O.from01(ref, dtype, vr)), shape
 
 
+def test_float_planes_outside_unit_range_and_nan(dev):
+    """kornia's native input is float: pixels outside [0, 1] and NaN are ignored by the histograms and clamped by
+    the lookup (NaN -> index 0) on the tuned CLAHE kernels and in the fused chain, exactly as in the oracle."""
+    import mie_b200 as M
+    import oracle as O
+
+    rng = np.random.default_rng(77)
+    for shape, grid in [((2, 1, 512, 512), (8, 8)), ((12, 1, 256, 256), (8, 8))]:
+        x = (rng.random(shape, dtype=np.float32) * 1.5 - 0.25).astype(np.float32)
+        x[0, 0, 10, 30:90] = np.nan
+        x[-1, 0, 200:203, :] = np.inf
+        xt = gpu(x, dev)
+        h_ref = O.clahe_hist(x, grid)
+        assert np.array_equal(cpu(M.clahe_histograms(xt, grid)).reshape(h_ref.shape), h_ref)
+        l_ref = O.clahe_luts(x, 2.0, grid)
+        assert np.array_equal(cpu(M.clahe_luts(xt, 2.0, grid)).reshape(l_ref.shape), l_ref)
+        assert np.array_equal(cpu(M.equalize_clahe(xt, 2.0, grid)), O.equalize_clahe(x, 2.0, grid), equal_nan=True)
+        # fused chain, every schedule: NaN / inf spread through the Gaussians; bins and lookups follow the same rules
+        ref = O.chain_gauss_clahe_unsharp(x, 9, 1.0, 2.0, grid, 9, 1.0, "reflect")
+        cfg = M.ChainConfig(grid_size=grid)
+        for stages in (3, 3 | 4, 3 | 8):
+            assert np.array_equal(cpu(M.enhance_chain(xt, cfg, stages=stages)), ref, equal_nan=True), (shape, stages)
+
+
 def test_clahe_constant_image_stays_constant(dev):
     import mie_b200 as M
 
