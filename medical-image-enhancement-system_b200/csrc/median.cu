@@ -3,6 +3,7 @@
 // Kernels, fastest first:
 //   median3x3_packed_kernel / median5x5_packed_kernel  8 / 16-bit pixels, rows a multiple of 8 pixels: two pixels
 //       per lane on min/max.{u,s}16x2, marching rows in registers, neighbours by shuffle, no shared memory;
+//   median3x3_f32_kernel     float planes, rows a multiple of 4 pixels: the same marching schedule, one pixel per register;
 //   median3d_direct_kernel   16-bit volumes of even width: sorted 9-lists of three planes in registers,
 //       rank 13 of 27 by column sorts + pruning + merges;
 //   median3d_packed_kernel   16-bit volumes of any width (planes staged in shared memory), same selection;
@@ -721,6 +722,99 @@ median5x5_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
     }
 }
 
+// ---------------------------------------------------------------- 2-D 3x3, float pixels (kornia's native dtype)
+// The marching schedule of the packed kernels with one pixel per register: a lane owns 4 consecutive columns
+// (one 128-bit load per row), the neighbours come from the adjacent lanes by shuffle, the three vertical
+// samples of every column are sorted once per row, and the median of 9 is med3(max of minima, med3 of medians,
+// min of maxima).  fminf / fmaxf semantics as in the generic kernel.
+__global__ void __launch_bounds__(256)
+median3x3_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                     int64_t dsh, int64_t nplanes, int h, int w, int strips, int bands, int rows_per_band, int border) {
+    const int lane = threadIdx.x & 31;
+    const int64_t wg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int strip = (int)(wg % strips), band = (int)((wg / strips) % bands);
+    const int64_t n = wg / ((int64_t)strips * bands);
+    if (n >= nplanes) return;                      // warp-uniform
+    const int x0 = strip * 128 + lane * 4;
+    const bool active = x0 < w;
+    const int y0 = band * rows_per_band, y1 = min(y0 + rows_per_band, h);
+    const float* plane = src + n * ssn;
+    float* oplane = dst + n * dsn;
+
+    auto load_row = [&](int y, float* r) {          // r[0] = pixel x0-1, r[1..4] = own pixels, r[5] = pixel x0+4
+        const int sy = border_index(y, h, border);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        float left = 0.f, right = 0.f;
+        if (sy >= 0) {                              // uniform
+            const float* row = plane + (int64_t)sy * ssh;
+            if (active) v = __ldg(reinterpret_cast<const float4*>(row + x0));
+            left = __shfl_up_sync(0xffffffffu, v.w, 1);
+            right = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (active) {
+                if (x0 == 0)
+                    left = border == MIE_BORDER_REFLECT ? v.y
+                         : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? v.x : 0.f;
+                else if (lane == 0)
+                    left = __ldg(row + x0 - 1);
+                if (x0 + 4 == w)
+                    right = border == MIE_BORDER_REFLECT ? v.z
+                          : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? v.w : 0.f;
+                else if (lane == 31)
+                    right = __ldg(row + x0 + 4);
+            }
+        }
+        r[0] = left; r[1] = v.x; r[2] = v.y; r[3] = v.z; r[4] = v.w; r[5] = right;
+    };
+
+    float ring[3][6];
+    load_row(y0 - 1, ring[0]);
+    load_row(y0, ring[1]);
+    for (int yb = y0; yb < y1; yb += 3) {
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const int y = yb + u;
+            if (y < y1) {                           // uniform
+                load_row(y + 1, ring[(u + 2) % 3]);
+                float lo[6], mi[6], hi[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) {
+                    float a = ring[u % 3][c], b = ring[(u + 1) % 3][c], cc = ring[(u + 2) % 3][c];
+                    cswap(a, b); cswap(b, cc); cswap(a, b);
+                    lo[c] = a; mi[c] = b; hi[c] = cc;
+                }
+                float o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float maxlo = fmaxf(fmaxf(lo[k], lo[k + 1]), lo[k + 2]);
+                    const float minhi = fminf(fminf(hi[k], hi[k + 1]), hi[k + 2]);
+                    const float a = fminf(mi[k], mi[k + 1]), b = fmaxf(mi[k], mi[k + 1]);
+                    const float medmi = fmaxf(a, fminf(b, mi[k + 2]));
+                    const float c = fminf(maxlo, medmi), d = fmaxf(maxlo, medmi);
+                    o[k] = fmaxf(c, fminf(d, minhi));
+                }
+                if (active) *reinterpret_cast<float4*>(oplane + (int64_t)y * dsh + x0) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+        }
+    }
+}
+
+static int try_median3x3_f32(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int64_t dsn,
+                             int64_t dsh, int border, cudaStream_t st) {
+    static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
+    if (off || (w & 3) || h < 2) return -1;
+    if (((uintptr_t)src % 16) || ((ssn * 4) % 16) || ((ssh * 4) % 16)) return -1;
+    if (((uintptr_t)dst % 16) || ((dsn * 4) % 16) || ((dsh * 4) % 16)) return -1;
+    const int strips = ceil_div(w, 128);
+    int rows = 32;
+    while (rows > 8 && n * strips * ceil_div(h, rows) < 8 * 148 * 4) rows >>= 1;
+    const int bands = ceil_div(h, rows);
+    const int64_t blocks = (n * strips * bands + 7) / 8;
+    if (blocks > 2147483647LL) return MIE_E_SHAPE;
+    median3x3_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float*)src, (float*)dst, ssn, ssh, dsn, dsh, n, h, w,
+                                                          strips, bands, rows, border);
+    return check_launch();
+}
+
 // 0 = launched, < 0 = not applicable (caller falls back to the generic kernel), > 0 = CUDA error
 template <typename T>
 static int try_median_packed(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
@@ -794,6 +888,10 @@ int mie_median2d(const void* src, void* dst, int dtype, int64_t n, int h, int w,
     if (ky <= 0 || kx <= 0 || !(ky & 1) || !(kx & 1)) return MIE_E_KERNEL;
     if (n == 0) return MIE_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (ky == 3 && kx == 3 && dtype == MIE_F32) {
+        rc = try_median3x3_f32(src, dst, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h, border, st);
+        if (rc >= 0) return rc;
+    }
     if (ky == kx && (ky == 3 || ky == 5) && dtype != MIE_F32) {   // packed marching kernels (8 / 16-bit pixels)
         rc = dtype == MIE_U16 ? try_median_packed<uint16_t>(src, dst, n, h, w, src_stride_n, src_stride_h,
                                                                dst_stride_n, dst_stride_h, border, st, ky)

@@ -46,7 +46,7 @@ def test_median_blur_bit_exact(dev, dtype, k):
             assert np.array_equal(got, O.median_blur(x, k, border)), (shape, k, border)
 
 
-@pytest.mark.parametrize("dtype", [np.uint16, np.int16, np.uint8])
+@pytest.mark.parametrize("dtype", [np.uint16, np.int16, np.uint8, np.float32])
 def test_median_blur_3x3_packed_kernel(dev, dtype):
     """16-bit 3x3 on 16-byte-aligned rows takes the marching packed kernel (two pixels per lane,
     neighbours by shuffle): partial warps, several 256-column strips, short bands, every border rule."""
@@ -56,7 +56,10 @@ def test_median_blur_3x3_packed_kernel(dev, dtype):
     for shape in [(2, 1, 70, 48), (1, 1, 33, 512), (1, 2, 9, 264), (1, 1, 2, 8), (3, 1, 100, 1032), (1, 1, 67, 256),
                   (1, 1, 4, 8), (1, 1, 5, 16)]:
         x = rand(dtype, shape, 5)
-        x[..., : shape[-2] // 2, :] //= (64 if dtype != np.uint8 else 8)  # many ties
+        if dtype == np.float32:
+            x[..., : shape[-2] // 2, :] = np.round(x[..., : shape[-2] // 2, :] * 8) / 8  # many ties
+        else:
+            x[..., : shape[-2] // 2, :] //= (64 if dtype != np.uint8 else 8)  # many ties
         for k in (3, 5):   # both packed marching kernels
             for border in ("constant", "replicate", "reflect", "symmetric"):
                 if border == "reflect" and k // 2 >= min(shape[-2:]):
@@ -67,6 +70,8 @@ def test_median_blur_3x3_packed_kernel(dev, dtype):
     from mie_b200 import synthetic
 
     x = synthetic.phantom((256, 1, 512, 512), np.uint16 if dtype != np.uint8 else np.uint8, seed=2).astype(dtype)
+    if dtype == np.float32:
+        x = (x / np.float32(4095.0)).astype(np.float32)
     got = cpu(M.median_blur(gpu(x, dev), 3))
     for i in (0, 1, 127, 255):
         assert np.array_equal(got[i], O.median_blur(x[i:i + 1], 3, "constant")[0]), i
