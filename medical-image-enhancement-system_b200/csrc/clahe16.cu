@@ -13,6 +13,8 @@
 // with 16-byte stores and stays in L2 for the interpolation pass, which gathers four uint16 entries
 // per pixel.  The caller's workspace bounds how many images' LUTs exist at a time (mie_clahe loops over
 // groups of images), so a batch never needs more LUT memory than fits in L2.
+#include <cstdlib>
+
 #include "clahe.cuh"
 
 namespace mie {
@@ -142,6 +144,107 @@ clahe16_lut_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_t ssh, C
     }
 }
 
+// ---------------------------------------------------------------- tiles of fewer than 65 536 pixels
+// The common case (64x64 .. 255x255-pixel tiles): every count fits 16 bits, so the WHOLE grey range fits the
+// 128 KB of shared memory as 16-bit counters packed two per word — one zeroing and one pass over the tile
+// instead of four of each — and the rest is trimmed to what the 65 536 LUT entries per tile really need:
+//   * the residual rule (+1 at bins 0, step, 2 step, ... for the first `res` positions) walks a running
+//     "next multiple of step" instead of dividing per bin;
+//   * lut = sat(rint(float(cum) * scale)) without I2F / FRND / F2I (conversion pipe, 16 lanes per clock):
+//     float(cum) by OR-ing the integer into the mantissa of 2^23, rint by adding 1.5 * 2^23, the result read
+//     back from the mantissa — the same values as the generic kernel, bit for bit.
+// Thread t owns bins 64t .. 64t+63 = words 32t .. 32t+31 (one padding word per 32: conflict-free).
+__device__ __forceinline__ int padw(int w) { return w + (w >> 5); }
+
+__global__ void __launch_bounds__(kThreads16)
+clahe16_lut_small_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, Lut16Params lp,
+                         uint16_t* __restrict__ luts) {
+    extern __shared__ __align__(16) int s_h[];   // 32768 + 1024 words
+    __shared__ int s_red[32];
+    const int64_t tile = blockIdx.x;
+    const int tx = (int)(tile % g.gw), ty = (int)((tile / g.gw) % g.gh);
+    const int64_t n = tile / ((int64_t)g.gw * g.gh);
+    const uint16_t* plane = src + n * ssn;
+    const int tid = threadIdx.x;
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_h);
+    for (int i = tid; i < kHalf16 + kHalf16 / 32; i += kThreads16) s_w[i] = 0u;
+    __syncthreads();
+    const int area = g.th * g.tw;
+    const bool inside = (ty + 1) * g.th <= g.h && (tx + 1) * g.tw <= g.w;   // block-uniform: no reflect padding
+    for (int i = tid; i < area; i += kThreads16) {
+        const int yy = i / g.tw, xx = i - yy * g.tw;
+        int sy = ty * g.th + yy, sx = tx * g.tw + xx;
+        if (!inside) {
+            sy = border_index(sy, g.h, MIE_BORDER_REFLECT);
+            sx = border_index(sx, g.w, MIE_BORDER_REFLECT);
+        }
+        const uint32_t v = plane[(int64_t)sy * ssh + sx];
+        atomicAdd(&s_w[padw((int)(v >> 1))], (v & 1u) ? 0x10000u : 1u);
+    }
+    __syncthreads();
+
+    const uint32_t* mine = s_w + tid * 33;       // padw(32 tid + k) = 33 tid + k for k < 32
+    const uint32_t clip = (uint32_t)lp.clip;
+    int rb = 0, res = 0, step = 1;
+    if (lp.clip > 0) {
+        int local = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t wv = mine[k];
+            const uint32_t c0 = wv & 0xFFFFu, c1 = wv >> 16;
+            local += (int)(c0 > clip ? c0 - clip : 0u) + (int)(c1 > clip ? c1 - clip : 0u);
+        }
+        const int clipped = block_sum_1024(local, s_red);
+        rb = clipped / kBins16;
+        res = clipped - rb * kBins16;
+        step = res ? max(kBins16 / res, 1) : 1;
+    }
+    // value of bin u after clipping / redistribution; the residual walk state is (next multiple, its index)
+    const int u0 = tid * 64;
+    int q = (u0 + step - 1) / step, next = q * step;
+    auto bin_value = [&](uint32_t c, int u) {
+        if (lp.clip > 0) {
+            c = min(c, clip) + (uint32_t)rb;
+            if (u == next) {
+                c += (res && q < res) ? 1u : 0u;
+                next += step; ++q;
+            }
+        }
+        return (int)c;
+    };
+    int sum = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t wv = mine[k];
+        sum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
+        sum += bin_value(wv >> 16, u0 + 2 * k + 1);
+    }
+    int total;
+    int cum = block_excl_scan_1024(sum, s_red, &total);
+    q = (u0 + step - 1) / step; next = q * step;                 // restart the walk for the second pass
+    const float scale = lp.lut_scale;
+    auto lut_entry = [&](int c) {                                  // sat(rint(float(c) * scale)), c < 2^23
+        const float f = __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)c), 8388608.0f);
+        const uint32_t r = __float_as_uint(__fadd_rn(__fmul_rn(f, scale), 12582912.0f)) - 0x4B400000u;
+        return min(r, 65535u);
+    };
+    uint4* dst = reinterpret_cast<uint4*>(luts + tile * (int64_t)kBins16 + u0);
+#pragma unroll 2
+    for (int k4 = 0; k4 < 8; ++k4) {
+        uint32_t packed[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * k4 + j;
+            const uint32_t wv = mine[k];
+            cum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
+            const uint32_t e0 = lut_entry(cum);
+            cum += bin_value(wv >> 16, u0 + 2 * k + 1);
+            packed[j] = e0 | (lut_entry(cum) << 16);
+        }
+        dst[k4] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+
 // Interpolation pass (cv::CLAHE_Interpolation_Body, fp32 in OpenCV's operation order): 4 pixels per thread.
 __global__ void __launch_bounds__(256)
 clahe16_apply_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
@@ -201,6 +304,13 @@ int clahe16_luts_impl(const void* src, int64_t n, int h, int w, int64_t ssn, int
     if (tiles == 0) return MIE_OK;
     if (tiles > 2147483647LL) return MIE_E_SHAPE;
     const size_t smem = (size_t)(kHalf16 + kHalf16 / 32) * sizeof(int);
+    static const bool no_small = [] { const char* e = getenv("MIE_CLAHE16_NO_SMALL"); return e && e[0] == '1'; }();
+    if ((int64_t)g.th * g.tw < 65536 && !no_small) {   // counts fit 16 bits: single-pass kernel
+        MIE_ENSURE_SMEM(clahe16_lut_small_kernel, smem);
+        clahe16_lut_small_kernel<<<(unsigned)tiles, kThreads16, smem, st>>>((const uint16_t*)src, ssn, ssh, g,
+                                                                         make_lut16_params(g, clip_limit), luts);
+        return check_launch();
+    }
     MIE_ENSURE_SMEM(clahe16_lut_kernel, smem);
     clahe16_lut_kernel<<<(unsigned)tiles, kThreads16, smem, st>>>((const uint16_t*)src, ssn, ssh, g,
                                                                make_lut16_params(g, clip_limit), luts);
