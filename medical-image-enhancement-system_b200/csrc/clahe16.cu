@@ -13,6 +13,8 @@
 // with 16-byte stores and stays in L2 for the interpolation pass, which gathers four uint16 entries
 // per pixel.  The caller's workspace bounds how many images' LUTs exist at a time (mie_clahe loops over
 // groups of images), so a batch never needs more LUT memory than fits in L2.
+#include <cooperative_groups.h>
+
 #include <cstdlib>
 
 #include "clahe.cuh"
@@ -245,6 +247,147 @@ clahe16_lut_small_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_t 
     }
 }
 
+// ---------------------------------------------------------------- the same, one tile per CLUSTER of two CTAs
+// With one 1 024-thread block per SM (135 KB of counters) nothing hides the latency of the per-tile passes
+// (zero, count, two sweeps, two block-wide reductions).  A thread-block cluster of two 512-thread CTAs splits the
+// grey range: CTA r owns bins r * 32 768 .. + 32 767 (66 KB of 16-bit counters), counts only its own pixels, and
+// the two numbers the halves need from each other — the clipped excess and the prefix total of the lower half —
+// travel through distributed shared memory between two cluster barriers.  Three CTAs fit an SM: 48 warps from
+// three different tiles interleave.
+constexpr int kClThreads = 512;
+
+template <int NW>
+__device__ __forceinline__ int block_sum_nw(int v, int* s_red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    int t = lane < NW ? s_red[lane] : 0;
+    return warp_sum(t);
+}
+template <int NW>
+__device__ __forceinline__ int block_excl_scan_nw(int v, int* s_red, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_red[warp] = incl;
+    __syncthreads();
+    int wv = lane < NW ? s_red[lane] : 0, winc = wv;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+    }
+    const int warp_off = __shfl_sync(0xffffffffu, winc - wv, warp);
+    *total = __shfl_sync(0xffffffffu, winc, 31);
+    return warp_off + incl - v;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClThreads)
+clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, Lut16Params lp,
+                           uint16_t* __restrict__ luts) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) int s_h[];   // 16384 + 512 words: this CTA's half of the grey range
+    __shared__ int s_red[32];
+    __shared__ int s_xchg[2];                    // [0] clipped excess of this half, [1] prefix total of this half
+    const unsigned rank = cluster.block_rank();  // 0: bins 0 .. 32767, 1: bins 32768 .. 65535
+    const int64_t tile = blockIdx.x >> 1;
+    const int tx = (int)(tile % g.gw), ty = (int)((tile / g.gw) % g.gh);
+    const int64_t n = tile / ((int64_t)g.gw * g.gh);
+    const uint16_t* plane = src + n * ssn;
+    const int tid = threadIdx.x;
+    uint32_t* s_w = reinterpret_cast<uint32_t*>(s_h);
+    for (int i = tid; i < kHalf16 / 2 + kHalf16 / 64; i += kClThreads) s_w[i] = 0u;
+    __syncthreads();
+    const int area = g.th * g.tw;
+    const bool inside = (ty + 1) * g.th <= g.h && (tx + 1) * g.tw <= g.w;   // block-uniform: no reflect padding
+    for (int i = tid; i < area; i += kClThreads) {
+        const int yy = i / g.tw, xx = i - yy * g.tw;
+        int sy = ty * g.th + yy, sx = tx * g.tw + xx;
+        if (!inside) {
+            sy = border_index(sy, g.h, MIE_BORDER_REFLECT);
+            sx = border_index(sx, g.w, MIE_BORDER_REFLECT);
+        }
+        const uint32_t v = plane[(int64_t)sy * ssh + sx];
+        if ((v >> 15) == rank) atomicAdd(&s_w[padw((int)((v & 0x7FFFu) >> 1))], (v & 1u) ? 0x10000u : 1u);
+    }
+    __syncthreads();
+
+    const uint32_t* mine = s_w + tid * 33;       // words 32 tid .. 32 tid + 31 of this half
+    const uint32_t clip = (uint32_t)lp.clip;
+    int rb = 0, res = 0, step = 1;
+    if (lp.clip > 0) {
+        int local = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t wv = mine[k];
+            const uint32_t c0 = wv & 0xFFFFu, c1 = wv >> 16;
+            local += (int)(c0 > clip ? c0 - clip : 0u) + (int)(c1 > clip ? c1 - clip : 0u);
+        }
+        const int mine_clipped = block_sum_nw<kClThreads / 32>(local, s_red);
+        if (tid == 0) s_xchg[0] = mine_clipped;
+        cluster.sync();
+        const int clipped = mine_clipped + *cluster.map_shared_rank(&s_xchg[0], rank ^ 1u);
+        rb = clipped / kBins16;
+        res = clipped - rb * kBins16;
+        step = res ? max(kBins16 / res, 1) : 1;
+    }
+    const int u0 = (int)rank * kHalf16 + tid * 64;
+    int q = (u0 + step - 1) / step, next = q * step;
+    auto bin_value = [&](uint32_t c, int u) {
+        if (lp.clip > 0) {
+            c = min(c, clip) + (uint32_t)rb;
+            if (u == next) {
+                c += (res && q < res) ? 1u : 0u;
+                next += step; ++q;
+            }
+        }
+        return (int)c;
+    };
+    int sum = 0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t wv = mine[k];
+        sum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
+        sum += bin_value(wv >> 16, u0 + 2 * k + 1);
+    }
+    int total;
+    int cum = block_excl_scan_nw<kClThreads / 32>(sum, s_red, &total);
+    if (tid == 0) s_xchg[1] = total;
+    cluster.sync();
+    if (rank == 1) cum += *cluster.map_shared_rank(&s_xchg[1], 0u);   // the upper half continues the lower half's prefix
+    q = (u0 + step - 1) / step; next = q * step;
+    const float scale = lp.lut_scale;
+    auto lut_entry = [&](int c) {
+        const float f = __fsub_rn(__uint_as_float(0x4B000000u | (uint32_t)c), 8388608.0f);
+        const uint32_t r = __float_as_uint(__fadd_rn(__fmul_rn(f, scale), 12582912.0f)) - 0x4B400000u;
+        return min(r, 65535u);
+    };
+    uint4* dst = reinterpret_cast<uint4*>(luts + tile * (int64_t)kBins16 + u0);
+#pragma unroll 2
+    for (int k4 = 0; k4 < 8; ++k4) {
+        uint32_t packed[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 4 * k4 + j;
+            const uint32_t wv = mine[k];
+            cum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
+            const uint32_t e0 = lut_entry(cum);
+            cum += bin_value(wv >> 16, u0 + 2 * k + 1);
+            packed[j] = e0 | (lut_entry(cum) << 16);
+        }
+        dst[k4] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    cluster.sync();   // the peer may still be reading this CTA's s_xchg
+}
+
 // Interpolation pass (cv::CLAHE_Interpolation_Body, fp32 in OpenCV's operation order): 4 pixels per thread.
 __global__ void __launch_bounds__(256)
 clahe16_apply_kernel(const uint16_t* __restrict__ src, uint16_t* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
@@ -305,6 +448,15 @@ int clahe16_luts_impl(const void* src, int64_t n, int h, int w, int64_t ssn, int
     if (tiles > 2147483647LL) return MIE_E_SHAPE;
     const size_t smem = (size_t)(kHalf16 + kHalf16 / 32) * sizeof(int);
     static const bool no_small = [] { const char* e = getenv("MIE_CLAHE16_NO_SMALL"); return e && e[0] == '1'; }();
+    static const bool no_cluster = [] { const char* e = getenv("MIE_CLAHE16_NO_CLUSTER"); return e && e[0] == '1'; }();
+    if ((int64_t)g.th * g.tw < 65536 && !no_small && !no_cluster && tiles <= 1073741823LL) {
+        // counts fit 16 bits: single pass, one tile per cluster of two CTAs
+        const size_t csmem = (size_t)(kHalf16 / 2 + kHalf16 / 64) * sizeof(int);
+        MIE_ENSURE_SMEM(clahe16_lut_cluster_kernel, csmem);
+        clahe16_lut_cluster_kernel<<<(unsigned)(2 * tiles), kClThreads, csmem, st>>>((const uint16_t*)src, ssn, ssh, g,
+                                                                                  make_lut16_params(g, clip_limit), luts);
+        return check_launch();
+    }
     if ((int64_t)g.th * g.tw < 65536 && !no_small) {   // counts fit 16 bits: single-pass kernel
         MIE_ENSURE_SMEM(clahe16_lut_small_kernel, smem);
         clahe16_lut_small_kernel<<<(unsigned)tiles, kThreads16, smem, st>>>((const uint16_t*)src, ssn, ssh, g,
