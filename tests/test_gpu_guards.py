@@ -138,3 +138,21 @@ def test_guards_bilateral_metrics_chain(dev, dtype):
                                                        ws.ptr, ws.nbytes, _stream(dev)))
             g.check(f"chain {(n, h, w)} stages {stages}")
             ws.check(f"chain workspace {(n, h, w)} stages {stages}")
+
+
+def test_guards_clahe16(dev):
+    """65 536-bin CLAHE (cluster kernel for small tiles, two-sweep kernel for 256x256-pixel tiles): output and the
+    LUT workspace (groups of images) stay inside their buffers."""
+    from mie_b200 import _ffi
+
+    L = _ffi.lib()
+    for (n, h, w, gh, gw) in [(3, 512, 512, 8, 8), (2, 100, 130, 4, 6), (1, 512, 512, 2, 2), (5, 64, 64, 1, 1)]:
+        x = torch.from_numpy(_rand(np.uint16, (n, h, w), 6)).to(dev)
+        per_image = L.mie_clahe16_lut_bytes(gh, gw)
+        for images_in_ws in (1, 2):
+            g = Guarded(n * h * w * 2, dev)
+            ws = Guarded(per_image * images_in_ws, dev)
+            _ffi.check(L.mie_clahe(x.data_ptr(), g.ptr, 1, 1, n, h, w, h * w, w, h * w, w, gh, gw, 2.0, 1, 0.0, 65535.0,
+                                   ws.ptr, ws.nbytes, _stream(dev)))
+            g.check(f"clahe16 {(n, h, w)}")
+            ws.check(f"clahe16 workspace {(n, h, w)}")
