@@ -10,7 +10,7 @@ bool gauss_march_ok(const void* src, const void* dst, int sd, int dd, int h, int
                     int64_t dsn, int64_t dsh, int kx, int ky, int border, float lo, float hi);
 int launch_gauss_march(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
                        int64_t dsn, int64_t dsh, const Taps& wx, const Taps& wy, int border, int unsharp,
-                       cudaStream_t st);
+                       float lo, float hi, cudaStream_t st);
 
 struct GaussArgs {
     const void* src;
@@ -191,7 +191,7 @@ int gauss_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int
     // common geometry (square 9-tap kernel, W % 128 == 0, H % 64 == 0): marching kernel (gauss_march.cu)
     if ((!unsharp || (amount == 1.0f && !clip)) &&
         gauss_march_ok(src, dst, sd, dd, h, w, ssn, ssh, dsn, dsh, kx, ky, border, lo, hi))
-        return launch_gauss_march(src, dst, sd, dd, n, h, w, ssn, ssh, dsn, dsh, wx, wy, border, unsharp, st);
+        return launch_gauss_march(src, dst, sd, dd, n, h, w, ssn, ssh, dsn, dsh, wx, wy, border, unsharp, lo, hi, st);
     GaussArgs a;
     a.src = src; a.dst = dst; a.ssn = ssn; a.ssh = ssh; a.dsn = dsn; a.dsh = dsh;
     a.h = h; a.w = w; a.tiles_x = a.tiles_y = 0; a.border = border; a.unsharp = unsharp;

@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "march.cuh"
+#include "window.cuh"
 
 namespace mie {
 
@@ -18,9 +19,11 @@ struct GaussMarchArgs {
     int h, w;
 };
 
-template <typename SrcT, typename DstT, int BORDER, bool UNSHARP>
+// WIN: integer value_range window (csrc/window.cuh) — the divide-free windowed conversion on the way in and the
+// windowed quantisation on the way out; everything in between is the same fp32 arithmetic.
+template <typename SrcT, typename DstT, int BORDER, bool UNSHARP, bool WIN>
 __global__ void __launch_bounds__(256, 2)
-gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy) {
+gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy, WinCvt cv) {
     typedef typename Fast<SrcT>::raw4 raw4;
     extern __shared__ __align__(16) float smem[];
     const int W = a.w, T = blockDim.x, h = a.h;
@@ -75,8 +78,8 @@ gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy) {
         if (p % 2 == 0) mbar_wait(bar32 + 8 * ((p / 2) % kRawBars), (uint32_t)((p / 2 / kRawBars) & 1));
         const raw4 r0 = *reinterpret_cast<const raw4*>(my_raw + (rslot % kRawRows) * row_bytes);
         const raw4 r1 = *reinterpret_cast<const raw4*>(my_raw + ((rslot + 1) % kRawRows) * row_bytes);
-        Fast<SrcT>::cvt_raw4(r0, x0);
-        Fast<SrcT>::cvt_raw4(r1, x1);
+        PixIO<SrcT, WIN>::cvt_raw4(r0, x0, cv);
+        PixIO<SrcT, WIN>::cvt_raw4(r1, x1, cv);
         if (BORDER == MIE_BORDER_CONSTANT) {
             if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
             if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
@@ -123,25 +126,16 @@ gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) g[k] = __fadd_rn(c0[k], __fsub_rn(c0[k], g[k]));
             }
-            Fast<DstT>::store4(op, g);
+            PixIO<DstT, WIN>::store4(op, g, cv);
             op += dsh;
             march_col_pass(ring, 2 * q + 1, wy, g);
             if (UNSHARP) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) g[k] = __fadd_rn(c1[k], __fsub_rn(c1[k], g[k]));
             }
-            Fast<DstT>::store4(op, g);
+            PixIO<DstT, WIN>::store4(op, g, cv);
             op += dsh;
         }
-    }
-}
-
-static bool default_range_of(int dtype, float lo, float hi) {
-    switch (dtype) {
-        case MIE_U8: return lo == 0.0f && hi == 255.0f;
-        case MIE_U16: return lo == 0.0f && hi == 65535.0f;
-        case MIE_I16: return lo == -32768.0f && hi == 32767.0f;
-        default: return true;
     }
 }
 
@@ -154,46 +148,54 @@ bool gauss_march_ok(const void* src, const void* dst, int sd, int dd, int h, int
     if (w % 128 != 0 || w > 1024 || h % kTile != 0) return false;
     if (border == MIE_BORDER_CIRCULAR || border == MIE_BORDER_SYMMETRIC) return false;
     if (dd != sd && dd != MIE_F32) return false;
-    if (!default_range_of(sd, lo, hi) || !default_range_of(dd, lo, hi)) return false;
+    WinCvt cv;
+    if (range_mode(sd, lo, hi, &cv) < 0) return false;   // default range, or an integer window the host has verified
     if (((uintptr_t)src % 16) || ((ssn * esz[sd]) % 16) || ((ssh * esz[sd]) % 16)) return false;
     if (((uintptr_t)dst % 16) || ((dsn * esz[dd]) % 16) || ((dsh * esz[dd]) % 16)) return false;
     if ((int64_t)h * ssh * 4 >= (1LL << 31)) return false;  // 32-bit source-row offsets
     return true;
 }
 
-template <typename SrcT, typename DstT, int BORDER>
+template <typename SrcT, typename DstT, int BORDER, bool WIN>
 static int launch_gm_b(const GaussMarchArgs& a, const Taps& wx, const Taps& wy, int unsharp, unsigned blocks,
-                       cudaStream_t st) {
+                       const WinCvt& cv, cudaStream_t st) {
     const int T = a.w / 4;
     const size_t smem = (size_t)(4 * 8 * (T + 2) + kMOffRows) * 4 + kRawBars * 8 + (size_t)kRawRows * a.w * sizeof(SrcT);
     if (unsharp) {
-        MIE_ENSURE_SMEM((gauss_march_kernel<SrcT, DstT, BORDER, true>), 100 * 1024);
-        gauss_march_kernel<SrcT, DstT, BORDER, true><<<blocks, T, smem, st>>>(a, wx, wy);
+        MIE_ENSURE_SMEM((gauss_march_kernel<SrcT, DstT, BORDER, true, WIN>), 100 * 1024);
+        gauss_march_kernel<SrcT, DstT, BORDER, true, WIN><<<blocks, T, smem, st>>>(a, wx, wy, cv);
     } else {
-        MIE_ENSURE_SMEM((gauss_march_kernel<SrcT, DstT, BORDER, false>), 100 * 1024);
-        gauss_march_kernel<SrcT, DstT, BORDER, false><<<blocks, T, smem, st>>>(a, wx, wy);
+        MIE_ENSURE_SMEM((gauss_march_kernel<SrcT, DstT, BORDER, false, WIN>), 100 * 1024);
+        gauss_march_kernel<SrcT, DstT, BORDER, false, WIN><<<blocks, T, smem, st>>>(a, wx, wy, cv);
     }
     return check_launch();
 }
 
-template <typename SrcT, typename DstT>
+template <typename SrcT, typename DstT, bool WIN>
 static int launch_gm(const GaussMarchArgs& a, const Taps& wx, const Taps& wy, int border, int unsharp, unsigned blocks,
-                     cudaStream_t st) {
+                     const WinCvt& cv, cudaStream_t st) {
     switch (border) {
-        case MIE_BORDER_REFLECT: return launch_gm_b<SrcT, DstT, MIE_BORDER_REFLECT>(a, wx, wy, unsharp, blocks, st);
-        case MIE_BORDER_REPLICATE: return launch_gm_b<SrcT, DstT, MIE_BORDER_REPLICATE>(a, wx, wy, unsharp, blocks, st);
-        default: return launch_gm_b<SrcT, DstT, MIE_BORDER_CONSTANT>(a, wx, wy, unsharp, blocks, st);
+        case MIE_BORDER_REFLECT: return launch_gm_b<SrcT, DstT, MIE_BORDER_REFLECT, WIN>(a, wx, wy, unsharp, blocks, cv, st);
+        case MIE_BORDER_REPLICATE: return launch_gm_b<SrcT, DstT, MIE_BORDER_REPLICATE, WIN>(a, wx, wy, unsharp, blocks, cv, st);
+        default: return launch_gm_b<SrcT, DstT, MIE_BORDER_CONSTANT, WIN>(a, wx, wy, unsharp, blocks, cv, st);
     }
 }
 
 int launch_gauss_march(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
                        int64_t dsn, int64_t dsh, const Taps& wx, const Taps& wy, int border, int unsharp,
-                       cudaStream_t st) {
+                       float lo, float hi, cudaStream_t st) {
+    WinCvt cv = {};
+    const int mode = range_mode(sd, lo, hi, &cv);
+    if (mode < 0) return MIE_E_UNSUPPORTED;   // callers test gauss_march_ok first
     GaussMarchArgs a;
     a.src = src; a.dst = dst; a.ssn = ssn; a.ssh = ssh; a.dsn = dsn; a.dsh = dsh; a.h = h; a.w = w;
     const int64_t blocks = n * (h / kTile);
     if (blocks > 2147483647LL) return MIE_E_SHAPE;
-    MIE_DISPATCH_SRC_DST(sd, dd, return (launch_gm<SrcT, DstT>(a, wx, wy, border, unsharp, (unsigned)blocks, st)));
+    if (mode == 1) {
+        MIE_DISPATCH_SRC_DST(sd, dd, return (launch_gm<SrcT, DstT, true>(a, wx, wy, border, unsharp, (unsigned)blocks, cv, st)));
+    } else {
+        MIE_DISPATCH_SRC_DST(sd, dd, return (launch_gm<SrcT, DstT, false>(a, wx, wy, border, unsharp, (unsigned)blocks, cv, st)));
+    }
     return MIE_OK;
 }
 

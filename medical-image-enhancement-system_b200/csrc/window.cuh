@@ -31,6 +31,7 @@ struct PixIO {   // WIN == false: the default-range conversions of chain_fast.cu
     static __device__ __forceinline__ void load8(const T* p, float* x, const WinCvt&) { Fast<T>::load8(p, x); }
     static __device__ __forceinline__ void load4(const T* p, float* x, const WinCvt&) { Fast<T>::load4(p, x); }
     static __device__ __forceinline__ void store4(T* p, const float* y, const WinCvt&) { Fast<T>::store4(p, y); }
+    static __device__ __forceinline__ void cvt_raw4(typename Fast<T>::raw4 r, float* x, const WinCvt&) { Fast<T>::cvt_raw4(r, x); }
 };
 __device__ __forceinline__ float win_one(uint32_t mant_bits, const WinCvt& c) {
     const float a = __fsub_rn(__uint_as_float(mant_bits), c.in_magic);
@@ -54,6 +55,7 @@ struct PixIO<uint16_t, true> {
         const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
         cvt2(b.x, x, c); cvt2(b.y, x + 2, c);
     }
+    static __device__ __forceinline__ void cvt_raw4(uint2 r, float* x, const WinCvt& c) { cvt2(r.x, x, c); cvt2(r.y, x + 2, c); }
     static __device__ __forceinline__ void store4(uint16_t* p, const float* y, const WinCvt& c) {
         uint2 o;
         o.x = __byte_perm(win_quant(y[0], c), win_quant(y[1], c), 0x5410);
@@ -71,6 +73,9 @@ struct PixIO<int16_t, true> {   // v + 32768 by flipping the sign bit; the bias 
     static __device__ __forceinline__ void load4(const int16_t* p, float* x, const WinCvt& c) {
         const uint2 b = __ldg(reinterpret_cast<const uint2*>(p));
         PixIO<uint16_t, true>::cvt2(b.x ^ 0x80008000u, x, c); PixIO<uint16_t, true>::cvt2(b.y ^ 0x80008000u, x + 2, c);
+    }
+    static __device__ __forceinline__ void cvt_raw4(uint2 r, float* x, const WinCvt& c) {
+        PixIO<uint16_t, true>::cvt2(r.x ^ 0x80008000u, x, c); PixIO<uint16_t, true>::cvt2(r.y ^ 0x80008000u, x + 2, c);
     }
     static __device__ __forceinline__ void store4(int16_t* p, const float* y, const WinCvt& c) {
         PixIO<uint16_t, true>::store4(reinterpret_cast<uint16_t*>(p), y, c);   // two's complement low halves
@@ -91,6 +96,7 @@ struct PixIO<uint8_t, true> {
     static __device__ __forceinline__ void load4(const uint8_t* p, float* x, const WinCvt& c) {
         cvt4(__ldg(reinterpret_cast<const uint32_t*>(p)), x, c);
     }
+    static __device__ __forceinline__ void cvt_raw4(uint32_t r, float* x, const WinCvt& c) { cvt4(r, x, c); }
     static __device__ __forceinline__ void store4(uint8_t* p, const float* y, const WinCvt& c) {
         *reinterpret_cast<uint32_t*>(p) = pack_low_bytes(win_quant(y[0], c), win_quant(y[1], c), win_quant(y[2], c),
                                                          win_quant(y[3], c));

@@ -310,6 +310,26 @@ def test_gaussian_and_unsharp_bit_exact(dev, dtype, op):
             assert np.array_equal(gq, O.from01(ref, dtype)), (shape, k, border)
 
 
+@pytest.mark.parametrize("case", [(np.int16, (-1024.0, 3071.0)), (np.uint16, (0.0, 4095.0)), (np.uint8, (10.0, 200.0))])
+@pytest.mark.parametrize("op", ["gaussian_blur2d", "unsharp_mask"])
+def test_gaussian_and_unsharp_integer_windows_on_marching_kernels(dev, case, op):
+    """value_range windows with integer bounds on the marching kernels (windowed conversion in, windowed
+    quantisation out): bit-exact against the oracle, float and integer output, every border the kernels take."""
+    import mie_b200 as M
+    import oracle as O
+
+    dtype, vr = case
+    for shape in [(2, 1, 128, 256), (1, 1, 64, 512), (3, 1, 192, 128)]:
+        x = images("U", shape, dtype, seed=51)          # full dtype range: pixels on both sides of the window
+        x01 = O.to01(x, vr)
+        xt = gpu(x, dev)
+        for border in ("reflect", "replicate", "constant"):
+            ref = getattr(O, op)(x01, 9, 1.0, border)
+            got = cpu(getattr(M, op)(xt, 9, 1.0, border, value_range=vr, out_dtype=torch.float32))
+            assert np.array_equal(got, ref), (shape, border)
+            assert np.array_equal(cpu(getattr(M, op)(xt, 9, 1.0, border, value_range=vr)), O.from01(ref, dtype, vr)), (shape, border)
+
+
 def test_gaussian_against_independent_binaries(dev):
     """cv2.GaussianBlur(BORDER_REFLECT_101) and scipy.ndimage.gaussian_filter(mode='mirror') use the same
     weights and border; they agree with the kernel to fp32 rounding."""
