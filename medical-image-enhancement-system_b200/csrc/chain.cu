@@ -16,7 +16,7 @@
 // non-square or > 9-tap kernels) run those three stages unfused.
 #include <cstdlib>
 
-#include "chain_fast.cuh"
+#include "window.cuh"
 
 namespace mie {
 
@@ -312,24 +312,29 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     a.src = src; a.ssn = src_stride_n; a.ssh = src_stride_h; a.idx = plane; a.luts = luts; a.g = g;
     a.lp = make_lut_params(g, clip_limit, MIE_CLAHE_KORNIA);
     a.border = border; a.lo = lo; a.rg = hi - lo;
-    const bool fast = fast_chain_ok(g, src_dtype, dst_dtype, src, src_stride_n, src_stride_h, dst, dst_stride_n,
-                                    dst_stride_h, kgx, kux, border, lo, hi);
+    bool windowed = false;   // integer value_range window: only the marching kernels implement it
+    const bool fast_geo = fast_chain_ok(g, src_dtype, dst_dtype, src, src_stride_n, src_stride_h, dst, dst_stride_n,
+                                        dst_stride_h, kgx, kux, border, lo, hi, &windowed);
+    WinCvt cv = {};
+    if (windowed) range_mode(src_dtype, lo, hi, &cv);
     ChainBArgs b;
     b.idx = plane; b.luts = luts; b.dst = dst; b.dsn = dst_stride_n; b.dsh = dst_stride_h; b.g = g;
     b.tiles_x = ceil_div(w, kTile); b.tiles_y = ceil_div(h, kTile); b.border = border; b.max_lut_tiles = lut_cap;
     b.lo = lo; b.rg = hi - lo;
     if (n * (int64_t)b.tiles_x * b.tiles_y > 2147483647LL) return MIE_E_SHAPE;
+    // The marching kernels run one block per 64-row band: unbeatable once the bands fill the machine, but a
+    // single 512x512 slice is 8 blocks walking 72 rows each (30.8 us for the step against 12.3 us with one
+    // block per 64x64 tile).  Measured crossover on B200: ~24 slices of 512x512 (benchmarks/
+    // chain_latency_probe.py), i.e. about 1.5 band-blocks per SM.
+    const bool enough_bands = n * (int64_t)g.gh >= 222;
+    const bool march = fast_geo && march_chain_ok(g, kgx, kux) && !g_disable_march &&
+                       !(hints & MIE_CHAIN_PREFER_TILES) && (enough_bands || (hints & MIE_CHAIN_PREFER_MARCH)) &&
+                       (int64_t)h * src_stride_h * 4 < (1LL << 31);  // 32-bit source-row offsets
+    const bool fast = fast_geo && (!windowed || march);
+    const WinCvt* win = windowed ? &cv : nullptr;
     if (fast) {
-        // The marching kernels run one block per 64-row band: unbeatable once the bands fill the machine, but a
-        // single 512x512 slice is 8 blocks walking 72 rows each (30.8 us for the step against 12.3 us with one
-        // block per 64x64 tile).  Measured crossover on B200: ~24 slices of 512x512 (benchmarks/
-        // chain_latency_probe.py), i.e. about 1.5 band-blocks per SM.
-        const bool enough_bands = n * (int64_t)g.gh >= 222;
-        const bool march = march_chain_ok(g, kgx, kux) && !g_disable_march && !(hints & MIE_CHAIN_PREFER_TILES) &&
-                           (enough_bands || (hints & MIE_CHAIN_PREFER_MARCH)) &&
-                           (int64_t)h * src_stride_h * 4 < (1LL << 31);  // 32-bit source-row offsets
         if (stages & MIE_CHAIN_STAGE_A) {
-            rc = march ? launch_chain_a_march(a, src_dtype, tgx, tgy, n, st)
+            rc = march ? launch_chain_a_march(a, src_dtype, tgx, tgy, n, st, win)
                        : launch_chain_a_fast(a, src_dtype, tgx, tgy, kgx / 2, n, st);
             if (rc) return rc;
         }
@@ -339,7 +344,7 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
             // 2 (gh+1)(gw+1) KB <= 3 bytes per pixel for 64x64-pixel tiles)
             size_t off = ((size_t)n * gh * gw * kBins + (size_t)n * h * w + 255) & ~(size_t)255;
             if (off + chain_cells_bytes(n, gh, gw) > workspace_bytes) return MIE_E_WORKSPACE;
-            return march ? launch_chain_b_march(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st)
+            return march ? launch_chain_b_march(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st, win)
                          : launch_chain_b_fast(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st);
         }
         stages = MIE_CHAIN_STAGE_B;  // other unsharp sizes: generic chain_b on the same index plane / LUTs

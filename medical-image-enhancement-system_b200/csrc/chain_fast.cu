@@ -1,7 +1,7 @@
 // chain_fast.cu — tuned kernels of the fused Gaussian -> CLAHE -> unsharp chain for
 // 64x64-pixel CLAHE tiles (see chain_fast.cuh for the instruction-level tricks and
 // chain.cu for the algorithm and the generic kernels these two must equal bit for bit).
-#include "chain_fast.cuh"
+#include "window.cuh"
 
 namespace mie {
 
@@ -274,12 +274,17 @@ static bool default_range(int dtype, float lo, float hi) {
 }
 
 bool fast_chain_ok(const ClaheGeom& g, int sd, int dd, const void* src, int64_t ssn, int64_t ssh, const void* dst,
-                   int64_t dsn, int64_t dsh, int kg, int ku, int border, float lo, float hi) {
+                   int64_t dsn, int64_t dsh, int kg, int ku, int border, float lo, float hi, bool* windowed) {
     static const int esz[4] = {1, 2, 2, 4};
     if (g.th != kTile || g.tw != kTile || g.hp != g.h || g.wp != g.w) return false;
     if (kg < 3 || kg > 9 || ku < 3 || ku > 9) return false;
     if (border == MIE_BORDER_CIRCULAR || border == MIE_BORDER_SYMMETRIC) return false;
-    if (!default_range(sd, lo, hi) || !default_range(dd, lo, hi)) return false;
+    if (windowed) *windowed = false;
+    if (!default_range(sd, lo, hi) || !default_range(dd, lo, hi)) {
+        WinCvt cv;
+        if (!windowed || range_mode(sd, lo, hi, &cv) != 1) return false;
+        *windowed = true;
+    }
     // 16-byte aligned rows for the vector loads / stores
     if (((uintptr_t)src % 16) || ((ssn * esz[sd]) % 16) || ((ssh * esz[sd]) % 16)) return false;
     if (((uintptr_t)dst % 16) || ((dsn * esz[dd]) % 16) || ((dsh * esz[dd]) % 16)) return false;

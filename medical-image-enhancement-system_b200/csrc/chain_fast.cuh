@@ -54,8 +54,12 @@ struct ChainBArgs {
 };
 
 // Defined in chain_fast.cu.  `fast_chain_ok` tells whether the tuned kernels cover the request.
+// `windowed` (optional): set when the range is not the dtype's default but an integer window the windowed
+// conversion of window.cuh can take — only the marching kernels implement it, the caller decides.
+struct WinCvt;
 bool fast_chain_ok(const ClaheGeom& g, int src_dtype, int dst_dtype, const void* src, int64_t ssn, int64_t ssh,
-                   const void* dst, int64_t dsn, int64_t dsh, int kg, int ku, int border, float lo, float hi);
+                   const void* dst, int64_t dsn, int64_t dsh, int kg, int ku, int border, float lo, float hi,
+                   bool* windowed = nullptr);
 int launch_chain_a_fast(const ChainAArgs& a, int src_dtype, const Taps& wx, const Taps& wy, int R, int64_t n,
                         cudaStream_t st);
 size_t chain_cells_bytes(int64_t n, int gh, int gw);
@@ -399,8 +403,8 @@ inline void fill_axis_weights(AxisWeights& aw) {
 // Marching kernels (chain_march.cu): full-width 64-row bands, 9-tap Gaussians, W % 128 == 0, W <= 1024.
 bool march_chain_ok(const ClaheGeom& g, int kg, int ku);
 int launch_chain_a_march(const ChainAArgs& a, int src_dtype, const Taps& wx, const Taps& wy, int64_t n,
-                         cudaStream_t st);
+                         cudaStream_t st, const WinCvt* win = nullptr);
 int launch_chain_b_march(const ChainBArgs& b, int dst_dtype, void* cells, const Taps& wx, const Taps& wy, int64_t n,
-                         cudaStream_t st);
+                         cudaStream_t st, const WinCvt* win = nullptr);
 
 }  // namespace mie

@@ -20,6 +20,7 @@
 #include <cstdlib>
 
 #include "march.cuh"
+#include "window.cuh"
 
 namespace mie {
 
@@ -30,11 +31,14 @@ namespace mie {
 // histogram).  After the walk each warp turns tile histograms into LUTs.
 // LE1: the host has proven that every blurred value lies in [0, 1] (integer pixels and
 // gauss_of_ones_le1), which removes the range tests from the index / bin rules.
-template <typename SrcT, int BORDER, bool LE1, int MAXT, int MINB>
+// WIN: integer value_range window (window.cuh): windowed conversion of the source pixels; the blurred values can
+// then lie outside [0, 1], so bins and lookups take the range-checked rules of float pixels.
+template <typename SrcT, int BORDER, bool LE1, int MAXT, int MINB, bool WIN = false>
 __global__ void __launch_bounds__(MAXT, MINB)
-chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
+chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
     typedef typename Fast<SrcT>::raw4 raw4;
-    constexpr bool NN = !(sizeof(SrcT) == 4);
+    constexpr bool NN = !(sizeof(SrcT) == 4) && !WIN;
+    static_assert(!(LE1 && WIN), "a window gives no [0, 1] guarantee");
     static_assert(!LE1 || NN, "LE1 needs integer pixels");
     extern __shared__ __align__(16) float smem[];
     const int W = a.g.w, T = blockDim.x, gw = a.g.gw, h = a.g.h;
@@ -99,8 +103,8 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy) {
         if (p % 2 == 0) mbar_wait(bar32 + 8 * ((p / 2) % kRawBars), (uint32_t)((p / 2 / kRawBars) & 1));
         const raw4 r0 = *reinterpret_cast<const raw4*>(my_raw + (rslot % kRawRows) * row_bytes);
         const raw4 r1 = *reinterpret_cast<const raw4*>(my_raw + ((rslot + 1) % kRawRows) * row_bytes);
-        Fast<SrcT>::cvt_raw4(r0, x0);
-        Fast<SrcT>::cvt_raw4(r1, x1);
+        PixIO<SrcT, WIN>::cvt_raw4(r0, x0, cv);
+        PixIO<SrcT, WIN>::cvt_raw4(r1, x1, cv);
         if (BORDER == MIE_BORDER_CONSTANT) {
             if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
             if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
@@ -178,9 +182,9 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     return v;
 }
 
-template <typename DstT, int BORDER>
+template <typename DstT, int BORDER, bool WIN = false>
 __global__ void __launch_bounds__(256)
-chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy) {
+chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy, WinCvt cv) {
     extern __shared__ __align__(16) float smem[];
     const int W = a.g.w, T = blockDim.x, gw = a.g.gw, gh = a.g.gh, h = a.g.h;
     const int pbuf = pairbuf_floats(T);
@@ -280,12 +284,12 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
             march_col_pass(ring, 2 * q, wy, g);
 #pragma unroll
             for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(c0[k], __fsub_rn(c0[k], g[k]));
-            Fast<DstT>::store4(op, y);
+            PixIO<DstT, WIN>::store4(op, y, cv);
             op += dsh;
             march_col_pass(ring, 2 * q + 1, wy, g);
 #pragma unroll
             for (int k = 0; k < 4; ++k) y[k] = __fadd_rn(c1[k], __fsub_rn(c1[k], g[k]));
-            Fast<DstT>::store4(op, y);
+            PixIO<DstT, WIN>::store4(op, y, cv);
             op += dsh;
         }
     }
@@ -319,75 +323,99 @@ static bool gauss_of_ones_le1(const Taps& wx, const Taps& wy) {
     return r <= 1.0f && c <= 1.0f;
 }
 
+template <typename SrcT, int BORDER>
+static int launch_a_march_win(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st,
+                              const WinCvt& cv) {
+    const size_t smem = march_a_smem(a.g, (int)sizeof(SrcT));
+    if (a.g.w <= 512) {
+        MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, false, 128, 5, true>), 100 * 1024);
+        chain_a_march_kernel<SrcT, BORDER, false, 128, 5, true><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
+    } else {
+        MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, false, 256, 2, true>), 100 * 1024);
+        chain_a_march_kernel<SrcT, BORDER, false, 256, 2, true><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
+    }
+    return check_launch();
+}
 template <typename SrcT, int BORDER, bool LE1>
 static int launch_a_march_tbl(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st) {
+    const WinCvt cv = {};
     // W <= 512: 128 threads per block, registers capped so that MINB blocks fit on an SM
     static const int minb_env = [] { const char* e = getenv("MIE_MARCH_A_MINB"); return e ? atoi(e) : 5; }();
     const size_t smem = march_a_smem(a.g, (int)sizeof(SrcT));
     if (a.g.w <= 512) {
         if (minb_env >= 6) {
             MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 6>), 100 * 1024);
-            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 6><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy);
+            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 6><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
         } else if (minb_env == 5) {
             MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5>), 100 * 1024);
-            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy);
+            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
         } else {
             MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 4>), 100 * 1024);
-            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 4><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy);
+            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 4><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
         }
     } else {
         MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2>), 100 * 1024);
-        chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy);
+        chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
     }
     return check_launch();
 }
 template <typename SrcT, int BORDER>
-static int launch_a_march_tb(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st) {
+static int launch_a_march_tb(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st,
+                             const WinCvt* win) {
+    if (win) return launch_a_march_win<SrcT, BORDER>(a, wx, wy, blocks, st, *win);
     if constexpr (sizeof(SrcT) != 4) {
         if (gauss_of_ones_le1(wx, wy)) return launch_a_march_tbl<SrcT, BORDER, true>(a, wx, wy, blocks, st);
     }
     return launch_a_march_tbl<SrcT, BORDER, false>(a, wx, wy, blocks, st);
 }
 template <typename SrcT>
-static int launch_a_march_t(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st) {
+static int launch_a_march_t(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st,
+                            const WinCvt* win) {
     switch (a.border) {
-        case MIE_BORDER_REFLECT: return launch_a_march_tb<SrcT, MIE_BORDER_REFLECT>(a, wx, wy, blocks, st);
-        case MIE_BORDER_REPLICATE: return launch_a_march_tb<SrcT, MIE_BORDER_REPLICATE>(a, wx, wy, blocks, st);
-        default: return launch_a_march_tb<SrcT, MIE_BORDER_CONSTANT>(a, wx, wy, blocks, st);
+        case MIE_BORDER_REFLECT: return launch_a_march_tb<SrcT, MIE_BORDER_REFLECT>(a, wx, wy, blocks, st, win);
+        case MIE_BORDER_REPLICATE: return launch_a_march_tb<SrcT, MIE_BORDER_REPLICATE>(a, wx, wy, blocks, st, win);
+        default: return launch_a_march_tb<SrcT, MIE_BORDER_CONSTANT>(a, wx, wy, blocks, st, win);
     }
 }
 
-int launch_chain_a_march(const ChainAArgs& a, int sd, const Taps& wx, const Taps& wy, int64_t n, cudaStream_t st) {
+int launch_chain_a_march(const ChainAArgs& a, int sd, const Taps& wx, const Taps& wy, int64_t n, cudaStream_t st,
+                         const WinCvt* win) {
     const unsigned blocks = (unsigned)(n * a.g.gh);
-    MIE_DISPATCH_SRC(sd, return launch_a_march_t<SrcT>(a, wx, wy, blocks, st));
+    MIE_DISPATCH_SRC(sd, return launch_a_march_t<SrcT>(a, wx, wy, blocks, st, win));
     return MIE_OK;
 }
 
 template <typename DstT, int BORDER>
 static int launch_b_march_tb(const ChainBArgs& b, const uint2* cells, const AxisWeights& aw, const Taps& wx,
-                             const Taps& wy, unsigned blocks, cudaStream_t st) {
-    MIE_ENSURE_SMEM((chain_b_march_kernel<DstT, BORDER>), 128 * 1024);
-    chain_b_march_kernel<DstT, BORDER><<<blocks, b.g.w / 4, march_b_smem(b.g), st>>>(b, cells, aw, wx, wy);
+                             const Taps& wy, unsigned blocks, cudaStream_t st, const WinCvt* win) {
+    if (win) {
+        MIE_ENSURE_SMEM((chain_b_march_kernel<DstT, BORDER, true>), 128 * 1024);
+        chain_b_march_kernel<DstT, BORDER, true><<<blocks, b.g.w / 4, march_b_smem(b.g), st>>>(b, cells, aw, wx, wy, *win);
+    } else {
+        const WinCvt cv = {};
+        MIE_ENSURE_SMEM((chain_b_march_kernel<DstT, BORDER, false>), 128 * 1024);
+        chain_b_march_kernel<DstT, BORDER, false><<<blocks, b.g.w / 4, march_b_smem(b.g), st>>>(b, cells, aw, wx, wy, cv);
+    }
     return check_launch();
 }
 template <typename DstT>
 static int launch_b_march_t(const ChainBArgs& b, const uint2* cells, const AxisWeights& aw, const Taps& wx,
-                            const Taps& wy, unsigned blocks, cudaStream_t st) {
+                            const Taps& wy, unsigned blocks, cudaStream_t st, const WinCvt* win) {
     switch (b.border) {
-        case MIE_BORDER_REFLECT: return launch_b_march_tb<DstT, MIE_BORDER_REFLECT>(b, cells, aw, wx, wy, blocks, st);
-        case MIE_BORDER_REPLICATE: return launch_b_march_tb<DstT, MIE_BORDER_REPLICATE>(b, cells, aw, wx, wy, blocks, st);
-        default: return launch_b_march_tb<DstT, MIE_BORDER_CONSTANT>(b, cells, aw, wx, wy, blocks, st);
+        case MIE_BORDER_REFLECT: return launch_b_march_tb<DstT, MIE_BORDER_REFLECT>(b, cells, aw, wx, wy, blocks, st, win);
+        case MIE_BORDER_REPLICATE: return launch_b_march_tb<DstT, MIE_BORDER_REPLICATE>(b, cells, aw, wx, wy, blocks, st, win);
+        default: return launch_b_march_tb<DstT, MIE_BORDER_CONSTANT>(b, cells, aw, wx, wy, blocks, st, win);
     }
 }
 
 int launch_chain_b_march(const ChainBArgs& b, int dd, void* cells_raw, const Taps& wx, const Taps& wy, int64_t n,
-                         cudaStream_t st) {
+                         cudaStream_t st, const WinCvt* win) {
     int rc = launch_pack_cells(b.luts, cells_raw, n, b.g.gh, b.g.gw, st);
     if (rc) return rc;
     AxisWeights aw;
     fill_axis_weights(aw);
     const unsigned blocks = (unsigned)(n * b.g.gh);
-    MIE_DISPATCH_SRC(dd, return launch_b_march_t<SrcT>(b, (const uint2*)cells_raw, aw, wx, wy, blocks, st));
+    MIE_DISPATCH_SRC(dd, return launch_b_march_t<SrcT>(b, (const uint2*)cells_raw, aw, wx, wy, blocks, st, win));
     return MIE_OK;
 }
 

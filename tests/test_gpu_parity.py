@@ -452,6 +452,35 @@ def test_chain_plan_graph_replay(dev):
     assert not np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("case", [(np.int16, (-1024.0, 3071.0)), (np.uint16, (0.0, 4095.0)), (np.uint8, (10.0, 200.0))])
+def test_chain_integer_windows_on_marching_kernels(dev, case):
+    """value_range windows with integer bounds (HU window, 12-bit data) on the marching chain kernels: the windowed
+    conversion on the way in, range-checked bins / lookups, windowed quantisation on the way out — bit-exact against
+    the oracle for every border; the default schedule of a small job (generic kernels) gives the same bits."""
+    import mie_b200 as M
+    import oracle as O
+
+    dtype, vr = case
+    for shape, grid in [((2, 1, 128, 256), (2, 4)), ((3, 1, 192, 384), (3, 6)), ((1, 1, 512, 512), (8, 8))]:
+        x = images("U", shape, dtype, seed=61)            # full dtype range: pixels on both sides of the window
+        x[..., : shape[-2] // 2, :] = images("P", shape, dtype, seed=62)[..., : shape[-2] // 2, :]
+        xt = gpu(x, dev)
+        for border in ("reflect", "replicate", "constant"):
+            cfg = M.ChainConfig(grid_size=grid, border_type=border, value_range=vr)
+            ref = O.chain_gauss_clahe_unsharp(x, 9, 1.0, 2.0, grid, 9, 1.0, border, value_range=vr)
+            got = cpu(M.enhance_chain(xt, cfg, stages=3 | 4))
+            assert np.array_equal(got, ref), (shape, border, int((got != ref).sum()))
+            assert np.array_equal(cpu(M.enhance_chain(xt, cfg)), ref), (shape, border)
+        cfg = M.ChainConfig(grid_size=grid, value_range=vr)
+        reff = O.chain_gauss_clahe_unsharp(x, 9, 1.0, 2.0, grid, 9, 1.0, "reflect", value_range=vr, out_dtype=np.float32)
+        assert np.array_equal(cpu(M.enhance_chain(xt, cfg, out_dtype=torch.float32, stages=3 | 4)), reff), shape
+    # a full-size windowed batch takes the marching kernels by itself
+    x = images("P", (32, 1, 512, 512), dtype, seed=63)
+    cfg = M.ChainConfig(value_range=vr)
+    ref = O.chain_gauss_clahe_unsharp(x, value_range=vr)
+    assert np.array_equal(cpu(M.enhance_chain(gpu(x, dev), cfg)), ref)
+
+
 def test_chain_ring_round_robin(dev):
     """ChainRing: independent batches replayed round-robin on their own streams give the same bits as
     direct calls, for one, two and three slots, also when the inputs are refilled between rounds."""
