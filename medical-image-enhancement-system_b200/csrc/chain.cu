@@ -312,7 +312,7 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     a.src = src; a.ssn = src_stride_n; a.ssh = src_stride_h; a.idx = plane; a.luts = luts; a.g = g;
     a.lp = make_lut_params(g, clip_limit, MIE_CLAHE_KORNIA);
     a.border = border; a.lo = lo; a.rg = hi - lo;
-    bool windowed = false;   // integer value_range window: only the marching kernels implement it
+    bool windowed = false;   // integer value_range window (window.cuh)
     const bool fast_geo = fast_chain_ok(g, src_dtype, dst_dtype, src, src_stride_n, src_stride_h, dst, dst_stride_n,
                                         dst_stride_h, kgx, kux, border, lo, hi, &windowed);
     WinCvt cv = {};
@@ -330,12 +330,12 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     const bool march = fast_geo && march_chain_ok(g, kgx, kux) && !g_disable_march &&
                        !(hints & MIE_CHAIN_PREFER_TILES) && (enough_bands || (hints & MIE_CHAIN_PREFER_MARCH)) &&
                        (int64_t)h * src_stride_h * 4 < (1LL << 31);  // 32-bit source-row offsets
-    const bool fast = fast_geo && (!windowed || march);
+    const bool fast = fast_geo;
     const WinCvt* win = windowed ? &cv : nullptr;
     if (fast) {
         if (stages & MIE_CHAIN_STAGE_A) {
             rc = march ? launch_chain_a_march(a, src_dtype, tgx, tgy, n, st, win)
-                       : launch_chain_a_fast(a, src_dtype, tgx, tgy, kgx / 2, n, st);
+                       : launch_chain_a_fast(a, src_dtype, tgx, tgy, kgx / 2, n, st, win);
             if (rc) return rc;
         }
         if (!(stages & MIE_CHAIN_STAGE_B)) return MIE_OK;
@@ -345,7 +345,7 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
             size_t off = ((size_t)n * gh * gw * kBins + (size_t)n * h * w + 255) & ~(size_t)255;
             if (off + chain_cells_bytes(n, gh, gw) > workspace_bytes) return MIE_E_WORKSPACE;
             return march ? launch_chain_b_march(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st, win)
-                         : launch_chain_b_fast(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st);
+                         : launch_chain_b_fast(b, dst_dtype, (uint8_t*)workspace + off, tux, tuy, n, st, win);
         }
         stages = MIE_CHAIN_STAGE_B;  // other unsharp sizes: generic chain_b on the same index plane / LUTs
     }

@@ -13,11 +13,12 @@ namespace mie {
 //   epilogue   : lookup index -> 32-bit stores into the index plane; histogram bin ->
 //                ATOMS.POPC.INC into the block histogram;
 //   LUT        : warp 8 clips / redistributes / scans (8 bins per lane).
-template <typename SrcT, int R>
+template <typename SrcT, int R, bool WIN>
 __global__ void __launch_bounds__(kFastThreads)
-chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
+chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
     constexpr int ROWS = kTile + 2 * R;
-    constexpr bool NN = !(sizeof(SrcT) == 4);  // integer pixels: blurred values are >= 0 and finite
+    // default-range integer pixels: blurred values are >= 0 and finite; windows (WIN) take the float rules
+    constexpr bool NN = !(sizeof(SrcT) == 4) && !WIN;
     __shared__ __align__(16) float s_mid[ROWS * kPMa];
     __shared__ __align__(16) int s_hist[kBins + 8];  // [256] = dummy slot for ignored pixels
 
@@ -40,7 +41,7 @@ chain_a_fast_kernel(ChainAArgs a, Taps wx, Taps wy) {
 #pragma unroll
             for (int k = 0; k < 24; ++k) x[k] = 0.0f;
         } else {
-            load_row24<SrcT>(plane + (int64_t)sy * a.ssh, tx0 + 16 * s, w, a.border, x);
+            load_row24_win<SrcT, WIN>(plane + (int64_t)sy * a.ssh, tx0 + 16 * s, w, a.border, x, cv);
         }
         float* mrow = s_mid + r * kPMa + 8 * s;
 #pragma unroll
@@ -119,9 +120,9 @@ chain_pack_cells_kernel(const uint8_t* __restrict__ luts, uint2* __restrict__ ce
 //   C pass : CLAHE output C for every haloed pixel -> s_in;
 //   row / col pass, epilogue: C + (C - blur(C)) -> quantise -> 64-bit stores.
 
-template <typename DstT>
+template <typename DstT, bool WIN>
 __global__ void __launch_bounds__(kFastThreads)
-chain_b_fast_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy) {
+chain_b_fast_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights aw, Taps wx, Taps wy, WinCvt cv) {
     constexpr int R = 4, E = kTile + 2 * R, PIN = TileSmem<R>::pin;
     extern __shared__ __align__(16) float smem[];
     float* s_in = smem;                                        // E x PIN
@@ -258,7 +259,7 @@ chain_b_fast_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights a
             float y[4];
             y[0] = __fadd_rn(c.x, __fsub_rn(c.x, g[0])); y[1] = __fadd_rn(c.y, __fsub_rn(c.y, g[1]));
             y[2] = __fadd_rn(c.z, __fsub_rn(c.z, g[2])); y[3] = __fadd_rn(c.w, __fsub_rn(c.w, g[3]));
-            Fast<DstT>::store4(op + (int64_t)j * a.dsh, y);
+            PixIO<DstT, WIN>::store4(op + (int64_t)j * a.dsh, y, cv);
         }
     }
 }
@@ -291,21 +292,24 @@ bool fast_chain_ok(const ClaheGeom& g, int sd, int dd, const void* src, int64_t 
     return true;
 }
 
-template <typename SrcT>
-static int launch_a_t(const ChainAArgs& a, const Taps& wx, const Taps& wy, int R, unsigned blocks, cudaStream_t st) {
+template <typename SrcT, bool WIN>
+static int launch_a_t(const ChainAArgs& a, const Taps& wx, const Taps& wy, int R, unsigned blocks, cudaStream_t st,
+                      const WinCvt& cv) {
     switch (R) {
-        case 1: chain_a_fast_kernel<SrcT, 1><<<blocks, kFastThreads, 0, st>>>(a, wx, wy); break;
-        case 2: chain_a_fast_kernel<SrcT, 2><<<blocks, kFastThreads, 0, st>>>(a, wx, wy); break;
-        case 3: chain_a_fast_kernel<SrcT, 3><<<blocks, kFastThreads, 0, st>>>(a, wx, wy); break;
-        default: chain_a_fast_kernel<SrcT, 4><<<blocks, kFastThreads, 0, st>>>(a, wx, wy); break;
+        case 1: chain_a_fast_kernel<SrcT, 1, WIN><<<blocks, kFastThreads, 0, st>>>(a, wx, wy, cv); break;
+        case 2: chain_a_fast_kernel<SrcT, 2, WIN><<<blocks, kFastThreads, 0, st>>>(a, wx, wy, cv); break;
+        case 3: chain_a_fast_kernel<SrcT, 3, WIN><<<blocks, kFastThreads, 0, st>>>(a, wx, wy, cv); break;
+        default: chain_a_fast_kernel<SrcT, 4, WIN><<<blocks, kFastThreads, 0, st>>>(a, wx, wy, cv); break;
     }
     return check_launch();
 }
 
 int launch_chain_a_fast(const ChainAArgs& a, int sd, const Taps& wx, const Taps& wy, int R, int64_t n,
-                        cudaStream_t st) {
+                        cudaStream_t st, const WinCvt* win) {
     const unsigned blocks = (unsigned)(n * a.g.gh * a.g.gw);
-    MIE_DISPATCH_SRC(sd, return launch_a_t<SrcT>(a, wx, wy, R, blocks, st));
+    const WinCvt none = {};
+    if (win) { MIE_DISPATCH_SRC(sd, return (launch_a_t<SrcT, true>(a, wx, wy, R, blocks, st, *win))); }
+    else { MIE_DISPATCH_SRC(sd, return (launch_a_t<SrcT, false>(a, wx, wy, R, blocks, st, none))); }
     return MIE_OK;
 }
 
@@ -318,28 +322,30 @@ int launch_pack_cells(const uint8_t* luts, void* cells, int64_t n, int gh, int g
 
 size_t chain_cells_bytes(int64_t n, int gh, int gw) { return (size_t)n * (gh + 1) * (gw + 1) * kBins * 8; }
 
-template <typename DstT>
+template <typename DstT, bool WIN>
 static int launch_b_t(const ChainBArgs& b, const uint2* cells, const AxisWeights& aw, const Taps& wx,
-                      const Taps& wy, unsigned blocks, cudaStream_t st) {
+                      const Taps& wy, unsigned blocks, cudaStream_t st, const WinCvt& cv) {
     constexpr int E = kTile + 8;
     constexpr size_t smem = (size_t)(E * TileSmem<4>::pin + E * kPMid + E) * 4;
     static_assert(E * kPMid * 4 >= 4 * kBins * 8, "cell tables must fit in the s_mid region");
-    MIE_ENSURE_SMEM((chain_b_fast_kernel<DstT>), smem);
-    chain_b_fast_kernel<DstT><<<blocks, kFastThreads, smem, st>>>(b, cells, aw, wx, wy);
+    MIE_ENSURE_SMEM((chain_b_fast_kernel<DstT, WIN>), smem);
+    chain_b_fast_kernel<DstT, WIN><<<blocks, kFastThreads, smem, st>>>(b, cells, aw, wx, wy, cv);
     return check_launch();
 }
 
 // Runs the cell-packing launch and the tuned chain_b (9-tap unsharp only).  `cells` must hold
 // chain_cells_bytes(n, gh, gw) bytes.
 int launch_chain_b_fast(const ChainBArgs& b, int dd, void* cells_raw, const Taps& wx, const Taps& wy, int64_t n,
-                        cudaStream_t st) {
+                        cudaStream_t st, const WinCvt* win) {
     uint2* cells = (uint2*)cells_raw;
     int rc = launch_pack_cells(b.luts, cells, n, b.g.gh, b.g.gw, st);
     if (rc) return rc;
     AxisWeights aw;
     fill_axis_weights(aw);
     const unsigned blocks = (unsigned)(n * b.tiles_x * b.tiles_y);
-    MIE_DISPATCH_SRC(dd, return launch_b_t<SrcT>(b, cells, aw, wx, wy, blocks, st));
+    const WinCvt none = {};
+    if (win) { MIE_DISPATCH_SRC(dd, return (launch_b_t<SrcT, true>(b, cells, aw, wx, wy, blocks, st, *win))); }
+    else { MIE_DISPATCH_SRC(dd, return (launch_b_t<SrcT, false>(b, cells, aw, wx, wy, blocks, st, none))); }
     return MIE_OK;
 }
 

@@ -53,20 +53,21 @@ struct ChainBArgs {
     float lo, rg;
 };
 
+struct WinCvt;   // window.cuh
+
 // Defined in chain_fast.cu.  `fast_chain_ok` tells whether the tuned kernels cover the request.
 // `windowed` (optional): set when the range is not the dtype's default but an integer window the windowed
-// conversion of window.cuh can take — only the marching kernels implement it, the caller decides.
-struct WinCvt;
+// conversion of window.cuh can take.
 bool fast_chain_ok(const ClaheGeom& g, int src_dtype, int dst_dtype, const void* src, int64_t ssn, int64_t ssh,
                    const void* dst, int64_t dsn, int64_t dsh, int kg, int ku, int border, float lo, float hi,
                    bool* windowed = nullptr);
 int launch_chain_a_fast(const ChainAArgs& a, int src_dtype, const Taps& wx, const Taps& wy, int R, int64_t n,
-                        cudaStream_t st);
+                        cudaStream_t st, const WinCvt* win = nullptr);
 size_t chain_cells_bytes(int64_t n, int gh, int gw);
 // cells[n][gh+1][gw+1][256] (8 bytes each) from luts[n][gh][gw][256]; see chain_fast.cu
 int launch_pack_cells(const uint8_t* luts, void* cells, int64_t n, int gh, int gw, cudaStream_t st);
 int launch_chain_b_fast(const ChainBArgs& b, int dst_dtype, void* cells, const Taps& wx, const Taps& wy,
-                        int64_t n, cudaStream_t st);
+                        int64_t n, cudaStream_t st, const WinCvt* win = nullptr);
 
 // low bytes of four words -> one word (3 PRMT)
 __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {

@@ -105,6 +105,30 @@ struct PixIO<uint8_t, true> {
 template <>
 struct PixIO<float, true> : PixIO<float, false> {};
 
+// load_row24 (chain_fast.cuh) with the windowed conversion: 24 converted pixels x[0..23] = image columns
+// c0-4 .. c0+19 of one row, the columns outside the image filled from the registers already loaded.
+template <typename SrcT, bool WIN>
+__device__ __forceinline__ void load_row24_win(const SrcT* row, int c0, int w, int border, float* x, const WinCvt& cv) {
+    PixIO<SrcT, WIN>::load8(row + c0, x + 4, cv);
+    PixIO<SrcT, WIN>::load8(row + c0 + 8, x + 12, cv);
+    if (c0 != 0) {
+        PixIO<SrcT, WIN>::load4(row + c0 - 4, x, cv);
+    } else if (border == MIE_BORDER_REFLECT) {
+        x[0] = x[8]; x[1] = x[7]; x[2] = x[6]; x[3] = x[5];
+    } else {
+        const float e = border == MIE_BORDER_REPLICATE ? x[4] : 0.0f;
+        x[0] = e; x[1] = e; x[2] = e; x[3] = e;
+    }
+    if (c0 + 16 != w) {
+        PixIO<SrcT, WIN>::load4(row + c0 + 16, x + 20, cv);
+    } else if (border == MIE_BORDER_REFLECT) {
+        x[20] = x[18]; x[21] = x[17]; x[22] = x[16]; x[23] = x[15];
+    } else {
+        const float e = border == MIE_BORDER_REPLICATE ? x[19] : 0.0f;
+        x[20] = e; x[21] = e; x[22] = e; x[23] = e;
+    }
+}
+
 // ---------------------------------------------------------------- integer rules for the default range
 // For integer pixels with the dtype's default range, the kornia histogram bin floor(x01 * 256) and lookup
 // index trunc(x01 * 255) (and equalize's floor(RN(RN(x01 * 255) / 255) * 256)) are pure integer functions

@@ -456,7 +456,7 @@ def test_chain_plan_graph_replay(dev):
 def test_chain_integer_windows_on_marching_kernels(dev, case):
     """value_range windows with integer bounds (HU window, 12-bit data) on the marching chain kernels: the windowed
     conversion on the way in, range-checked bins / lookups, windowed quantisation on the way out — bit-exact against
-    the oracle for every border; the default schedule of a small job (generic kernels) gives the same bits."""
+    the oracle for every border, on the marching kernels and on the tile kernels (the default for small jobs)."""
     import mie_b200 as M
     import oracle as O
 
@@ -470,7 +470,8 @@ def test_chain_integer_windows_on_marching_kernels(dev, case):
             ref = O.chain_gauss_clahe_unsharp(x, 9, 1.0, 2.0, grid, 9, 1.0, border, value_range=vr)
             got = cpu(M.enhance_chain(xt, cfg, stages=3 | 4))
             assert np.array_equal(got, ref), (shape, border, int((got != ref).sum()))
-            assert np.array_equal(cpu(M.enhance_chain(xt, cfg)), ref), (shape, border)
+            assert np.array_equal(cpu(M.enhance_chain(xt, cfg)), ref), (shape, border)            # default: tile kernels
+            assert np.array_equal(cpu(M.enhance_chain(xt, cfg, stages=3 | 8)), ref), (shape, border)
         cfg = M.ChainConfig(grid_size=grid, value_range=vr)
         reff = O.chain_gauss_clahe_unsharp(x, 9, 1.0, 2.0, grid, 9, 1.0, "reflect", value_range=vr, out_dtype=np.float32)
         assert np.array_equal(cpu(M.enhance_chain(xt, cfg, out_dtype=torch.float32, stages=3 | 4)), reff), shape
