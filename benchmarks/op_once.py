@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs ONE operator a few times on its BASELINE.json config shape (for ncu captures and quick timings):
-    python benchmarks/op_once.py median3d|median2d|equalize|clahe|clahe16|gauss|unsharp|bilateral|nlm [reps]
+    python benchmarks/op_once.py median3d|median2d|median2d_f32|median5|equalize|clahe|clahe16|gauss|unsharp|bilateral|nlm [reps]
 Prints one JSON line with the CUDA-event time per call (eager calls; never quote a number taken under ncu)."""
 import json
 import os
@@ -29,6 +29,10 @@ if op == "median3d":
     fn, px = (lambda: M.median(v)), d * 512 * 512
 elif op == "median2d":
     x = batch2(); fn, px = (lambda: M.median_blur(x, 3)), x.numel()
+elif op == "median2d_f32":
+    x = batch2().to(torch.float32) / 65535.0; fn, px = (lambda: M.median_blur(x, 3)), x.numel()
+elif op == "median5":
+    x = batch2(); fn, px = (lambda: M.median_blur(x, 5)), x.numel()
 elif op == "equalize":
     x = batch2(); fn, px = (lambda: M.equalize(x)), x.numel()
 elif op == "clahe":

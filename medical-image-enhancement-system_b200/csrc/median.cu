@@ -488,7 +488,7 @@ median3d_direct_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t s
 // median-of-9 identity: med3(max of the column minima, med3 of the column medians, min of the column
 // maxima).  ~27 integer-pipe instructions per pixel pair, no shared memory.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
                         int64_t dsh, int64_t nplanes, int h, int w, int strips, int bands, int rows_per_band,
                         int border) {
@@ -504,21 +504,38 @@ median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
     const T* plane = src + n * ssn;
     T* oplane = dst + n * dsn;
 
-    // six packed words of image row y: [pair left of x0 | four own pairs | pair right of x0 + 7]
-    auto load_row = [&](int y, P* r) {
+    // Row y arrives in two steps so that the loads of row y + 2 are in flight while row y + 1 is consumed
+    // (with the load issued where it is used the kernel sat on the scoreboard: 6.8 stalled warps per issue,
+    // profiles/r1_ncu_full_standalone_ops2.txt).  issue_row: the global loads only — the lane's 8 pixels plus
+    // the pair across the strip boundary for lanes 0 / 31.  finish_row: widening, neighbour shuffles and the
+    // border rule, giving six packed words [pair left of x0 | four own pairs | pair right of x0 + 7].
+    struct Raw { uint4 q; uint32_t l, r; };
+    auto issue_row = [&](int y, Raw& t) {
         const int sy = border_index(y, h, border);
+        t.q = make_uint4(0u, 0u, 0u, 0u); t.l = 0u; t.r = 0u;
+        if (sy >= 0 && active) {
+            const T* row = plane + (int64_t)sy * ssh;
+            if constexpr (sizeof(T) == 1) {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + x0));
+                t.q.x = raw.x; t.q.y = raw.y;
+                if (lane == 0 && x0 != 0) t.l = (uint32_t)__ldg(row + x0 - 1) << 16;
+                if (lane == 31 && x0 + 8 != w) t.r = (uint32_t)__ldg(row + x0 + 8);
+            } else {
+                t.q = __ldg(reinterpret_cast<const uint4*>(row + x0));
+                if (lane == 0 && x0 != 0) t.l = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
+                if (lane == 31 && x0 + 8 != w) t.r = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
+            }
+        }
+    };
+    auto finish_row = [&](int y, const Raw& t, P* r) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         uint32_t left = 0u, right = 0u;
-        if (sy >= 0) {                              // uniform
-            const T* row = plane + (int64_t)sy * ssh;
-            if (active) {
-                if constexpr (sizeof(T) == 1) {     // 8 bytes -> four (pixel, pixel) words of 16-bit lanes
-                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + x0));
-                    v.x = __byte_perm(raw.x, 0u, 0x4140); v.y = __byte_perm(raw.x, 0u, 0x4342);
-                    v.z = __byte_perm(raw.y, 0u, 0x4140); v.w = __byte_perm(raw.y, 0u, 0x4342);
-                } else {
-                    v = __ldg(reinterpret_cast<const uint4*>(row + x0));
-                }
+        if (border_index(y, h, border) >= 0) {      // uniform
+            if constexpr (sizeof(T) == 1) {         // 8 bytes -> four (pixel, pixel) words of 16-bit lanes
+                v.x = __byte_perm(t.q.x, 0u, 0x4140); v.y = __byte_perm(t.q.x, 0u, 0x4342);
+                v.z = __byte_perm(t.q.y, 0u, 0x4140); v.w = __byte_perm(t.q.y, 0u, 0x4342);
+            } else {
+                v = t.q;
             }
             left = __shfl_up_sync(0xffffffffu, v.w, 1);
             right = __shfl_down_sync(0xffffffffu, v.x, 1);
@@ -527,15 +544,13 @@ median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
                     left = border == MIE_BORDER_REFLECT ? (v.x & 0xFFFF0000u)
                          : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? (v.x << 16) : 0u;
                 } else if (lane == 0) {
-                    if constexpr (sizeof(T) == 1) left = (uint32_t)__ldg(row + x0 - 1) << 16;
-                    else left = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
+                    left = t.l;
                 }
                 if (x0 + 8 == w) {                  // pixel w sits in the low half
                     right = border == MIE_BORDER_REFLECT ? (v.w & 0xFFFFu)
                           : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? (v.w >> 16) : 0u;
                 } else if (lane == 31) {
-                    if constexpr (sizeof(T) == 1) right = (uint32_t)__ldg(row + x0 + 8);
-                    else right = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
+                    right = t.r;
                 }
             }
         }
@@ -543,14 +558,20 @@ median3x3_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
     };
 
     P ring[3][6];
-    load_row(y0 - 1, ring[0]);
-    load_row(y0, ring[1]);
+    Raw nxt;
+    {
+        Raw t0, t1;
+        issue_row(y0 - 1, t0); issue_row(y0, t1); issue_row(y0 + 1, nxt);
+        finish_row(y0 - 1, t0, ring[0]); finish_row(y0, t1, ring[1]);
+    }
     for (int yb = y0; yb < y1; yb += 3) {
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             const int y = yb + u;
             if (y < y1) {                           // uniform
-                load_row(y + 1, ring[(u + 2) % 3]);
+                const Raw cur = nxt;
+                if (y + 1 < y1) issue_row(y + 2, nxt);   // uniform; consumed by the next output row
+                finish_row(y + 1, cur, ring[(u + 2) % 3]);
                 P lo[6], mi[6], hi[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
@@ -741,13 +762,23 @@ median3x3_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int
     const float* plane = src + n * ssn;
     float* oplane = dst + n * dsn;
 
-    auto load_row = [&](int y, float* r) {          // r[0] = pixel x0-1, r[1..4] = own pixels, r[5] = pixel x0+4
+    // issue_row / finish_row: loads one row ahead of their use, as in median3x3_packed_kernel
+    struct Raw { float4 q; float l, r; };
+    auto issue_row = [&](int y, Raw& t) {
         const int sy = border_index(y, h, border);
+        t.q = make_float4(0.f, 0.f, 0.f, 0.f); t.l = 0.f; t.r = 0.f;
+        if (sy >= 0 && active) {
+            const float* row = plane + (int64_t)sy * ssh;
+            t.q = __ldg(reinterpret_cast<const float4*>(row + x0));
+            if (lane == 0 && x0 != 0) t.l = __ldg(row + x0 - 1);
+            if (lane == 31 && x0 + 4 != w) t.r = __ldg(row + x0 + 4);
+        }
+    };
+    auto finish_row = [&](int y, const Raw& t, float* r) {   // r[0] = pixel x0-1, r[1..4] = own pixels, r[5] = pixel x0+4
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         float left = 0.f, right = 0.f;
-        if (sy >= 0) {                              // uniform
-            const float* row = plane + (int64_t)sy * ssh;
-            if (active) v = __ldg(reinterpret_cast<const float4*>(row + x0));
+        if (border_index(y, h, border) >= 0) {      // uniform
+            v = t.q;
             left = __shfl_up_sync(0xffffffffu, v.w, 1);
             right = __shfl_down_sync(0xffffffffu, v.x, 1);
             if (active) {
@@ -755,26 +786,32 @@ median3x3_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int
                     left = border == MIE_BORDER_REFLECT ? v.y
                          : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? v.x : 0.f;
                 else if (lane == 0)
-                    left = __ldg(row + x0 - 1);
+                    left = t.l;
                 if (x0 + 4 == w)
                     right = border == MIE_BORDER_REFLECT ? v.z
                           : (border == MIE_BORDER_REPLICATE || border == MIE_BORDER_SYMMETRIC) ? v.w : 0.f;
                 else if (lane == 31)
-                    right = __ldg(row + x0 + 4);
+                    right = t.r;
             }
         }
         r[0] = left; r[1] = v.x; r[2] = v.y; r[3] = v.z; r[4] = v.w; r[5] = right;
     };
 
     float ring[3][6];
-    load_row(y0 - 1, ring[0]);
-    load_row(y0, ring[1]);
+    Raw nxt;
+    {
+        Raw t0, t1;
+        issue_row(y0 - 1, t0); issue_row(y0, t1); issue_row(y0 + 1, nxt);
+        finish_row(y0 - 1, t0, ring[0]); finish_row(y0, t1, ring[1]);
+    }
     for (int yb = y0; yb < y1; yb += 3) {
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
             const int y = yb + u;
             if (y < y1) {                           // uniform
-                load_row(y + 1, ring[(u + 2) % 3]);
+                const Raw cur = nxt;
+                if (y + 1 < y1) issue_row(y + 2, nxt);   // uniform
+                finish_row(y + 1, cur, ring[(u + 2) % 3]);
                 float lo[6], mi[6], hi[6];
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
