@@ -660,21 +660,35 @@ median5x5_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
     const T* plane = src + n * ssn;
     T* oplane = dst + n * dsn;
 
-    // six packed words of image row y: [pixels x0-2, x0-1 | four own pairs | pixels x0+8, x0+9]
-    auto load_row = [&](int y, P* r) {
+    // issue_row / finish_row as in the 3x3 kernel (loads one row ahead of their use); finish_row gives six packed
+    // words of image row y: [pixels x0-2, x0-1 | four own pairs | pixels x0+8, x0+9]
+    struct Raw { uint4 q; uint32_t l, r; };
+    auto issue_row = [&](int y, Raw& t) {
         const int sy = border_index(y, h, border);
+        t.q = make_uint4(0u, 0u, 0u, 0u); t.l = 0u; t.r = 0u;
+        if (sy >= 0 && active) {
+            const T* row = plane + (int64_t)sy * ssh;
+            if constexpr (sizeof(T) == 1) {
+                const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + x0));
+                t.q.x = raw.x; t.q.y = raw.y;
+                if (lane == 0 && x0 != 0) t.l = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(row + x0 - 2));
+                if (lane == 31 && x0 + 8 != w) t.r = (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(row + x0 + 8));
+            } else {
+                t.q = __ldg(reinterpret_cast<const uint4*>(row + x0));
+                if (lane == 0 && x0 != 0) t.l = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
+                if (lane == 31 && x0 + 8 != w) t.r = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
+            }
+        }
+    };
+    auto finish_row = [&](int y, const Raw& t, P* r) {
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         uint32_t left = 0u, right = 0u;
-        if (sy >= 0) {                              // uniform
-            const T* row = plane + (int64_t)sy * ssh;
-            if (active) {
-                if constexpr (sizeof(T) == 1) {
-                    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(row + x0));
-                    v.x = __byte_perm(raw.x, 0u, 0x4140); v.y = __byte_perm(raw.x, 0u, 0x4342);
-                    v.z = __byte_perm(raw.y, 0u, 0x4140); v.w = __byte_perm(raw.y, 0u, 0x4342);
-                } else {
-                    v = __ldg(reinterpret_cast<const uint4*>(row + x0));
-                }
+        if (border_index(y, h, border) >= 0) {      // uniform
+            if constexpr (sizeof(T) == 1) {
+                v.x = __byte_perm(t.q.x, 0u, 0x4140); v.y = __byte_perm(t.q.x, 0u, 0x4342);
+                v.z = __byte_perm(t.q.y, 0u, 0x4140); v.w = __byte_perm(t.q.y, 0u, 0x4342);
+            } else {
+                v = t.q;
             }
             left = __shfl_up_sync(0xffffffffu, v.w, 1);
             right = __shfl_down_sync(0xffffffffu, v.x, 1);
@@ -684,20 +698,16 @@ median5x5_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
                          : border == MIE_BORDER_SYMMETRIC ? __byte_perm(v.x, 0u, 0x1032)       // (px 1, px 0)
                          : border == MIE_BORDER_REPLICATE ? __byte_perm(v.x, 0u, 0x1010) : 0u; // (px 0, px 0)
                 } else if (lane == 0) {
-                    if constexpr (sizeof(T) == 1)
-                        left = __byte_perm((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(row + x0 - 2)), 0u, 0x4140);
-                    else
-                        left = __ldg(reinterpret_cast<const uint32_t*>(row + x0 - 2));
+                    if constexpr (sizeof(T) == 1) left = __byte_perm(t.l, 0u, 0x4140);
+                    else left = t.l;
                 }
                 if (x0 + 8 == w) {                  // pixels w (low half), w + 1 (high half)
                     right = border == MIE_BORDER_REFLECT ? __byte_perm(v.w, v.z, 0x7610)       // (px w-2, px w-3)
                           : border == MIE_BORDER_SYMMETRIC ? __byte_perm(v.w, 0u, 0x1032)      // (px w-1, px w-2)
                           : border == MIE_BORDER_REPLICATE ? __byte_perm(v.w, 0u, 0x3232) : 0u;// (px w-1, px w-1)
                 } else if (lane == 31) {
-                    if constexpr (sizeof(T) == 1)
-                        right = __byte_perm((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(row + x0 + 8)), 0u, 0x4140);
-                    else
-                        right = __ldg(reinterpret_cast<const uint32_t*>(row + x0 + 8));
+                    if constexpr (sizeof(T) == 1) right = __byte_perm(t.r, 0u, 0x4140);
+                    else right = t.r;
                 }
             }
         }
@@ -705,16 +715,21 @@ median5x5_packed_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t 
     };
 
     P ring[5][6];
-    load_row(y0 - 2, ring[0]);
-    load_row(y0 - 1, ring[1]);
-    load_row(y0, ring[2]);
-    load_row(y0 + 1, ring[3]);
+    Raw nxt;
+    {
+        Raw t0, t1, t2, t3;
+        issue_row(y0 - 2, t0); issue_row(y0 - 1, t1); issue_row(y0, t2); issue_row(y0 + 1, t3); issue_row(y0 + 2, nxt);
+        finish_row(y0 - 2, t0, ring[0]); finish_row(y0 - 1, t1, ring[1]);
+        finish_row(y0, t2, ring[2]); finish_row(y0 + 1, t3, ring[3]);
+    }
     for (int yb = y0; yb < y1; yb += 5) {
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
             const int y = yb + u;
             if (y < y1) {                           // uniform
-                load_row(y + 2, ring[(u + 4) % 5]);
+                const Raw cur = nxt;
+                if (y + 1 < y1) issue_row(y + 3, nxt);   // uniform
+                finish_row(y + 2, cur, ring[(u + 4) % 5]);
                 P s[6][5];                          // vertically sorted samples of every word
 #pragma unroll
                 for (int c = 0; c < 6; ++c) {
