@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs ONE operator a few times on its BASELINE.json config shape (for ncu captures and quick timings):
-    python benchmarks/op_once.py median3d|median2d|median2d_f32|median5|equalize|clahe|clahe16|gauss|unsharp|bilateral|nlm [reps]
+    python benchmarks/op_once.py median3d|median2d|median2d_f32|median5|mse|ssim|equalize|clahe|clahe16|gauss|unsharp|bilateral|nlm [reps]
 Prints one JSON line with the CUDA-event time per call (eager calls; never quote a number taken under ncu)."""
 import json
 import os
@@ -33,6 +33,9 @@ elif op == "median2d_f32":
     x = batch2().to(torch.float32) / 65535.0; fn, px = (lambda: M.median_blur(x, 3)), x.numel()
 elif op == "median5":
     x = batch2(); fn, px = (lambda: M.median_blur(x, 5)), x.numel()
+elif op in ("mse", "ssim"):
+    x = batch2(); y = M.unsharp_mask(x, 9, 1.0)
+    fn, px = ((lambda: M.mse(x, y)) if op == "mse" else (lambda: M.ssim(x, y))), x.numel()
 elif op == "equalize":
     x = batch2(); fn, px = (lambda: M.equalize(x)), x.numel()
 elif op == "clahe":
