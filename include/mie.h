@@ -253,8 +253,15 @@ enum mie_chain_stages {
 /* Which path (h, w, grid, kernel sizes) takes: 0 = stages run unfused (4 launches), 1 = generic
  * fused kernels (2 launches), 2 = tuned fused kernels for 64x64-pixel tiles and a 9-tap unsharp
  * (3 launches: chain_a, cell-table packing, chain_b; needs 16-byte aligned rows and the dtype's
- * default value range, otherwise 1 applies). */
+ * default value range or a window mie_value_range_mode() reports as 1, otherwise 1 applies). */
 int mie_chain_is_fused(int h, int w, int gh, int gw, int kgx, int kgy, int kux, int kuy);
+/* How the tuned kernels treat the pixel mapping (lo, hi) of `dtype` (the value_range= extension of the Python
+ * surface): 0 = the dtype's default range (or float pixels); 1 = an integer window inside the
+ * dtype's range whose divide-free conversion the host has checked against the IEEE quotient
+ * (float(v) - lo) / (hi - lo) for EVERY code of the dtype — the tuned CLAHE / equalize / Gaussian / chain kernels
+ * run it; -1 = neither (non-integer or out-of-range bounds, hi <= lo, or a code where the conversion would
+ * differ): the generic kernels run it with the IEEE division.  Host-only; no CUDA call. */
+int mie_value_range_mode(int dtype, float lo, float hi);
 size_t mie_chain_workspace_bytes(int64_t n, int h, int w, int gh, int gw);
 int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int dst_dtype,
                                   int64_t n, int h, int w,

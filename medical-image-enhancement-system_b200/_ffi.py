@@ -55,6 +55,7 @@ SIGNATURES = {
     "mie_chain_gauss_clahe_unsharp": (
         [_p, _p, _i, _i, *_planes, *_taps, _i, _i, _d, *_taps, _i, _f, _f, _i, _p, _sz, _p], _i),
     "mie_chain_is_fused": ([_i] * 8, _i),
+    "mie_value_range_mode": ([_i, _f, _f], _i),
 }
 
 _lib = None
@@ -114,6 +115,22 @@ def value_range_of(t: torch.Tensor, value_range):
     if not hi > lo:
         raise ValueError("value_range must satisfy hi > lo")
     return lo, hi
+
+
+def value_range_mode(dtype: torch.dtype, value_range=None) -> str:
+    """Which kernels a pixel mapping runs on (host-only query, mie_value_range_mode in include/mie.h):
+    'default' — the dtype's own range (or float pixels); 'window' — an integer window the tuned kernels run through
+    their divide-free conversion, checked on the host against the IEEE quotient for every code of the dtype;
+    'generic' — anything else (the generic kernels compute the mapping with the IEEE division)."""
+    if dtype not in DTYPE_CODE:
+        raise TypeError(f"dtype {dtype} not supported (uint8, uint16, int16, float32)")
+    if dtype == torch.float32 or value_range is None:
+        lo, hi = DTYPE_RANGE.get(dtype, (0.0, 1.0))
+    else:
+        lo, hi = float(value_range[0]), float(value_range[1])
+        if not hi > lo:
+            raise ValueError("value_range must satisfy hi > lo")
+    return {0: "default", 1: "window", -1: "generic"}[lib().mie_value_range_mode(DTYPE_CODE[dtype], lo, hi)]
 
 
 def as_planes(t: torch.Tensor):

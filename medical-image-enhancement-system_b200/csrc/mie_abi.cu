@@ -1,5 +1,6 @@
 // mie_abi.cu — version / error / device entry points of the C ABI (include/mie.h).
 #include "mie_common.cuh"
+#include "window.cuh"
 
 extern "C" {
 
@@ -22,6 +23,12 @@ const char* mie_error_string(int code) {
         case MIE_E_UNSUPPORTED: return "request not implemented by this build";
         default: return "unknown error";
     }
+}
+
+int mie_value_range_mode(int dtype, float lo, float hi) {
+    if (dtype < MIE_U8 || dtype > MIE_F32) return -1;
+    mie::WinCvt cv;
+    return mie::range_mode(dtype, lo, hi, &cv);
 }
 
 int mie_device_info(int* sm_count, int* cc_major, int* cc_minor) {

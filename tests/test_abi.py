@@ -146,3 +146,55 @@ def test_newer_entry_points_reject_bad_arguments_before_any_launch():
     assert L.mie_chain_gauss_clahe_unsharp(fake, fake, 1, 1, 0, 512, 512, 262144, 512, 262144, 512, w9.ctypes.data, 9,
                                            w9.ctypes.data, 9, 8, 8, 2.0, w9.ctypes.data, 9, w9.ctypes.data, 9, 1, 0.0,
                                            65535.0, 3 | 4, fake, 0, None) == 0
+
+
+def _fma32(a, b, c):
+    """float32 fma through exact rational arithmetic (numpy has no fmaf)."""
+    from fractions import Fraction
+    import numpy as np
+    return np.float32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+
+def test_value_range_mode_is_a_host_query_and_its_verdicts_hold():
+    """mie_value_range_mode (include/mie.h) needs no GPU.  Its verdicts: the dtype default -> 0, an integer window inside
+    the dtype -> 1 (after the exhaustive host check), anything else -> -1.  For an accepted window the divide-free
+    conversion of csrc/window.cuh is re-evaluated here on a sample of codes against the IEEE quotient the oracle uses."""
+    import numpy as np
+    import mie_b200 as M
+    L = M._ffi.lib()
+    U8, U16, I16, F32 = 0, 1, 2, 3
+    assert L.mie_value_range_mode(U16, 0.0, 65535.0) == 0
+    assert L.mie_value_range_mode(I16, -32768.0, 32767.0) == 0
+    assert L.mie_value_range_mode(U8, 0.0, 255.0) == 0
+    assert L.mie_value_range_mode(F32, 0.0, 1.0) == 0 and L.mie_value_range_mode(F32, -3.0, 7.5) == 0
+    assert L.mie_value_range_mode(I16, -1024.0, 3071.0) == 1          # the HU window of config 3
+    assert L.mie_value_range_mode(U16, 0.0, 4095.0) == 1              # 12-bit occupancy of a uint16 container
+    assert L.mie_value_range_mode(U8, 16.0, 235.0) == 1
+    assert L.mie_value_range_mode(I16, -1000.5, 3000.0) == -1         # non-integer bound
+    assert L.mie_value_range_mode(U16, -1.0, 4095.0) == -1            # outside the dtype
+    assert L.mie_value_range_mode(U8, 0.0, 256.0) == -1
+    assert L.mie_value_range_mode(U16, 100.0, 100.0) == -1            # hi <= lo
+    assert L.mie_value_range_mode(7, 0.0, 1.0) == -1                  # unknown dtype
+    assert M.value_range_mode(torch.int16) == "default"
+    assert M.value_range_mode(torch.int16, (-1024, 3071)) == "window"
+    assert M.value_range_mode(torch.int16, (-1000.5, 3000.0)) == "generic"
+    assert M.value_range_mode(torch.float32, (5, 9)) == "default"
+    with pytest.raises(ValueError):
+        M.value_range_mode(torch.uint16, (10, 10))
+    with pytest.raises(TypeError):
+        M.value_range_mode(torch.float64)
+
+    # the conversion itself, int16 in the HU window: a = (2^23 + v + 32768) - (2^23 + 32768 + lo) is exact,
+    # q0 = a * r, q = fma(fma(-rg, q0, a), r, q0) must equal (float(v) - lo) / rg
+    lo, hi = np.float32(-1024.0), np.float32(3071.0)
+    rg = np.float32(hi - lo)
+    r = np.float32(1.0) / rg
+    rng = np.random.default_rng(0)
+    codes = np.concatenate([np.array([-32768, -1025, -1024, -1023, 0, 3070, 3071, 3072, 32767]),
+                            rng.integers(-32768, 32768, 400)])
+    for v in codes:
+        exact = (np.float32(v) - lo) / rg
+        a = np.float32(np.float32(8388608.0 + float(v) + 32768.0) - np.float32(8388608.0 + 32768.0 + float(lo)))
+        q0 = np.float32(a * r)
+        q = _fma32(_fma32(-rg, q0, a), r, q0)
+        assert q == exact, (v, q, exact)
