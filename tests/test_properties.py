@@ -8,7 +8,7 @@ import torch
 from hypothesis import given, settings
 from hypothesis import strategies as st
 
-SMALL = settings(max_examples=15, deadline=None)
+SMALL = settings(max_examples=25, deadline=None, derandomize=True)   # fixed examples: the suite is a gate, not a fuzzer
 
 
 # ---------------------------------------------------------------------------- CPU: oracle
