@@ -65,7 +65,8 @@ enum mie_error {
     MIE_E_BORDER = -8,      /* unknown border mode, or halo >= image for reflect */
     MIE_E_WORKSPACE = -9,   /* workspace too small */
     MIE_E_RANGE = -10,      /* hi <= lo for an integer dtype */
-    MIE_E_UNSUPPORTED = -11 /* valid request this build does not implement */
+    MIE_E_UNSUPPORTED = -11,/* valid request this build does not implement */
+    MIE_E_ALIGN = -12       /* workspace (or a buffer a tuned kernel needs aligned) is not 256-byte aligned */
 };
 
 int mie_abi_version(void);

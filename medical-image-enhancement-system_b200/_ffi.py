@@ -22,7 +22,7 @@ DTYPE_CODE = {torch.uint8: MIE_U8, torch.uint16: MIE_U16, torch.int16: MIE_I16, 
 DTYPE_RANGE = {torch.uint8: (0.0, 255.0), torch.uint16: (0.0, 65535.0), torch.int16: (-32768.0, 32767.0)}
 
 _E_TYPE = {-2}  # -> TypeError
-_E_VALUE = {-1, -3, -4, -5, -6, -7, -8, -9, -10}  # -> ValueError
+_E_VALUE = {-1, -3, -4, -5, -6, -7, -8, -9, -10, -12}  # -> ValueError
 
 _p, _i, _i64, _f, _d, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t
 _planes = [_i64, _i, _i, _i64, _i64, _i64, _i64]  # n, h, w, ssn, ssh, dsn, dsh

@@ -71,6 +71,10 @@ def enhance_chain(input: torch.Tensor, config: ChainConfig = ChainConfig(), *, o
         workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=x.device)
     elif workspace.dtype != torch.uint8 or workspace.numel() < need or workspace.device != x.device:
         raise ValueError(f"workspace must be a uint8 tensor of >= {need} bytes on the input's device")
+    elif workspace.data_ptr() % 256 or not workspace.is_contiguous():
+        # the kernels store 32-bit index words and load LUTs / cell tables as 16-byte pieces (MIE_E_ALIGN)
+        raise ValueError("workspace must be contiguous and 256-byte aligned (a fresh torch.empty is; a sliced view "
+                         "such as ws[1:] is not)")
     wgx, wgy = get_gaussian_kernel1d(gkx, gsx), get_gaussian_kernel1d(gky, gsy)
     wux, wuy = get_gaussian_kernel1d(ukx, usx), get_gaussian_kernel1d(uky, usy)
     with torch.cuda.device(x.device):

@@ -144,6 +144,7 @@ chain_b_kernel(ChainBArgs a, Taps wx, Taps wy) {
     __syncthreads();
     const int jlo = s_lim[0], ilo = s_lim[2];
     const int nlr = s_lim[1] - jlo + 1, nlc = s_lim[3] - ilo + 1;
+    if (nlr * nlc > a.max_lut_tiles) __trap();   // host-side capacity rule (fused_ok) violated: never write past s_lut
     // stage the nlr x nlc neighbourhood of LUTs (256 B each) with 16-byte copies
     {
         const uint4* gl = reinterpret_cast<const uint4*>(a.luts + n * (int64_t)a.g.gh * a.g.gw * kBins);
@@ -193,13 +194,16 @@ chain_b_kernel(ChainBArgs a, Taps wx, Taps wy) {
 }
 
 // ---------------------------------------------------------------- host side
-static bool fused_ok(const ClaheGeom& g, int kgx, int kgy, int kux, int kuy, int* lut_cap) {
+static bool fused_ok(const ClaheGeom& g, int kgx, int kgy, int kux, int kuy, int border, int* lut_cap) {
     if (kgx != kgy || kux != kuy) return false;
     if (kgx < 3 || kgx > 9 || kux < 3 || kux > 9) return false;
     if (g.hp != g.h || g.wp != g.w) return false;
     if (g.th > kTile || g.tw > kTile) return false;
     const int R = kux / 2;
-    const int capr = (kTile + 2 * R) / g.th + 3, capc = (kTile + 2 * R) / g.tw + 3;
+    // A block's haloed rows / columns touch a contiguous run of tiles — except with a circular border, where
+    // the halo of the first / last blocks wraps to the opposite edge: the run then spans the whole grid.
+    const bool wrap = border == MIE_BORDER_CIRCULAR;
+    const int capr = wrap ? g.gh : (kTile + 2 * R) / g.th + 3, capc = wrap ? g.gw : (kTile + 2 * R) / g.tw + 3;
     const int cr = capr < g.gh ? capr : g.gh, cc = capc < g.gw ? capc : g.gw;
     if ((size_t)cr * cc * kBins > 96 * 1024) return false;
     *lut_cap = cr * cc;
@@ -243,7 +247,7 @@ int mie_chain_is_fused(int h, int w, int gh, int gw, int kgx, int kgy, int kux, 
     ClaheGeom g;
     int cap = 0;
     if (make_clahe_geom(h, w, gh, gw, MIE_CLAHE_KORNIA, &g)) return 0;
-    if (!fused_ok(g, kgx, kgy, kux, kuy, &cap)) return 0;
+    if (!fused_ok(g, kgx, kgy, kux, kuy, MIE_BORDER_REFLECT, &cap)) return 0;
     // 2: tuned kernels (chain_a, cell packing, chain_b = 3 launches) when the buffers are 16-byte
     // aligned and the integer range is the dtype default; 1: generic fused kernels (2 launches)
     return (g.th == kTile && g.tw == kTile && kux == 9) ? 2 : 1;
@@ -281,6 +285,9 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     if (stages < MIE_CHAIN_STAGE_A) return MIE_E_UNSUPPORTED;
     if (n == 0) return MIE_OK;
     if (!workspace) return MIE_E_NULL;
+    // chain_a stores 32-bit index words, chain_b loads LUTs as uint4 and cell tables as uint2: the carve-up below
+    // keeps every piece 256-byte aligned only if the workspace itself is
+    if ((uintptr_t)workspace % 256) return MIE_E_ALIGN;
     if (workspace_bytes < mie_chain_workspace_bytes(n, h, w, gh, gw)) return MIE_E_WORKSPACE;
     if (n * (int64_t)gh * gw > 2147483647LL) return MIE_E_SHAPE;
 
@@ -288,7 +295,7 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     uint8_t* plane = luts + (size_t)n * gh * gw * kBins;  // 256-byte aligned when workspace is
 
     int lut_cap = 0;
-    if (!fused_ok(g, kgx, kgy, kux, kuy, &lut_cap)) {
+    if (!fused_ok(g, kgx, kgy, kux, kuy, border, &lut_cap)) {
         if (stages != MIE_CHAIN_ALL) return MIE_E_UNSUPPORTED;
         float* f = (float*)plane;
         const int64_t fsn = (int64_t)h * w, fsh = w;

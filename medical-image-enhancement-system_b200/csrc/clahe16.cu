@@ -484,6 +484,8 @@ int clahe16_apply_impl(const void* src, void* dst, int64_t n, int h, int w, int6
 // luts + apply for a batch, LUTs of at most `group` images alive at a time.
 int clahe16_impl(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int64_t dsn, int64_t dsh,
                  int gh, int gw, double clip_limit, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (h <= 0 || w <= 0 || n < 0) return MIE_E_SHAPE;   // validated BEFORE the grid enters a division below
+    if (gh <= 0 || gw <= 0) return MIE_E_GRID;
     const size_t per_image = (size_t)gh * gw * kBins16 * sizeof(uint16_t);
     if (n == 0) return MIE_OK;
     if (!workspace) return MIE_E_NULL;

@@ -21,6 +21,7 @@ const char* mie_error_string(int code) {
         case MIE_E_WORKSPACE: return "workspace too small";
         case MIE_E_RANGE: return "value range must satisfy hi > lo";
         case MIE_E_UNSUPPORTED: return "request not implemented by this build";
+        case MIE_E_ALIGN: return "workspace must be 256-byte aligned";
         default: return "unknown error";
     }
 }

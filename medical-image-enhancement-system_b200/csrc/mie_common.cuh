@@ -97,7 +97,8 @@ struct ClaheGeom {
 };
 
 // kornia: tile = ceil(dim/grid), +1 if odd; pad bottom/right with 'reflect'.
-// opencv: pad to the next multiple of the grid with BORDER_REFLECT_101.
+// opencv: pad to the next multiple of the grid with BORDER_REFLECT_101 — BOTH axes by tiles - dim % tiles as soon
+// as either is not divisible, so an evenly dividing axis then grows by a full `tiles` pixels (cv::CLAHE::apply).
 inline int make_clahe_geom(int h, int w, int gh, int gw, int semantics, ClaheGeom* g) {
     if (h <= 0 || w <= 0) return MIE_E_SHAPE;
     if (gh <= 0 || gw <= 0) return MIE_E_GRID;
@@ -106,7 +107,8 @@ inline int make_clahe_geom(int h, int w, int gh, int gw, int semantics, ClaheGeo
         g->th = (h + gh - 1) / gh; g->tw = (w + gw - 1) / gw;
         g->th += g->th & 1; g->tw += g->tw & 1;
     } else if (semantics == MIE_CLAHE_OPENCV) {
-        g->th = (h + gh - 1) / gh; g->tw = (w + gw - 1) / gw;
+        if (h % gh == 0 && w % gw == 0) { g->th = h / gh; g->tw = w / gw; }
+        else { g->th = (h + gh - h % gh) / gh; g->tw = (w + gw - w % gw) / gw; }
     } else {
         return MIE_E_UNSUPPORTED;
     }

@@ -210,8 +210,9 @@ def median(image: torch.Tensor, footprint=None, out=None, mode: str = "nearest",
         else:
             d, h, w = x.shape
             for hp in (halo_lo, halo_hi):
-                if hp is not None and (hp.shape != (h, w) or hp.dtype != x.dtype or not hp.is_contiguous()):
-                    raise ValueError("halo planes must be contiguous (H, W) tensors of the volume's dtype")
+                if hp is not None and (hp.shape != (h, w) or hp.dtype != x.dtype or not hp.is_contiguous()
+                                       or hp.device != x.device):
+                    raise ValueError("halo planes must be contiguous (H, W) tensors of the volume's dtype on its device")
             check(lib().mie_median3d(x.data_ptr(), dst.data_ptr(), DTYPE_CODE[x.dtype], d, h, w, h * w, w, h * w, w,
                                      halo_lo.data_ptr() if halo_lo is not None else None,
                                      halo_hi.data_ptr() if halo_hi is not None else None, border,

@@ -71,6 +71,7 @@ class HostSlicePipeline:
         and launch cost of every chunk — ~0.1 ms each, more than the chunk's kernels — on every call.
         So the second call with the same (src, dst) captures the whole run — every copy, kernel and
         cross-stream dependency of all chunks — into one CUDA graph, and later calls replay it."""
+        self._validate(src, dst)
         key = (src.data_ptr(), dst.data_ptr(), tuple(src.shape), src.dtype, dst.dtype)
         if graph and self._graph is not None and self._graph_key == key:
             self._graph.replay()
@@ -87,12 +88,38 @@ class HostSlicePipeline:
                 self._graph, self._graph_key, self._graph_refs = g, key, (src, dst)
                 return self.run(src, dst, graph=True)
             except RuntimeError:
-                self._graph = None  # capture refused (e.g. pageable memory): stay eager
+                # capture refused (e.g. pageable memory): stay eager.  The streams the failed capture forked into are
+                # left in an invalidated capture state, so they are replaced along with their events.
+                self._graph = None
                 torch.cuda.synchronize(self.device)
+                with torch.cuda.device(self.device):
+                    self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream() for _ in range(3))
+                    self.ev_in = [torch.cuda.Event() for _ in range(self.depth)]
+                    self.ev_comp = [torch.cuda.Event() for _ in range(self.depth)]
+                    self.ev_out = [torch.cuda.Event() for _ in range(self.depth)]
         self._last_key = key
         self._enqueue(src, dst)
         self.s_out.synchronize()
         return dst
+
+    def _validate(self, src: torch.Tensor, dst: torch.Tensor) -> None:
+        """A dtype mismatch would be converted silently by copy_ (a blocking CPU cast that defeats the asynchronous
+        pipeline, and data then processed with the wrong value range): refuse up front."""
+        for name, t in (("src", src), ("dst", dst)):
+            if not isinstance(t, torch.Tensor):
+                raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
+            if t.is_cuda:
+                raise ValueError(f"{name} must be a host tensor (use enhance_chain for device tensors)")
+            if t.dim() not in (3, 4) or tuple(t.shape[-2:]) != (self.h, self.w) or (t.dim() == 4 and t.shape[1] != 1):
+                raise ValueError(f"{name} must be (N, {self.h}, {self.w}) or (N, 1, {self.h}, {self.w}); got {tuple(t.shape)}")
+            if not t.is_contiguous():
+                raise ValueError(f"{name} must be contiguous")
+        if src.dtype != self.dtype:
+            raise TypeError(f"src dtype {src.dtype} does not match the pipeline's dtype {self.dtype}")
+        if dst.dtype != self.out_dtype:
+            raise TypeError(f"dst dtype {dst.dtype} does not match the pipeline's out_dtype {self.out_dtype}")
+        if src.shape[0] != dst.shape[0]:
+            raise ValueError("src and dst must hold the same number of slices")
 
     def _enqueue(self, src: torch.Tensor, dst: torch.Tensor) -> None:
         n = src.shape[0]
@@ -156,6 +183,7 @@ class HostVolumePipeline:
         self.h, self.w = int(plane_shape[-2]), int(plane_shape[-1])
         self.chunk, self.depth = int(chunk), int(depth)
         self.clip_limit, self.grid_size, self.mode, self.value_range = float(clip_limit), tuple(grid_size), mode, value_range
+        self.dtype = dtype
         with torch.cuda.device(self.device):
             self.s_in, self.s_comp, self.s_out = (torch.cuda.Stream() for _ in range(3))
             # chunk planes plus one halo plane on either side
@@ -174,6 +202,8 @@ class HostVolumePipeline:
             raise ValueError("HostVolumePipeline takes host tensors")
         if src.dim() != 3 or src.shape != dst.shape or src.shape[1:] != (self.h, self.w):
             raise ValueError("expected (D, H, W) volumes of the pipeline's plane shape")
+        if src.dtype != self.dtype or dst.dtype != self.dtype:
+            raise TypeError(f"src / dst dtype must be the pipeline's dtype {self.dtype}; got {src.dtype} / {dst.dtype}")
         d = int(src.shape[0])
         caller = torch.cuda.current_stream(self.device)
         for st in (self.s_in, self.s_comp, self.s_out):

@@ -304,7 +304,11 @@ int orc_clahe_apply_kornia(const float* in, float* out, int64_t n, int h, int w,
  * cv::CLAHE::apply — SURVEY.md §8(a) A1', Appendix A (bit-exact against cv2 4.13). */
 static void opencv_geom(int h, int w, int gh, int gw, geom_t* g) {
     g->h = h; g->w = w; g->gh = gh; g->gw = gw;
-    g->th = (h + gh - 1) / gh; g->tw = (w + gw - 1) / gw;
+    /* cv::CLAHE pads BOTH axes by tiles - dim % tiles as soon as EITHER is not divisible, so an axis that
+     * divides evenly then still grows by a full `tiles` pixels (tile size dim/tiles + 1); checked against
+     * cv2 4.13 on 512x500 and 300x512 (tests/golden/cv2_clahe.json). */
+    if (h % gh == 0 && w % gw == 0) { g->th = h / gh; g->tw = w / gw; }
+    else { g->th = (h + gh - h % gh) / gh; g->tw = (w + gw - w % gw) / gw; }
     g->hp = g->th * gh; g->wp = g->tw * gw;
 }
 

@@ -220,8 +220,12 @@ def equalize_clahe(x01, clip_limit=40.0, grid_size=(8, 8)) -> np.ndarray:
 
 # ------------------------------------------------------------------ CLAHE (OpenCV semantics, uint8)
 def opencv_tile_size(h, w, grid_size):
+    """cv::CLAHE pads both axes by tiles - dim % tiles when either is not divisible (a divisible axis then grows by
+    a full `tiles` pixels)."""
     gh, gw = grid_size
-    return -(-h // gh), -(-w // gw)
+    if h % gh == 0 and w % gw == 0:
+        return h // gh, w // gw
+    return (h + gh - h % gh) // gh, (w + gw - w % gw) // gw
 
 
 def opencv_clahe_hist(img, grid_size=(8, 8)) -> np.ndarray:

@@ -42,6 +42,12 @@ CASES = [
     ("u16_37x53_3x5_clip1.5", 37, 53, "uint16", 16, (3, 5), 1.5),
     ("u8_512_8x8_clip2", 512, 512, "uint8", 8, (8, 8), 2.0),
     ("u8_300x500_8x8_clip40", 300, 500, "uint8", 8, (8, 8), 40.0),
+    # one axis divisible, the other not: cv::CLAHE then pads the divisible axis by a full `tiles` pixels
+    ("u8_512x500_8x8_clip2", 512, 500, "uint8", 8, (8, 8), 2.0),
+    ("u8_300x512_8x8_clip2", 300, 512, "uint8", 8, (8, 8), 2.0),
+    ("u16_512x500_8x8_clip2", 512, 500, "uint16", 12, (8, 8), 2.0),
+    ("u16_300x512_8x8_clip2", 300, 512, "uint16", 16, (8, 8), 2.0),
+    ("u8_64x61_4x4_clip3", 64, 61, "uint8", 8, (4, 4), 3.0),
 ]
 
 

@@ -34,7 +34,7 @@ def test_error_strings():
 
     L = _ffi.lib()
     assert L.mie_error_string(0) == b"ok"
-    for code in range(-11, 0):
+    for code in range(-12, 0):
         assert L.mie_error_string(code) != b"unknown error"
     with pytest.raises(ValueError):
         _ffi.check(-6)
@@ -146,6 +146,29 @@ def test_newer_entry_points_reject_bad_arguments_before_any_launch():
     assert L.mie_chain_gauss_clahe_unsharp(fake, fake, 1, 1, 0, 512, 512, 262144, 512, 262144, 512, w9.ctypes.data, 9,
                                            w9.ctypes.data, 9, 8, 8, 2.0, w9.ctypes.data, 9, w9.ctypes.data, 9, 1, 0.0,
                                            65535.0, 3 | 4, fake, 0, None) == 0
+
+
+def test_round2_advice_validation_paths():
+    """a misaligned workspace is refused (MIE_E_ALIGN) instead of faulting in a 32-bit / 128-bit
+    access, and the 65 536-bin CLAHE validates the grid before it enters a division (was SIGFPE through the C ABI)."""
+    import numpy as np
+    from mie_b200 import _ffi
+
+    L = _ffi.lib()
+    w9 = np.ones(9, np.float32) / 9
+    fake = 0x10000
+    need = L.mie_chain_workspace_bytes(1, 512, 512, 8, 8)
+    common = (1, 512, 512, 262144, 512, 262144, 512, w9.ctypes.data, 9, w9.ctypes.data, 9, 8, 8, 2.0, w9.ctypes.data, 9,
+              w9.ctypes.data, 9, 1, 0.0, 65535.0, 3)
+    assert L.mie_chain_gauss_clahe_unsharp(fake, fake, 1, 1, *common, fake + 1, need, None) == -12
+    assert L.mie_chain_gauss_clahe_unsharp(fake, fake, 1, 1, *common, fake + 128, need, None) == -12
+    with pytest.raises(ValueError):
+        _ffi.check(-12)
+    # mie_clahe, uint16 + OpenCV semantics (65 536 bins): zero / negative grids and shapes return codes
+    for gh, gw, code in ((0, 8, -5), (8, 0, -5), (-3, 8, -5)):
+        assert L.mie_clahe(fake, fake, 1, 1, 1, 64, 64, 4096, 64, 4096, 64, gh, gw, 2.0, 1, 0.0, 65535.0, fake, 1 << 20,
+                           None) == code
+    assert L.mie_clahe(fake, fake, 1, 1, 1, 0, 64, 4096, 64, 4096, 64, 8, 8, 2.0, 1, 0.0, 65535.0, fake, 1 << 20, None) == -3
 
 
 def _fma32(a, b, c):

@@ -392,6 +392,11 @@ def test_chain_fused_bit_exact_and_equals_composition(dev, kind):
     dict(shape=(1, 1, 512, 512), grid=(2, 2)),                      # 256-px tiles -> unfused
     dict(shape=(1, 1, 96, 96), grid=(2, 2), dk=11),                 # 11 taps -> unfused
     dict(shape=(1, 1, 64, 64), grid=(8, 8), border="replicate"),    # 8-px tiles: many LUTs per block
+    # circular halos wrap to the opposite edge: the first / last blocks need LUTs of BOTH ends of the grid
+    dict(shape=(2, 1, 512, 512), grid=(8, 8), border="circular"),
+    dict(shape=(1, 1, 128, 192), grid=(4, 4), dk=5, sk=7, border="circular"),
+    dict(shape=(1, 1, 64, 64), grid=(8, 8), border="circular"),     # 8-px tiles, 64 LUTs staged per block
+    dict(shape=(1, 1, 256, 256), grid=(4, 4), border="constant"),
 ])
 @pytest.mark.parametrize("dtype", [np.uint16, np.int16, np.uint8, np.float32])
 def test_chain_geometries(dev, case, dtype):
