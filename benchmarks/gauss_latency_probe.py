@@ -1,5 +1,5 @@
 """Latency of gaussian_blur2d / unsharp_mask / median_blur for small batches of 512x512 uint16 slices (graph replay).
-MIE_GAUSS_NO_MARCH=1 selects the tile kernel.  python benchmarks/gauss_latency_probe.py"""
+Wrap the calls in `with M.kernel_policy('generic_gauss'):` to time the tile kernel.  python benchmarks/gauss_latency_probe.py"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)

@@ -70,6 +70,29 @@ enum mie_error {
 };
 
 int mie_abi_version(void);
+
+/* Kernel-selection policy (process-wide; a verification hook, not a tuning knob).  Every operator picks the tuned
+ * sm_100a kernel whenever the request's geometry / dtype / alignment allows and a generic kernel otherwise; both
+ * compute the same result bit for bit.  A set bit forces the generic variant for that operator although the tuned
+ * one applies, so that tests can compare the two on the same input.  Replaces what round 1 read from MIE_*
+ * environment variables: nothing in the library calls getenv().  mie_set_kernel_policy returns MIE_E_UNSUPPORTED
+ * for unknown bits; call it while no other thread is inside the library. */
+enum mie_kernel_policy {
+    MIE_POLICY_DEFAULT = 0,
+    MIE_POLICY_GENERIC_GAUSS = 1,          /* gauss_tile / gauss_generic kernels instead of the marching kernel */
+    MIE_POLICY_GENERIC_CLAHE = 2,          /* per-tile histogram + generic interpolation kernels */
+    MIE_POLICY_CLAHE_FLOAT_RULES = 4,      /* tuned CLAHE, but bins / indices from the float conversion, not the integer rules */
+    MIE_POLICY_GENERIC_EQUALIZE = 8,
+    MIE_POLICY_EQUALIZE_FLOAT_RULES = 16,
+    MIE_POLICY_GENERIC_MEDIAN = 32,        /* forgetful-selection tile kernels instead of the packed marching kernels */
+    MIE_POLICY_GENERIC_BILATERAL = 64,
+    MIE_POLICY_GENERIC_NLM = 128,
+    MIE_POLICY_CLAHE16_NO_CLUSTER = 256,   /* 65 536-bin CLAHE: one CTA per tile instead of a 2-CTA cluster */
+    MIE_POLICY_CLAHE16_TWO_SWEEP = 512,    /* 65 536-bin CLAHE: the two-sweep kernel of tiles >= 65 536 pixels */
+    MIE_POLICY_ALL = 1023
+};
+int mie_set_kernel_policy(unsigned mask);
+unsigned mie_get_kernel_policy(void);
 const char* mie_error_string(int code);
 /* SM count / compute capability of the current device (for grid sizing, tests). */
 int mie_device_info(int* sm_count, int* cc_major, int* cc_minor);

@@ -7,7 +7,7 @@ operator calls hand-written sm_100a CUDA kernels through the C ABI declared in
 include/mie.h; there is no CPU or PyTorch fallback.
 """
 from ._ffi import lib as _lib  # noqa: F401
-from ._ffi import value_range_mode
+from ._ffi import kernel_policy, value_range_mode
 from .chain import ChainConfig, ChainPlan, ChainRing, chain_workspace_bytes, enhance_chain
 from .enhance import clahe16_luts, clahe_apply, clahe_histograms, clahe_luts, equalize, equalize_clahe
 from .filters import bilateral_blur, denoise_nl_means, gaussian_blur2d, get_gaussian_kernel1d, median, median_blur, unsharp_mask
@@ -23,6 +23,6 @@ __all__ = [
     "denoise_nl_means",
     "ChainConfig", "ChainPlan", "ChainRing", "enhance_chain", "chain_workspace_bytes",
     "HostSlicePipeline", "enhance_chain_host", "HostVolumePipeline", "median3d_clahe_host",
-    "mse", "rmse", "psnr", "ssim", "mae", "value_range_mode",
+    "mse", "rmse", "psnr", "ssim", "mae", "value_range_mode", "kernel_policy",
     "shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab", "SlabPlan",
 ]

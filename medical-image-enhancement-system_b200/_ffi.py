@@ -30,6 +30,8 @@ _taps = [_p, _i, _p, _i]
 
 SIGNATURES = {
     "mie_abi_version": ([], _i),
+    "mie_set_kernel_policy": ([C.c_uint], _i),
+    "mie_get_kernel_policy": ([], C.c_uint),
     "mie_error_string": ([_i], C.c_char_p),
     "mie_device_info": ([C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)], _i),
     "mie_gaussian2d": ([_p, _p, _i, _i, *_planes, *_taps, _i, _f, _f, _p], _i),
@@ -90,6 +92,30 @@ def check(rc: int) -> None:
     if rc == -11:
         raise NotImplementedError(msg)
     raise RuntimeError(f"CUDA error {rc}: {msg}")
+
+
+POLICY = {"generic_gauss": 1, "generic_clahe": 2, "clahe_float_rules": 4, "generic_equalize": 8,
+          "equalize_float_rules": 16, "generic_median": 32, "generic_bilateral": 64, "generic_nlm": 128,
+          "clahe16_no_cluster": 256, "clahe16_two_sweep": 512}
+
+
+class kernel_policy:
+    """Context manager around mie_set_kernel_policy (include/mie.h): force the generic kernel of the named
+    operators inside the block — a verification hook for tests, e.g. `with kernel_policy("generic_median"): ...`."""
+
+    def __init__(self, *names: str):
+        self.mask = 0
+        for n in names:
+            self.mask |= POLICY[n]
+
+    def __enter__(self):
+        self.prev = lib().mie_get_kernel_policy()
+        check(lib().mie_set_kernel_policy(self.prev | self.mask))
+        return self
+
+    def __exit__(self, *exc):
+        check(lib().mie_set_kernel_policy(self.prev))
+        return False
 
 
 def stream_ptr(device: torch.device) -> int:

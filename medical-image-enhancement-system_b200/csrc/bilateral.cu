@@ -8,7 +8,6 @@
 // polynomial for 2^f (max rel err 1.7e-7) and an exponent-field add — the same sequence as
 // oracle/mie_oracle.c:mie_exp2n, so the result is reproducible bit for bit.  This op is FMA-pipe bound
 // (81 taps x 14 FMA-pipe operations), not HBM bound.
-#include <cstdlib>
 
 #include "chain_fast.cuh"
 
@@ -241,7 +240,7 @@ int bilateral_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h,
     const int tiles_x = ceil_div(w, 32), tiles_y = ceil_div(h, 32);
     const int64_t blocks = n * tiles_x * tiles_y;
     if (blocks > 2147483647LL) return MIE_E_SHAPE;
-    static const bool no_packed = [] { const char* e = getenv("MIE_BILATERAL_NO_PACKED"); return e && e[0] == '1'; }();
+    const bool no_packed = kernel_policy(MIE_POLICY_GENERIC_BILATERAL);
     if (!no_packed && ky == kx && ky >= 3 && ky <= 9) {   // square 3 / 5 / 7 / 9 windows: packed, fully unrolled kernel
         MIE_DISPATCH_SRC_DST(sd, dd, return (launch_bilateral_packed<SrcT, DstT>(
                                          ky, src, dst, ssn, ssh, dsn, dsh, h, w, tiles_x, tiles_y, (unsigned)blocks,

@@ -14,7 +14,6 @@
 // intermediates bit for bit (same operation order; tests/test_chain_gpu.py).
 // Shapes the fused kernels do not cover (CLAHE padding needed, tiles > 64 px,
 // non-square or > 9-tap kernels) run those three stages unfused.
-#include <cstdlib>
 
 #include "window.cuh"
 
@@ -226,13 +225,6 @@ static int launch_b(const ChainBArgs& a, const Taps& wx, const Taps& wy, int64_t
     return check_launch();
 }
 
-// Test / benchmark hook: 1 = keep the tiled tuned kernels even where the marching kernels apply
-// (MIE_CHAIN_NO_MARCH=1 in the environment; read once).
-static const bool g_disable_march = [] {
-    const char* e = getenv("MIE_CHAIN_NO_MARCH");
-    return e && e[0] == '1';
-}();
-
 static void fill_taps(Taps& t, const float* w, int k) {
     for (int i = 0; i < MIE_MAX_TAPS; ++i) t.w[i] = i < k ? w[i] : 0.f;
 }
@@ -334,7 +326,7 @@ int mie_chain_gauss_clahe_unsharp(const void* src, void* dst, int src_dtype, int
     // block per 64x64 tile).  Measured crossover on B200: ~24 slices of 512x512 (benchmarks/
     // chain_latency_probe.py), i.e. about 1.5 band-blocks per SM.
     const bool enough_bands = n * (int64_t)g.gh >= 222;
-    const bool march = fast_geo && march_chain_ok(g, kgx, kux) && !g_disable_march &&
+    const bool march = fast_geo && march_chain_ok(g, kgx, kux) &&
                        !(hints & MIE_CHAIN_PREFER_TILES) && (enough_bands || (hints & MIE_CHAIN_PREFER_MARCH)) &&
                        (int64_t)h * src_stride_h * 4 < (1LL << 31);  // 32-bit source-row offsets
     const bool fast = fast_geo;

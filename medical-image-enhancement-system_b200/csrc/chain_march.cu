@@ -17,7 +17,6 @@
 //   * global loads (4 pixels / 4 index bytes per thread and row) are issued four rows at a time, four
 //     to seven rows ahead of their use; source-row offsets (mirrored at the image border) come from a
 //     small shared-memory table instead of per-row index arithmetic.
-#include <cstdlib>
 
 #include "march.cuh"
 #include "window.cuh"
@@ -339,20 +338,11 @@ static int launch_a_march_win(const ChainAArgs& a, const Taps& wx, const Taps& w
 template <typename SrcT, int BORDER, bool LE1>
 static int launch_a_march_tbl(const ChainAArgs& a, const Taps& wx, const Taps& wy, unsigned blocks, cudaStream_t st) {
     const WinCvt cv = {};
-    // W <= 512: 128 threads per block, registers capped so that MINB blocks fit on an SM
-    static const int minb_env = [] { const char* e = getenv("MIE_MARCH_A_MINB"); return e ? atoi(e) : 5; }();
+    // W <= 512: 128 threads per block, registers capped so that five blocks fit on an SM (4 and 6 measured slower)
     const size_t smem = march_a_smem(a.g, (int)sizeof(SrcT));
     if (a.g.w <= 512) {
-        if (minb_env >= 6) {
-            MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 6>), 100 * 1024);
-            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 6><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
-        } else if (minb_env == 5) {
-            MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5>), 100 * 1024);
-            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
-        } else {
-            MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 4>), 100 * 1024);
-            chain_a_march_kernel<SrcT, BORDER, LE1, 128, 4><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
-        }
+        MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5>), 100 * 1024);
+        chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
     } else {
         MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2>), 100 * 1024);
         chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);

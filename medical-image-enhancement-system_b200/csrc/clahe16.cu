@@ -15,7 +15,6 @@
 // groups of images), so a batch never needs more LUT memory than fits in L2.
 #include <cooperative_groups.h>
 
-#include <cstdlib>
 
 #include "clahe.cuh"
 
@@ -447,8 +446,8 @@ int clahe16_luts_impl(const void* src, int64_t n, int h, int w, int64_t ssn, int
     if (tiles == 0) return MIE_OK;
     if (tiles > 2147483647LL) return MIE_E_SHAPE;
     const size_t smem = (size_t)(kHalf16 + kHalf16 / 32) * sizeof(int);
-    static const bool no_small = [] { const char* e = getenv("MIE_CLAHE16_NO_SMALL"); return e && e[0] == '1'; }();
-    static const bool no_cluster = [] { const char* e = getenv("MIE_CLAHE16_NO_CLUSTER"); return e && e[0] == '1'; }();
+    const bool no_small = kernel_policy(MIE_POLICY_CLAHE16_TWO_SWEEP);
+    const bool no_cluster = kernel_policy(MIE_POLICY_CLAHE16_NO_CLUSTER);
     if ((int64_t)g.th * g.tw < 65536 && !no_small && !no_cluster && tiles <= 1073741823LL) {
         // counts fit 16 bits: single pass, one tile per cluster of two CTAs
         const size_t csmem = (size_t)(kHalf16 / 2 + kHalf16 / 64) * sizeof(int);

@@ -7,7 +7,6 @@
 //     8-byte table entry per grey level (chain_fast.cu: chain_pack_cells_kernel), a block stages the
 //     (gw + 1) tables of one cell row in shared memory, and a pixel costs ONE shared-memory lookup;
 //     threads own 4 consecutive columns (64-bit loads / stores), no divides, no F2I.
-#include <cstdlib>
 
 #include "window.cuh"
 
@@ -211,14 +210,10 @@ clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells, WinCvt
 
 // ---------------------------------------------------------------- host side
 static const int kEsz[4] = {1, 2, 2, 4};
-static bool int_rules_disabled() {   // MIE_CLAHE_NO_INT_RULES=1: keep the float conversion of the input (A/B tests)
-    static const bool off = [] { const char* e = getenv("MIE_CLAHE_NO_INT_RULES"); return e && e[0] == '1'; }();
-    return off;
+static bool int_rules_disabled() {   // keep the float conversion of the input (cross-check of the integer bin rules)
+    return kernel_policy(MIE_POLICY_CLAHE_FLOAT_RULES);
 }
-static bool fast_disabled() {
-    static const bool off = [] { const char* e = getenv("MIE_CLAHE_NO_FAST"); return e && e[0] == '1'; }();
-    return off;
-}
+static bool fast_disabled() { return kernel_policy(MIE_POLICY_GENERIC_CLAHE); }
 
 bool clahe_lut_fast_ok(const ClaheGeom& g, int sd, const void* src, int64_t ssn, int64_t ssh, float lo, float hi) {
     if (fast_disabled()) return false;

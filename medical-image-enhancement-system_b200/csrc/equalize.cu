@@ -9,7 +9,6 @@
 // Three launches: per-plane histogram (shared-memory sub-histograms, warp-voted
 // adds, one global atomic per non-empty bin per block), LUT (one block per plane),
 // apply.
-#include <cstdlib>
 
 #include "window.cuh"
 
@@ -222,7 +221,7 @@ equalize_apply_fast_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst,
 
 static bool equalize_fast_ok(int sd, int dd, const void* src, const void* dst, int w, int64_t ssn, int64_t ssh,
                              int64_t dsn, int64_t dsh, float lo, float hi) {
-    static const bool off = [] { const char* e = getenv("MIE_EQUALIZE_NO_FAST"); return e && e[0] == '1'; }();
+    const bool off = kernel_policy(MIE_POLICY_GENERIC_EQUALIZE);
     static const int esz[4] = {1, 2, 2, 4};
     WinCvt cv;
     if (off || (w & 7) || range_mode(sd, lo, hi, &cv) < 0) return false;
@@ -269,7 +268,7 @@ int mie_equalize(const void* src, void* dst, int src_dtype, int dst_dtype, int64
         // float planes (kornia's native input) may hold values outside [0, 1] or NaN: they take the range-checked
         // code path of the windowed kernels (PixIO<float, true> is a plain load)
         const bool win = range_mode(src_dtype, lo, hi, &cv) == 1 || src_dtype == MIE_F32;
-        static const bool no_int = [] { const char* e = getenv("MIE_EQUALIZE_NO_INT_RULES"); return e && e[0] == '1'; }();
+        const bool no_int = kernel_policy(MIE_POLICY_EQUALIZE_FLOAT_RULES);
         const bool idx = !win && !no_int && int_rules_ok(src_dtype);
 #define MIE_EQ_HIST(T_)                                                                                            \
     if (win) equalize_hist_fast_kernel<T_, true, false><<<grid, 256, 0, st>>>((const T_*)src, src_stride_n, src_stride_h, h, w, rows, state, cv); \

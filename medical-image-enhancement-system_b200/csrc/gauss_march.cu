@@ -5,7 +5,6 @@
 // rows streamed through a bulk-copy (TMA) ring, row-pair buffers in shared memory, the vertical pass out
 // of a register ring, packed fma.rn.f32x2 in both passes.  For unsharp the centre pixels of the rows that
 // become complete are re-read from the row-pair buffers of four steps earlier.
-#include <cstdlib>
 
 #include "march.cuh"
 #include "window.cuh"
@@ -142,7 +141,7 @@ gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy, WinCvt cv) {
 bool gauss_march_ok(const void* src, const void* dst, int sd, int dd, int h, int w, int64_t ssn, int64_t ssh,
                     int64_t dsn, int64_t dsh, int kx, int ky, int border, float lo, float hi) {
     static const int esz[4] = {1, 2, 2, 4};
-    static const bool off = [] { const char* e = getenv("MIE_GAUSS_NO_MARCH"); return e && e[0] == '1'; }();
+    const bool off = kernel_policy(MIE_POLICY_GENERIC_GAUSS);
     if (off) return false;
     if (kx != 9 || ky != 9) return false;
     if (w % 128 != 0 || w > 1024 || h % kTile != 0) return false;

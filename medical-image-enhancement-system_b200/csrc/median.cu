@@ -20,7 +20,6 @@
 // of N/2+2 candidates, repeatedly drop its minimum and maximum (neither can be
 // the median) and insert the next sample.  All indices are compile-time, so the
 // whole network is min/max instructions on registers.
-#include <cstdlib>
 
 #include "mie_common.cuh"
 
@@ -852,7 +851,7 @@ median3x3_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int
 
 static int try_median3x3_f32(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int64_t dsn,
                              int64_t dsh, int border, cudaStream_t st) {
-    static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
+    const bool off = kernel_policy(MIE_POLICY_GENERIC_MEDIAN);
     if (off || (w & 3) || h < 2) return -1;
     if (((uintptr_t)src % 16) || ((ssn * 4) % 16) || ((ssh * 4) % 16)) return -1;
     if (((uintptr_t)dst % 16) || ((dsn * 4) % 16) || ((dsh * 4) % 16)) return -1;
@@ -871,7 +870,7 @@ static int try_median3x3_f32(const void* src, void* dst, int64_t n, int h, int w
 template <typename T>
 static int try_median_packed(const void* src, void* dst, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
                                 int64_t dsn, int64_t dsh, int border, cudaStream_t st, int k = 3) {
-    static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
+    const bool off = kernel_policy(MIE_POLICY_GENERIC_MEDIAN);
     if (off || (w & 7) || h < k - 1) return -1;
     constexpr int esz = (int)sizeof(T), al = 8 * esz;   // one 8-pixel vector per lane and row
     if (((uintptr_t)src % al) || ((ssn * esz) % al) || ((ssh * esz) % al)) return -1;
@@ -897,7 +896,7 @@ static int launch_median3d(const void* src, void* dst, int d, int h, int w, int6
                            int64_t dsh, const void* lo, const void* hi, int border, cudaStream_t st) {
     const int zchunk = d >= 64 ? 32 : (d >= 16 ? 8 : d);
     if constexpr (sizeof(T) == 2) {
-        static const bool off = [] { const char* e = getenv("MIE_MEDIAN_NO_PACKED"); return e && e[0] == '1'; }();
+        const bool off = kernel_policy(MIE_POLICY_GENERIC_MEDIAN);
         const bool words_ok = !(w & 1) && !(ssd & 1) && !(ssh & 1) && !(dsd & 1) && !(dsh & 1) &&
                               !((uintptr_t)src & 3) && !((uintptr_t)dst & 3) && !((uintptr_t)lo & 3) &&
                               !((uintptr_t)hi & 3);

@@ -2,9 +2,21 @@
 #include "mie_common.cuh"
 #include "window.cuh"
 
+namespace mie {
+unsigned g_kernel_policy = MIE_POLICY_DEFAULT;
+}
+
 extern "C" {
 
 int mie_abi_version(void) { return MIE_ABI_VERSION; }
+
+int mie_set_kernel_policy(unsigned mask) {
+    if (mask & ~(unsigned)MIE_POLICY_ALL) return MIE_E_UNSUPPORTED;
+    mie::g_kernel_policy = mask;
+    return MIE_OK;
+}
+
+unsigned mie_get_kernel_policy(void) { return mie::g_kernel_policy; }
 
 const char* mie_error_string(int code) {
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -121,6 +121,12 @@ inline int make_clahe_geom(int h, int w, int gh, int gw, int semantics, ClaheGeo
 }
 
 // ---------------------------------------------------------------- host plumbing
+// Process-wide kernel-selection mask set through mie_set_kernel_policy (include/mie.h): a verification hook that
+// routes a request to the generic kernel although a tuned one covers it, so that tests can compare both on the
+// same input.  Defined in mie_abi.cu; never read from the environment.
+extern unsigned g_kernel_policy;
+inline bool kernel_policy(unsigned bit) { return (g_kernel_policy & bit) != 0; }
+
 inline int check_launch() {
     cudaError_t e = cudaPeekAtLastError();
     return e == cudaSuccess ? MIE_OK : (int)e;

@@ -16,7 +16,6 @@
 // sums in registers) and accumulates the weighted shifted pixel — ~35 instructions per pixel and shift
 // instead of ~110 for the direct 36-term patch distance.  exp() is ex2.approx (MUFU): the result is
 // within the north star's fp32 tolerance (rel 1e-5) of the float64 oracle, not bit-exact.
-#include <cstdlib>
 
 #include "mie_common.cuh"
 
@@ -240,7 +239,7 @@ int nlm_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w
     a.inv_h2s2 = (float)(1.0 / ((double)hpar * hpar * s * s));
     a.var_term = (float)((double)(2 * o) * (2 * o) * 2.0 * (double)sigma * sigma);
     a.lo = lo; a.rg = hi - lo;
-    static const bool no_march = [] { const char* e = getenv("MIE_NLM_NO_MARCH"); return e && e[0] == '1'; }();
+    const bool no_march = kernel_policy(MIE_POLICY_GENERIC_NLM);
     if (!no_march) {
 #define MIE_NLM_MARCH(O_)                                                                                      \
     {                                                                                                          \
