@@ -66,7 +66,8 @@ enum mie_error {
     MIE_E_WORKSPACE = -9,   /* workspace too small */
     MIE_E_RANGE = -10,      /* hi <= lo for an integer dtype */
     MIE_E_UNSUPPORTED = -11,/* valid request this build does not implement */
-    MIE_E_ALIGN = -12       /* workspace (or a buffer a tuned kernel needs aligned) is not 256-byte aligned */
+    MIE_E_ALIGN = -12,      /* workspace (or a buffer a tuned kernel needs aligned) is not 256-byte aligned */
+    MIE_E_NCCL_BASE = -100  /* mie_halo_exchange_z: ncclResult_t r of a failed NCCL call is returned as -100 - r */
 };
 
 int mie_abi_version(void);
@@ -257,6 +258,23 @@ int mie_ssim_sums(const void* a, const void* b, int dtype, int64_t n, int h, int
                   int64_t a_stride_n, int64_t a_stride_h, int64_t b_stride_n, int64_t b_stride_h,
                   int ws, double c1, double c2,
                   double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ z-halo exchange (BASELINE.json config 3)
+ * The one exchange step of the path: a volume sharded into z-slabs, one per rank, needs the
+ * neighbouring slab's boundary plane on every interior face before mie_median3d(halo_lo, halo_hi) can run.
+ * `nccl_comm` is the caller's ncclComm_t (passed as void*; from torch.distributed: ProcessGroupNCCL._comm_ptr())
+ * whose rank numbering `rank` / `world` use.  Enqueues, in ONE NCCL group on `stream`:
+ *     rank > 0        : ncclSend(first_plane -> rank-1), ncclRecv(halo_lo <- rank-1)
+ *     rank < world-1  : ncclSend(last_plane  -> rank+1), ncclRecv(halo_hi <- rank+1)
+ * plane_bytes each (h*w*element size; shipped as bytes).  Pointers of a missing neighbour may be NULL.  Every rank
+ * of the communicator must make the call.  No allocation, no synchronisation; capturable into a CUDA graph.
+ * NCCL is not linked into the library: the four entry points are resolved from the libnccl.so.2 already loaded into
+ * the process, so the calls reach the same NCCL that created `nccl_comm`; MIE_E_UNSUPPORTED if there is none
+ * (mie_halo_exchange_available() == 0).  world == 1 is a no-op.  NCCL failures: -100 - ncclResult_t. */
+int mie_halo_exchange_available(void);
+int mie_halo_exchange_z(void* nccl_comm, int rank, int world,
+                        const void* first_plane, const void* last_plane,
+                        void* halo_lo, void* halo_hi, size_t plane_bytes, void* stream);
 
 /* ------------------------------------------------------------------ fused chain (BASELINE.json config 2)
  * Gaussian denoise -> CLAHE -> unsharp mask in two launches; equals

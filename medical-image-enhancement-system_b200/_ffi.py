@@ -53,6 +53,8 @@ SIGNATURES = {
     "mie_metric_workspace_bytes": ([_i64, _i, _i, _i], _sz),
     "mie_sqdiff_sums": ([_p, _p, _i, *_planes, _p, _p, _sz, _p], _i),
     "mie_ssim_sums": ([_p, _p, _i, *_planes, _i, _d, _d, _p, _p, _sz, _p], _i),
+    "mie_halo_exchange_available": ([], _i),
+    "mie_halo_exchange_z": ([_p, _i, _i, _p, _p, _p, _p, _sz, _p], _i),
     "mie_chain_workspace_bytes": ([_i64, _i, _i, _i, _i], _sz),
     "mie_chain_gauss_clahe_unsharp": (
         [_p, _p, _i, _i, *_planes, *_taps, _i, _i, _d, *_taps, _i, _f, _f, _i, _p, _sz, _p], _i),

@@ -20,6 +20,18 @@ unsigned mie_get_kernel_policy(void) { return mie::g_kernel_policy; }
 
 const char* mie_error_string(int code) {
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    if (code <= MIE_E_NCCL_BASE) {
+        switch (MIE_E_NCCL_BASE - code) {   // ncclResult_t
+            case 1: return "NCCL: unhandled CUDA error";
+            case 2: return "NCCL: unhandled system error";
+            case 3: return "NCCL: internal error";
+            case 4: return "NCCL: invalid argument";
+            case 5: return "NCCL: invalid usage";
+            case 6: return "NCCL: remote error";
+            case 7: return "NCCL: operation in progress";
+            default: return "NCCL: error";
+        }
+    }
     switch (code) {
         case MIE_OK: return "ok";
         case MIE_E_NULL: return "null pointer argument";

@@ -31,18 +31,32 @@ def _worker(rank, world, port, out_dir):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
     try:
+        # the data plane is native: the process group's own ncclComm_t is handed to mie_halo_exchange_z
+        from mie_b200 import volume as V
+        assert V.nccl_comm_ptr(dev) != 0, "native NCCL halo exchange not in use"
+        # the C ABI called directly: plane r goes to both neighbours of rank r
+        mine = torch.full((64, 96), rank + 1, dtype=torch.int16, device=dev)
+        lo_b, hi_b = torch.zeros_like(mine), torch.zeros_like(mine)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        rc = M._lib().mie_halo_exchange_z(V.nccl_comm_ptr(dev), rank, world, mine.data_ptr(), mine.data_ptr(),
+                                          lo_b.data_ptr(), hi_b.data_ptr(), mine.numel() * 2, st)
+        assert rc == 0, rc
+        torch.cuda.synchronize()
+        assert int(lo_b[0, 0]) == (rank if rank > 0 else 0) and int(hi_b[-1, -1]) == (rank + 2 if rank < world - 1 else 0)
         vol = synthetic.phantom_volume((37, 128, 192), np.int16, seed=5)  # ragged split on purpose
         z0, z1 = M.shard_range(vol.shape[0], world, rank)
         slab = torch.from_numpy(vol[z0:z1].copy()).to(dev)
         out = M.median3d_clahe_slab(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0))
         np.save(os.path.join(out_dir, f"vol{rank}.npy"), out.cpu().numpy())
         # the same step captured into a CUDA graph (NCCL halo exchange included) and replayed on new data
-        plan = M.SlabPlan(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0))
-        assert torch.equal(plan.replay(), out)
-        vol2 = synthetic.phantom_volume((37, 128, 192), np.int16, seed=7)
-        slab.copy_(torch.from_numpy(vol2[z0:z1].copy()).to(dev))
-        np.save(os.path.join(out_dir, f"vol2_{rank}.npy"), plan.replay().cpu().numpy())
-        plan.close()
+        with M.SlabPlan(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0)) as plan:
+            assert torch.equal(plan.replay(), out)
+            vol2 = synthetic.phantom_volume((37, 128, 192), np.int16, seed=7)
+            slab.copy_(torch.from_numpy(vol2[z0:z1].copy()).to(dev))
+            np.save(os.path.join(out_dir, f"vol2_{rank}.npy"), plan.replay().cpu().numpy())
+        # a plan nobody closes must not hang destroy_process_group() in the finally block below
+        forgotten = M.SlabPlan(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0))
+        forgotten.replay()
         x = synthetic.phantom((10, 1, 256, 256), np.uint16, seed=6)
         s0, s1 = M.shard_range(10, world, rank)
         y = M.enhance_chain(torch.from_numpy(x[s0:s1].copy()).to(dev), M.ChainConfig(grid_size=(4, 4)))
