@@ -291,7 +291,7 @@ def run_reference(args):
         "e2e": {"value": round(value, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- GPU helpers
@@ -797,13 +797,33 @@ def run_ours(args):
             "checksum": checksum,
             "sub": sub,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _claim_stdout():
+    """Exactly ONE line may reach stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG=VERSION is set on the box), so fd 1 is pointed at stderr for the whole run and the JSON line is written
+    to the saved descriptor at the end."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+_OUT = None
+
+
+def emit(line: dict) -> None:
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
 def main():
+    global _OUT
+    _OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

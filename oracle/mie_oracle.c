@@ -737,3 +737,258 @@ int orc_equalize(const float* in, float* out, int64_t n, int h, int w) {
     }
     return 0;
 }
+
+/* ====================================================================== scikit-image exposure / restoration
+ * RECALLED restatements (scikit-image 0.26.0, reference pyproject.toml:12 — the package is
+ * not on disk: parity unpinned).  Per-pixel formulation, structurally independent of the array-level numpy twin in
+ * oracle/skimage_twin.py; the two must agree bit for bit (tests/test_skimage_exposure.py).  The CUDA kernels
+ * (csrc/sk_exposure.cu, csrc/sk_bilateral.cu) follow THIS formulation.  All float64 arithmetic is plain IEEE in the
+ * order written (-ffp-contract=off). */
+
+/* img_as_float of one code (skimage.util.dtype): unsigned v / max; signed (2 v + 1) / (max - min). */
+static inline double sk_as_float(int dtype, int v) {
+    if (dtype == DT_U8) return (double)v / 255.0;
+    if (dtype == DT_U16) return (double)v / 65535.0;
+    return ((double)v * 2.0 + 1.0) / 65535.0; /* int16: [-1, 1] */
+}
+static inline int sk_code(const void* img, int dtype, size_t p) {
+    if (dtype == DT_U8) return ((const uint8_t*)img)[p];
+    if (dtype == DT_U16) return ((const uint16_t*)img)[p];
+    return ((const int16_t*)img)[p];
+}
+
+/* numpy.pad(mode='reflect') index (no edge repeat; repeated reflection for pads longer than the axis). */
+static inline int sk_reflect(int i, int n) {
+    if (n == 1) return 0;
+    int p = 2 * (n - 1);
+    int m = i % p;
+    if (m < 0) m += p;
+    return m < n ? m : p - m;
+}
+
+/* Stage 1 of equalize_adapthist: img_as_float -> rescale_intensity(out_range=(0, 2^14 - 1)) -> np.round -> uint16.
+ * One image (h x w) of an integer dtype or float32 (float32 images are processed in float32, like upstream). */
+int orc_sk_adapthist_grey(const void* img, int dtype, int h, int w, uint16_t* grey) {
+    const size_t px = (size_t)h * w;
+    if (dtype == DT_F32) {
+        const float* f = (const float*)img;
+        float mn = f[0], mx = f[0];
+        for (size_t p = 1; p < px; ++p) { if (f[p] < mn) mn = f[p]; if (f[p] > mx) mx = f[p]; }
+        for (size_t p = 0; p < px; ++p) {
+            float g;
+            if (mn != mx) { float t = (f[p] - mn) / (mx - mn); g = t * 16383.0f + 0.0f; }
+            else g = fminf(fmaxf(f[p], 0.0f), 16383.0f);
+            grey[p] = (uint16_t)(int64_t)rintf(g);
+        }
+        return 0;
+    }
+    int vmin = sk_code(img, dtype, 0), vmax = vmin;
+    for (size_t p = 1; p < px; ++p) { int v = sk_code(img, dtype, p); if (v < vmin) vmin = v; if (v > vmax) vmax = v; }
+    const double fmin_ = sk_as_float(dtype, vmin), fmax_ = sk_as_float(dtype, vmax);
+    for (size_t p = 0; p < px; ++p) {
+        double f = sk_as_float(dtype, sk_code(img, dtype, p)), g;
+        if (vmin != vmax) { double t = (f - fmin_) / (fmax_ - fmin_); g = t * 16383.0 + 0.0; }
+        else g = fmin(fmax(f, 0.0), 16383.0);
+        grey[p] = (uint16_t)(int64_t)rint(g); /* np.round: half to even; astype(uint16) */
+    }
+    return 0;
+}
+
+/* skimage.exposure._adapthist.clip_histogram on one histogram (in place). */
+static void sk_clip_histogram(int64_t* hist, int nbins, int64_t clim) {
+    int64_t n_excess = 0;
+    for (int b = 0; b < nbins; ++b)
+        if (hist[b] > clim) { n_excess += hist[b] - clim; hist[b] = clim; }
+    const int64_t bin_incr = n_excess / nbins;
+    const int64_t upper = clim - bin_incr;
+    /* the mid mask is taken AFTER the low bins were raised (upstream evaluates it on the updated histogram), so a low
+     * bin that lands in [upper, clim) is raised again, to the limit, and the excess shrinks accordingly */
+    for (int b = 0; b < nbins; ++b)
+        if (hist[b] < upper) { n_excess -= bin_incr; hist[b] += bin_incr; }
+    for (int b = 0; b < nbins; ++b)
+        if (hist[b] >= upper && hist[b] < clim) { n_excess += hist[b] - clim; hist[b] = clim; }
+    while (n_excess > 0) {
+        const int64_t prev = n_excess;
+        for (int index = 0; index < nbins; ++index) {
+            int64_t under = 0;
+            for (int b = 0; b < nbins; ++b) under += hist[b] < clim;
+            int64_t step = under / n_excess;
+            if (step < 1) step = 1;
+            int64_t given = 0;
+            for (int64_t b = index; b < nbins; b += step)
+                if (hist[b] < clim) { hist[b] += 1; ++given; }
+            n_excess -= given;
+            if (n_excess <= 0) break;
+        }
+        if (prev == n_excess) break;
+    }
+}
+
+/* _clahe on the 2^14-level image: per-pixel coordinates instead of upstream's block reshapes.
+ * Contextual regions (histogram blocks) tile the ORIGINAL image from its origin with kernel (kr, kc) — ceil(h/kr) x
+ * ceil(w/kc) of them, the far ones completed by numpy 'reflect' padding; a pixel at (y, x) lies in interpolation block
+ * ((y + kr/2) / kr, (x + kc/2) / kc) at position ((y + kr/2) % kr, (x + kc/2) % kc), blends the mappings of the regions
+ * clamp(block - 1) and clamp(block) per axis with coefficients pos / k, accumulating float32(mapped * coef_x * coef_y) in
+ * the order (row,col) = (0,0), (0,1), (1,0), (1,1), and truncates to uint16. */
+int orc_sk_clahe(const uint16_t* grey, int h, int w, int kr, int kc, double clip_limit, int nbins, uint16_t* out,
+                 int64_t* maps_out /* optional: nbr * nbc * nbins */) {
+    if (kr <= 0 || kc <= 0 || nbins <= 0 || nbins > 16384) return -3;
+    const int nbr = (h + kr - 1) / kr, nbc = (w + kc - 1) / kc;
+    const int bin_size = 1 + 16384 / nbins;
+    const int64_t kernel_elements = (int64_t)kr * kc;
+    int64_t clim;
+    if (clip_limit > 0.0) {
+        double c = clip_limit * (double)kernel_elements;
+        if (c < 1.0) c = 1.0;
+        clim = (int64_t)c;
+    } else {
+        clim = 65535; /* np.iinfo(uint16).max: "no clipping" */
+    }
+    int64_t* maps = (int64_t*)malloc((size_t)nbr * nbc * nbins * sizeof(int64_t));
+    if (!maps) return -1;
+    const double scale = 16383.0 / (double)kernel_elements;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < nbr * nbc; ++b) {
+        const int bi = b / nbc, bj = b % nbc;
+        int64_t* hist = maps + (size_t)b * nbins;
+        memset(hist, 0, (size_t)nbins * sizeof(int64_t));
+        for (int r = 0; r < kr; ++r) {
+            const int sy = sk_reflect(bi * kr + r, h);
+            for (int c = 0; c < kc; ++c) {
+                const int sx = sk_reflect(bj * kc + c, w);
+                hist[grey[(size_t)sy * w + sx] / bin_size] += 1;
+            }
+        }
+        sk_clip_histogram(hist, nbins, clim);
+        int64_t cum = 0;
+        for (int k = 0; k < nbins; ++k) { /* map_histogram */
+            cum += hist[k];
+            double v = (double)cum * scale;
+            v += 0.0;
+            if (v > 16383.0) v = 16383.0;
+            hist[k] = (int64_t)v;
+        }
+    }
+    if (maps_out) memcpy(maps_out, maps, (size_t)nbr * nbc * nbins * sizeof(int64_t));
+    const int r0 = kr / 2, c0 = kc / 2;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < h; ++y) {
+        const int py = y + r0, by = py / kr, ry = py % kr;
+        const double cy = (double)ry / (double)kr;
+        int hb_r[2] = {by - 1, by};
+        for (int e = 0; e < 2; ++e) { if (hb_r[e] < 0) hb_r[e] = 0; if (hb_r[e] > nbr - 1) hb_r[e] = nbr - 1; }
+        const double wy[2] = {1.0 - cy, cy};
+        for (int x = 0; x < w; ++x) {
+            const int pxx = x + c0, bx = pxx / kc, rx = pxx % kc;
+            const double cx = (double)rx / (double)kc;
+            int hb_c[2] = {bx - 1, bx};
+            for (int e = 0; e < 2; ++e) { if (hb_c[e] < 0) hb_c[e] = 0; if (hb_c[e] > nbc - 1) hb_c[e] = nbc - 1; }
+            const double wx[2] = {1.0 - cx, cx};
+            const int bin = grey[(size_t)y * w + x] / bin_size;
+            float acc = 0.0f;
+            for (int er = 0; er < 2; ++er)
+                for (int ec = 0; ec < 2; ++ec) {
+                    const int64_t m = maps[((size_t)hb_r[er] * nbc + hb_c[ec]) * nbins + bin];
+                    const double coef = wx[ec] * wy[er];
+                    acc = acc + (float)((double)m * coef);
+                }
+            out[(size_t)y * w + x] = (uint16_t)acc;
+        }
+    }
+    free(maps);
+    return 0;
+}
+
+/* Last stage of equalize_adapthist: rescale_intensity(out_range=(0, 1)) of the uint16 CLAHE result as float64
+ * (as_f32 != 0: float32 input images keep float32 arithmetic, like upstream). */
+int orc_sk_rescale01(const uint16_t* c, int h, int w, int as_f32, void* out) {
+    const size_t px = (size_t)h * w;
+    uint16_t mn = c[0], mx = c[0];
+    for (size_t p = 1; p < px; ++p) { if (c[p] < mn) mn = c[p]; if (c[p] > mx) mx = c[p]; }
+    for (size_t p = 0; p < px; ++p) {
+        if (as_f32) {
+            float v = (float)c[p], r;
+            if (mn != mx) { r = (v - (float)mn) / ((float)mx - (float)mn); r = r * 1.0f + 0.0f; }
+            else r = fminf(fmaxf(v, 0.0f), 1.0f);
+            ((float*)out)[p] = r;
+        } else {
+            double v = (double)c[p], r;
+            if (mn != mx) { r = (v - (double)mn) / ((double)mx - (double)mn); r = r * 1.0 + 0.0; }
+            else r = fmin(fmax(v, 0.0), 1.0);
+            ((double*)out)[p] = r;
+        }
+    }
+    return 0;
+}
+
+/* skimage.exposure.equalize_hist on one INTEGER image: one bin per integer value between min and max, cdf = cumsum /
+ * total (float64), out = np.interp(image, centers, cdf) = cdf[v - min] because every pixel sits on a bin centre. */
+int orc_sk_equalize_hist(const void* img, int dtype, int h, int w, double* out) {
+    if (dtype == DT_F32) return -2;
+    const size_t px = (size_t)h * w;
+    int vmin = sk_code(img, dtype, 0), vmax = vmin;
+    for (size_t p = 1; p < px; ++p) { int v = sk_code(img, dtype, p); if (v < vmin) vmin = v; if (v > vmax) vmax = v; }
+    const int nb = vmax - vmin + 1;
+    int64_t* hist = (int64_t*)calloc((size_t)nb, sizeof(int64_t));
+    if (!hist) return -1;
+    for (size_t p = 0; p < px; ++p) hist[sk_code(img, dtype, p) - vmin] += 1;
+    for (int b = 1; b < nb; ++b) hist[b] += hist[b - 1];
+    const double total = (double)hist[nb - 1];
+    for (size_t p = 0; p < px; ++p) out[p] = (double)hist[sk_code(img, dtype, p) - vmin] / total;
+    free(hist);
+    return 0;
+}
+
+/* skimage.restoration.denoise_bilateral on one 2-D single-channel image of an integer dtype (float64 arithmetic) —
+ * the loop of the upstream Cython kernel.  color_lut (bins entries) and range_lut (win*win entries, row-major) are
+ * computed by the caller (numpy exp, as upstream does in Python).  mode: 0 constant(cval), 1 edge, 2 symmetric,
+ * 3 reflect, 4 wrap.  Negative images are shifted by their minimum first and shifted back at the end. */
+static inline int sk_border(int i, int n, int mode) {
+    if (i >= 0 && i < n) return i;
+    if (mode == 1) return i < 0 ? 0 : n - 1;
+    if (mode == 2) { int p = 2 * n; int m = i % p; if (m < 0) m += p; return m < n ? m : p - 1 - m; }
+    if (mode == 3) return sk_reflect(i, n);
+    if (mode == 4) { int m = i % n; return m < 0 ? m + n : m; }
+    return -1;
+}
+int orc_sk_bilateral(const void* img, int dtype, int h, int w, int win, int bins, int mode, double cval,
+                     const double* color_lut, const double* range_lut, double* out) {
+    if (dtype == DT_F32) return -2;
+    const size_t px = (size_t)h * w;
+    int vmin = sk_code(img, dtype, 0), vmax = vmin;
+    for (size_t p = 1; p < px; ++p) { int v = sk_code(img, dtype, p); if (v < vmin) vmin = v; if (v > vmax) vmax = v; }
+    const double min_value = sk_as_float(dtype, vmin);
+    double max_value = sk_as_float(dtype, vmax);
+    if (vmin == vmax) { for (size_t p = 0; p < px; ++p) out[p] = min_value; return 0; }
+    const int shift = min_value < 0.0;
+    if (shift) max_value = max_value - min_value;
+    const double dist_scale = (double)bins / max_value;
+    const int ext = (win - 1) / 2;
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < h; ++r)
+        for (int c = 0; c < w; ++c) {
+            double centre = sk_as_float(dtype, sk_code(img, dtype, (size_t)r * w + c));
+            if (shift) centre = centre - min_value;
+            double total_v = 0.0, total_w = 0.0;
+            for (int kr = 0; kr < win; ++kr) {
+                const int rr = sk_border(r + kr - ext, h, mode);
+                for (int kc = 0; kc < win; ++kc) {
+                    const int cc = sk_border(c + kc - ext, w, mode);
+                    double v;
+                    if (rr < 0 || cc < 0) v = cval; /* np.pad(constant) happens AFTER the shift: the pad value is cval itself */
+                    else { v = sk_as_float(dtype, sk_code(img, dtype, (size_t)rr * w + cc)); if (shift) v = v - min_value; }
+                    const double t = centre - v;
+                    const double dist = sqrt(t * t);
+                    int64_t b = (int64_t)(dist * dist_scale);
+                    if (b > bins - 1) b = bins - 1;
+                    const double weight = range_lut[kr * win + kc] * color_lut[b];
+                    total_v = total_v + v * weight;
+                    total_w = total_w + weight;
+                }
+            }
+            double o = total_v / total_w;
+            if (shift) o = o + min_value;
+            out[(size_t)r * w + c] = o;
+        }
+    return 0;
+}

@@ -63,6 +63,11 @@ class _Sig:
     orc_exp2n = ([_p, _p, _i64], None)
     orc_bilateral = ([_p, _p, _i64, _i, _i, _p, _i, _i, _f, _i], _i)
     orc_equalize = ([_p, _p, _i64, _i, _i], _i)
+    orc_sk_adapthist_grey = ([_p, _i, _i, _i, _p], _i)
+    orc_sk_clahe = ([_p, _i, _i, _i, _i, _d, _i, _p, _p], _i)
+    orc_sk_rescale01 = ([_p, _i, _i, _i, _p], _i)
+    orc_sk_equalize_hist = ([_p, _i, _i, _i, _p], _i)
+    orc_sk_bilateral = ([_p, _i, _i, _i, _i, _i, _i, _d, _p, _p, _p], _i)
 
 
 def _ptr(a: np.ndarray):
@@ -442,3 +447,86 @@ def sewar_ssim(GT, P, ws=11, K1=0.01, K2=0.03, MAX=None):
         ss.append(np.mean(ssim_map))
         cs.append(np.mean(cs_map))
     return float(np.mean(ss)), float(np.mean(cs))
+
+
+# ------------------------------------------------------------------ scikit-image exposure / restoration (RECALLED)
+SK_MODES = {"constant": 0, "edge": 1, "symmetric": 2, "reflect": 3, "wrap": 4}
+
+
+def sk_adapthist_kernel(shape, kernel_size):
+    if kernel_size is None:
+        return [max(s // 8, 1) for s in shape]
+    if isinstance(kernel_size, (int, float)):
+        return [int(kernel_size)] * len(shape)
+    if len(kernel_size) != len(shape):
+        raise ValueError(f"Incorrect value of `kernel_size`: {kernel_size}")
+    return [int(k) for k in kernel_size]
+
+
+def sk_equalize_adapthist(image, kernel_size=None, clip_limit=0.01, nbins=256, return_stages=False):
+    """skimage.exposure.equalize_adapthist on ONE 2-D image (per-pixel C restatement; see mie_oracle.c)."""
+    x = np.ascontiguousarray(image)
+    if x.ndim != 2 or x.dtype not in _DT:
+        raise ValueError("expected one 2-D image of dtype uint8 / uint16 / int16 / float32")
+    h, w = x.shape
+    kr, kc = sk_adapthist_kernel(x.shape, kernel_size)
+    grey = np.empty((h, w), np.uint16)
+    _check(lib().orc_sk_adapthist_grey(_ptr(x), _DT[x.dtype], h, w, _ptr(grey)))
+    c = np.empty((h, w), np.uint16)
+    nbr, nbc = -(-h // kr), -(-w // kc)
+    maps = np.empty((nbr, nbc, nbins), np.int64)
+    _check(lib().orc_sk_clahe(_ptr(grey), h, w, kr, kc, float(clip_limit), int(nbins), _ptr(c), _ptr(maps)))
+    f32 = x.dtype == np.float32
+    out = np.empty((h, w), np.float32 if f32 else np.float64)
+    _check(lib().orc_sk_rescale01(_ptr(c), h, w, int(f32), _ptr(out)))
+    if return_stages:
+        return out, {"grey": grey, "clahe": c, "maps": maps}
+    return out
+
+
+def sk_equalize_hist(image):
+    x = np.ascontiguousarray(image)
+    if x.ndim != 2 or x.dtype not in _DT or x.dtype == np.float32:
+        raise ValueError("expected one 2-D image of dtype uint8 / uint16 / int16")
+    out = np.empty(x.shape, np.float64)
+    _check(lib().orc_sk_equalize_hist(_ptr(x), _DT[x.dtype], x.shape[0], x.shape[1], _ptr(out)))
+    return out
+
+
+def sk_bilateral_luts(bins, sigma_color, max_value, win_size, sigma_spatial):
+    """The two LUTs upstream builds in Python (numpy exp, float64): colour weights over [0, max_value) and the spatial
+    Gaussian of the win_size x win_size window."""
+    values = np.linspace(0, max_value, bins, endpoint=False)
+    color = np.exp(-0.5 * (values ** 2 / sigma_color ** 2))
+    ext = (win_size - 1) // 2
+    g = np.arange(-ext, ext + 1)
+    rr, cc = np.meshgrid(g, g, indexing="ij")
+    spatial = np.exp(-0.5 * (np.hypot(rr, cc) ** 2 / sigma_spatial ** 2)).ravel()
+    return np.ascontiguousarray(color), np.ascontiguousarray(spatial)
+
+
+def sk_denoise_bilateral(image, win_size=None, sigma_color=None, sigma_spatial=1, bins=10000, mode="constant", cval=0):
+    """skimage.restoration.denoise_bilateral on ONE 2-D integer image (per-pixel C restatement)."""
+    import math
+
+    x = np.ascontiguousarray(image)
+    if x.ndim != 2 or x.dtype not in _DT or x.dtype == np.float32:
+        raise ValueError("expected one 2-D image of dtype uint8 / uint16 / int16")
+    info = np.iinfo(x.dtype)
+    if x.dtype.kind == "u":
+        f = x.astype(np.float64) / float(info.max)
+    else:
+        f = (x.astype(np.float64) * 2.0 + 1.0) / (float(info.max) - float(info.min))
+    sigma_color = sigma_color or f.std()
+    if win_size is None:
+        win_size = max(5, 2 * int(math.ceil(3 * sigma_spatial)) + 1)
+    mn, mx = f.min(), f.max()
+    out = np.empty(x.shape, np.float64)
+    if mn == mx:
+        out[...] = mn
+        return out
+    max_value = mx - mn if mn < 0 else mx
+    color, spatial = sk_bilateral_luts(bins, sigma_color, max_value, win_size, sigma_spatial)
+    _check(lib().orc_sk_bilateral(_ptr(x), _DT[x.dtype], x.shape[0], x.shape[1], int(win_size), int(bins), SK_MODES[mode],
+                                  float(cval), _ptr(color), _ptr(spatial), _ptr(out)))
+    return out
