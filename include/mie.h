@@ -38,7 +38,10 @@ extern "C" {
 
 #define MIE_ABI_VERSION 1
 
-enum mie_dtype { MIE_U8 = 0, MIE_U16 = 1, MIE_I16 = 2, MIE_F32 = 3 };
+enum mie_dtype {
+    MIE_U8 = 0, MIE_U16 = 1, MIE_I16 = 2, MIE_F32 = 3,
+    MIE_F64 = 4   /* OUTPUT dtype of the scikit-image entry points only (skimage returns float64 for integer images) */
+};
 
 /* kornia border_type names: 'constant' (zeros), 'reflect' (mirror, edge not
  * repeated = scipy.ndimage 'mirror'), 'replicate' (= scipy 'nearest'), 'circular' (= scipy 'wrap').
@@ -258,6 +261,42 @@ int mie_ssim_sums(const void* a, const void* b, int dtype, int64_t n, int h, int
                   int64_t a_stride_n, int64_t a_stride_h, int64_t b_stride_n, int64_t b_stride_h,
                   int ws, double c1, double c2,
                   double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ scikit-image exposure / restoration (F3)
+ * skimage.exposure.equalize_adapthist(image, kernel_size, clip_limit, nbins), skimage.exposure.equalize_hist(image)
+ * and skimage.restoration.denoise_bilateral(image, win_size, sigma_color, sigma_spatial, bins, mode, cval)
+ * (reference pyproject.toml:12) — different algorithms from their kornia counterparts
+ * above.  RECALLED semantics: the kernels follow oracle/mie_oracle.c:orc_sk_* bit for bit.  Every plane of the batch
+ * is one image (skimage on a 2-D array).  dst_dtype: MIE_F64 (skimage's dtype for integer images) or MIE_F32 (the
+ * float64 result rounded once).  Outputs are floats in [0, 1] (bilateral: on the img_as_float scale).
+ *
+ * mie_sk_equalize_adapthist: src u8 / u16 / i16 / f32; (kr, kc) = kernel_size in pixels (skimage default: max(dim/8, 1));
+ *   nbins <= 4096.  Four launches: per-image min/max, one block per contextual region (histogram on 2^14 grey levels,
+ *   iterative clip redistribution, mapping), interpolation (+ min/max of the result), final min-max rescale.
+ * mie_sk_equalize_hist: src u8 / u16 / i16 (one bin per integer value between the image's min and max).
+ * mie_sk_denoise_bilateral: src u8 / u16 / i16; win_size odd; mode 0 constant(cval) 1 edge 2 symmetric 3 reflect 4 wrap;
+ *   color_luts: DEVICE float64 [n][bins] and range_lut: DEVICE float64 [win_size^2], built by the caller exactly as
+ *   upstream builds them in Python; ranges: DEVICE int [n][2] = per-image (min, max) code.                              */
+size_t mie_sk_adapthist_workspace_bytes(int64_t n, int h, int w, int kr, int kc, int nbins);
+int mie_sk_equalize_adapthist(const void* src, void* dst, int src_dtype, int dst_dtype,
+                              int64_t n, int h, int w,
+                              int64_t src_stride_n, int64_t src_stride_h,
+                              int64_t dst_stride_n, int64_t dst_stride_h,
+                              int kr, int kc, double clip_limit, int nbins,
+                              void* workspace, size_t workspace_bytes, void* stream);
+size_t mie_sk_equalize_hist_workspace_bytes(int64_t n, int src_dtype);
+int mie_sk_equalize_hist(const void* src, void* dst, int src_dtype, int dst_dtype,
+                         int64_t n, int h, int w,
+                         int64_t src_stride_n, int64_t src_stride_h,
+                         int64_t dst_stride_n, int64_t dst_stride_h,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int mie_sk_denoise_bilateral(const void* src, void* dst, int src_dtype, int dst_dtype,
+                             int64_t n, int h, int w,
+                             int64_t src_stride_n, int64_t src_stride_h,
+                             int64_t dst_stride_n, int64_t dst_stride_h,
+                             int win_size, int bins, int mode, double cval,
+                             const double* color_luts, const double* range_lut, const int* ranges,
+                             void* stream);
 
 /* ------------------------------------------------------------------ z-halo exchange (BASELINE.json config 3)
  * The one exchange step of the path: a volume sharded into z-slabs, one per rank, needs the

@@ -14,7 +14,7 @@ import torch
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libmie_b200.so")
 
-MIE_U8, MIE_U16, MIE_I16, MIE_F32 = 0, 1, 2, 3
+MIE_U8, MIE_U16, MIE_I16, MIE_F32, MIE_F64 = 0, 1, 2, 3, 4
 BORDER = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3, "symmetric": 4}
 CLAHE_KORNIA, CLAHE_OPENCV = 0, 1
 
@@ -53,6 +53,11 @@ SIGNATURES = {
     "mie_metric_workspace_bytes": ([_i64, _i, _i, _i], _sz),
     "mie_sqdiff_sums": ([_p, _p, _i, *_planes, _p, _p, _sz, _p], _i),
     "mie_ssim_sums": ([_p, _p, _i, *_planes, _i, _d, _d, _p, _p, _sz, _p], _i),
+    "mie_sk_adapthist_workspace_bytes": ([_i64, _i, _i, _i, _i, _i], _sz),
+    "mie_sk_equalize_adapthist": ([_p, _p, _i, _i, *_planes, _i, _i, _d, _i, _p, _sz, _p], _i),
+    "mie_sk_equalize_hist_workspace_bytes": ([_i64, _i], _sz),
+    "mie_sk_equalize_hist": ([_p, _p, _i, _i, *_planes, _p, _sz, _p], _i),
+    "mie_sk_denoise_bilateral": ([_p, _p, _i, _i, *_planes, _i, _i, _i, _d, _p, _p, _p, _p], _i),
     "mie_halo_exchange_available": ([], _i),
     "mie_halo_exchange_z": ([_p, _i, _i, _p, _p, _p, _p, _sz, _p], _i),
     "mie_chain_workspace_bytes": ([_i64, _i, _i, _i, _i], _sz),
