@@ -6,10 +6,13 @@ this image, so this module restates its enhancement functions with the same
 clamp/redistribute -> cumsum -> gather -> addcmul lerps; pad -> conv2d; unfold ->
 median), written from the published algorithm.  It is
 structurally independent of the per-pixel restatement in mie_oracle.c, which is
-the point: tests/test_oracle_twin.py checks that the two agree (LUTs bit-exact,
-float outputs to ~1e-6), which pins the tile/half-tile/weight bookkeeping of the
-oracle.  It is also the "kornia-style torch-CPU pipeline" BASELINE.md §4 names as
-the primary CPU stand-in and is timed by bench.py as a secondary CPU figure.
+the point: tests/test_oracle.py (test_kornia_clahe_oracle_matches_tensor_level_twin and
+its neighbours) checks that the two agree (LUTs bit-exact, float outputs to ~1e-6),
+which pins the tile/half-tile/weight bookkeeping of the oracle.  It is also the
+"kornia-style torch-CPU pipeline" SURVEY.md §8(d) names as the PRIMARY CPU figure:
+bench.py times it as `cpu_baseline` and as the `--impl reference` arm
+(bench.py:_twin_chain).  tests/test_live_pins.py compares it with the real kornia
+whenever that package is importable.
 """
 from __future__ import annotations
 
