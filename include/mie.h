@@ -262,6 +262,24 @@ int mie_ssim_sums(const void* a, const void* b, int dtype, int64_t n, int h, int
                   int ws, double c1, double c2,
                   double* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ fused bilateral -> CLAHE (BASELINE.json config 4)
+ * equalize_clahe(bilateral_blur(x01, (k, k), sigma_color, sigma_space, border), clip_limit, (gh, gw)), quantised once at
+ * the end — the same bits as mie_bilateral (F32 out) -> mie_clahe, without the fp32 image in between: stage 1 writes the
+ * CLAHE lookup index of every filtered pixel (1 byte) and accumulates the tile histograms, stage 2 turns histograms into
+ * LUTs, stage 4 blends and quantises.  `stages` is a mask of 1 | 2 | 4 (7 = everything; single stages for timing).
+ * Covered geometry (mie_bilateral_clahe_is_fused() == 1): k in {3,5,7,9}, CLAHE tiles that are multiples of 32 pixels and
+ * need no padding, w % 4 == 0, w <= 4096, gw <= 32, integer pixels in their dtype's default range or float pixels;
+ * anything else returns MIE_E_UNSUPPORTED (call mie_bilateral and mie_clahe).  wspace: k*k spatial weights (HOST).   */
+size_t mie_bilateral_clahe_workspace_bytes(int64_t n, int h, int w, int gh, int gw);
+int mie_bilateral_clahe_is_fused(int h, int w, int gh, int gw, int k, int dtype);
+int mie_bilateral_clahe(const void* src, void* dst, int src_dtype, int dst_dtype,
+                        int64_t n, int h, int w,
+                        int64_t src_stride_n, int64_t src_stride_h,
+                        int64_t dst_stride_n, int64_t dst_stride_h,
+                        const float* wspace, int k, float sigma_color, int border,
+                        int gh, int gw, double clip_limit, float lo, float hi, int stages,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------ scikit-image exposure / restoration (F3)
  * skimage.exposure.equalize_adapthist(image, kernel_size, clip_limit, nbins), skimage.exposure.equalize_hist(image)
  * and skimage.restoration.denoise_bilateral(image, win_size, sigma_color, sigma_spatial, bins, mode, cval)

@@ -53,6 +53,9 @@ SIGNATURES = {
     "mie_metric_workspace_bytes": ([_i64, _i, _i, _i], _sz),
     "mie_sqdiff_sums": ([_p, _p, _i, *_planes, _p, _p, _sz, _p], _i),
     "mie_ssim_sums": ([_p, _p, _i, *_planes, _i, _d, _d, _p, _p, _sz, _p], _i),
+    "mie_bilateral_clahe_workspace_bytes": ([_i64, _i, _i, _i, _i], _sz),
+    "mie_bilateral_clahe_is_fused": ([_i] * 6, _i),
+    "mie_bilateral_clahe": ([_p, _p, _i, _i, *_planes, _p, _i, _f, _i, _i, _i, _d, _f, _f, _i, _p, _sz, _p], _i),
     "mie_sk_adapthist_workspace_bytes": ([_i64, _i, _i, _i, _i, _i], _sz),
     "mie_sk_equalize_adapthist": ([_p, _p, _i, _i, *_planes, _i, _i, _d, _i, _p, _sz, _p], _i),
     "mie_sk_equalize_hist_workspace_bytes": ([_i64, _i], _sz),

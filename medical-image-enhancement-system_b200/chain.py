@@ -16,7 +16,8 @@ from ._ffi import DTYPE_CODE, as_planes, check, lib, require_cuda, stream_ptr, v
 from .enhance import _check_clahe_args
 from .filters import _border, _check_kernel, _pair_float, _pair_int, get_gaussian_kernel1d
 
-__all__ = ["ChainConfig", "ChainPlan", "ChainRing", "enhance_chain", "chain_workspace_bytes"]
+__all__ = ["ChainConfig", "ChainPlan", "ChainRing", "enhance_chain", "chain_workspace_bytes", "bilateral_clahe",
+           "BilateralClahePlan", "bilateral_clahe_workspace_bytes"]
 
 
 @dataclass(frozen=True)
@@ -177,3 +178,85 @@ class ChainRing:
         cur = torch.cuda.current_stream(self.device)
         for s in self.streams:
             cur.wait_stream(s)
+
+
+# ---------------------------------------------------------------------------------------------- bilateral -> CLAHE
+def bilateral_clahe_workspace_bytes(n: int, h: int, w: int, grid_size=(16, 16)) -> int:
+    return int(lib().mie_bilateral_clahe_workspace_bytes(n, h, w, int(grid_size[0]), int(grid_size[1])))
+
+
+def bilateral_clahe(input: torch.Tensor, kernel_size=9, sigma_color=0.1, sigma_space=(1.5, 1.5), clip_limit: float = 2.0,
+                    grid_size: tuple = (16, 16), border_type: str = "reflect", *, value_range=None, out: torch.Tensor = None,
+                    out_dtype=None, workspace: torch.Tensor = None, stages: int = 7) -> torch.Tensor:
+    """BASELINE.json config 4 as one fused path: equalize_clahe(bilateral_blur(x, kernel_size, sigma_color, sigma_space,
+    border_type), clip_limit, grid_size), quantised once at the end to the input's dtype (or float32).
+
+    Bit-identical to `equalize_clahe(bilateral_blur(x, ..., out_dtype=torch.float32), ...)` followed by the integer
+    quantisation, but the filtered image never exists: the bilateral kernel emits the CLAHE lookup index of each pixel
+    (1 byte) and the tile histograms, and the interpolation pass reads that byte.  Geometry outside the fused kernels'
+    reach (see mie_bilateral_clahe in include/mie.h) raises NotImplementedError — call the two operators instead."""
+    _check_clahe_args(clip_limit, grid_size)
+    require_cuda(input)
+    k, kx = _pair_int(kernel_size, "kernel_size")
+    if k != kx:
+        raise NotImplementedError("the fused path needs a square bilateral window")
+    _check_kernel(k, kx)
+    sy, sx = _pair_float(sigma_space, "sigma_space")
+    x, n, h, w = as_planes(input)
+    lo, hi = value_range_of(x, value_range)
+    if out is None:
+        dt = x.dtype if out_dtype is None else out_dtype
+        if dt != x.dtype and dt != torch.float32:
+            raise TypeError("out_dtype must be the input dtype or torch.float32")
+        out = torch.empty(x.shape, dtype=dt, device=x.device)
+    elif out.shape != x.shape or not out.is_contiguous() or out.device != x.device or \
+            (out.dtype != x.dtype and out.dtype != torch.float32):
+        raise ValueError("out must be a contiguous tensor of the input's shape on its device (same dtype or float32)")
+    gh, gw = int(grid_size[0]), int(grid_size[1])
+    L = lib()
+    need = L.mie_bilateral_clahe_workspace_bytes(n, h, w, gh, gw)
+    if workspace is None:
+        workspace = torch.empty(max(need, 1), dtype=torch.uint8, device=x.device)
+    elif workspace.dtype != torch.uint8 or workspace.numel() < need or workspace.device != x.device or \
+            workspace.data_ptr() % 256:
+        raise ValueError(f"workspace must be a 256-byte aligned uint8 tensor of >= {need} bytes on the input's device")
+    import numpy as np
+
+    wsp = np.ascontiguousarray(
+        (get_gaussian_kernel1d(k, sy)[:, None] * get_gaussian_kernel1d(k, sx)[None, :]).astype(np.float32))
+    with torch.cuda.device(x.device):
+        check(L.mie_bilateral_clahe(x.data_ptr(), out.data_ptr(), DTYPE_CODE[x.dtype], DTYPE_CODE[out.dtype], n, h, w,
+                                    h * w, w, h * w, w, wsp.ctypes.data, k, float(sigma_color), _border(border_type), gh, gw,
+                                    float(clip_limit), lo, hi, int(stages), workspace.data_ptr(), workspace.numel(),
+                                    stream_ptr(x.device)))
+    return out
+
+
+class BilateralClahePlan:
+    """bilateral_clahe on fixed device buffers (input, output, workspace allocated once): `run()` enqueues one pass;
+    `stage_ms()` times the three stages separately with CUDA events."""
+
+    def __init__(self, input: torch.Tensor, *, out: torch.Tensor = None, **kwargs):
+        require_cuda(input)
+        self.input, self.kwargs = input, kwargs
+        x, n, h, w = as_planes(input)
+        self.out = out if out is not None else torch.empty_like(input)
+        grid = kwargs.get("grid_size", (16, 16))
+        self.workspace = torch.empty(max(bilateral_clahe_workspace_bytes(n, h, w, grid), 1), dtype=torch.uint8,
+                                     device=input.device)
+
+    def run(self, stages: int = 7) -> torch.Tensor:
+        return bilateral_clahe(self.input, out=self.out, workspace=self.workspace, stages=stages, **self.kwargs)
+
+    def stage_ms(self) -> dict:
+        res = {}
+        for name, mask in (("bilateral_index_hist", 1), ("hist_to_lut", 2), ("pack_cells+apply_index", 4)):
+            self.run(mask)
+            torch.cuda.synchronize(self.input.device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.run(mask)
+            e1.record()
+            torch.cuda.synchronize(self.input.device)
+            res[name] = round(e0.elapsed_time(e1), 4)
+        return res

@@ -10,6 +10,7 @@
 // (81 taps x 14 FMA-pipe operations), not HBM bound.
 
 #include "chain_fast.cuh"
+#include "window.cuh"
 
 #define MIE_HAVE_BILATERAL 1
 
@@ -148,17 +149,14 @@ struct SpaceW2 {   // spatial weights, row-major K x K
     float w[81];
 };
 
-template <typename SrcT, typename DstT, int K>
-__global__ void __launch_bounds__(256)
-bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
-                        int64_t dsh, int h, int w, int tiles_x, int tiles_y, float coef, int border, float lo,
-                        float rg, SpaceW2 sw) {
+// Stages the haloed tile and evaluates the window for the thread's four pixels (rows ly0 + 8 k, column lx):
+// num[k] / den[k] is the filter output.  Shared by the pixel-output kernel and the index-plane kernel of the fused
+// bilateral -> CLAHE chain.
+template <typename SrcT, int K>
+__device__ __forceinline__ void bilateral_packed_core(const SrcT* __restrict__ plane, int64_t ssh, int h, int w, int tx0,
+                                                      int ty0, float coef, int border, float lo, float rg,
+                                                      const SpaceW2& sw, float* smem, float* num, float* den) {
     constexpr int T = 32, R = K / 2, EW = T + 2 * R, EH = T + 2 * R, PITCH = EW | 1;
-    __shared__ float smem[EH * PITCH];
-    const int64_t tile = blockIdx.x;
-    const int tx0 = (int)(tile % tiles_x) * T, ty0 = (int)((tile / tiles_x) % tiles_y) * T;
-    const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
-    const SrcT* plane = src + n * ssn;
     for (int i = threadIdx.x; i < EH * EW; i += 256) {
         const int r = i / EW, c = i - r * EW;
         const int sy = border_index(ty0 - R + r, h, border), sx = border_index(tx0 - R + c, w, border);
@@ -188,9 +186,23 @@ bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, in
             numB = f2_fma(wB, vB, numB); denB = f2_add(denB, wB);
         }
     }
-    float num[4], den[4];
     f2_unpack(numA, num[0], num[1]); f2_unpack(numB, num[2], num[3]);
     f2_unpack(denA, den[0], den[1]); f2_unpack(denB, den[2], den[3]);
+}
+
+template <typename SrcT, typename DstT, int K>
+__global__ void __launch_bounds__(256)
+bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                        int64_t dsh, int h, int w, int tiles_x, int tiles_y, float coef, int border, float lo,
+                        float rg, SpaceW2 sw) {
+    constexpr int T = 32, R = K / 2, EW = T + 2 * R, EH = T + 2 * R, PITCH = EW | 1;
+    __shared__ float smem[EH * PITCH];
+    const int64_t tile = blockIdx.x;
+    const int tx0 = (int)(tile % tiles_x) * T, ty0 = (int)((tile / tiles_x) % tiles_y) * T;
+    const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
+    float num[4], den[4];
+    bilateral_packed_core<SrcT, K>(src + n * ssn, ssh, h, w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
+    const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
     const int x = tx0 + lx;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -198,6 +210,53 @@ bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, in
         if (y < h && x < w)
             dst[n * dsn + (int64_t)y * dsh + x] = Px<DstT>::from01(__fdiv_rn(num[k], den[k]), lo, rg);
     }
+}
+
+// Stage A of the fused bilateral -> CLAHE chain (BASELINE.json config 4): the filtered value b never leaves the SM — only
+// its CLAHE lookup index trunc(clamp(b * 255)) (one byte per pixel) is written, while its histogram bin floor(b * 256)
+// goes into a block histogram that is flushed with one global atomic per occupied bin.  Requires 32-pixel-aligned CLAHE
+// tiles without padding (checked on the host), so that a block's 32 x 32 pixels lie in ONE tile.
+template <typename SrcT, int K>
+__global__ void __launch_bounds__(256)
+bilateral_index_kernel(const SrcT* __restrict__ src, uint8_t* __restrict__ idx, uint32_t* __restrict__ hist, int64_t ssn,
+                       int64_t ssh, ClaheGeom g, int tiles_x, int tiles_y, float coef, int border, float lo, float rg,
+                       SpaceW2 sw) {
+    constexpr int T = 32, R = K / 2, EW = T + 2 * R, EH = T + 2 * R, PITCH = EW | 1;
+    __shared__ float smem[EH * PITCH];
+    __shared__ int s_hist[kBins + 8];
+    for (int i = threadIdx.x; i < kBins + 8; i += 256) s_hist[i] = 0;
+    const int64_t tile = blockIdx.x;
+    const int tx0 = (int)(tile % tiles_x) * T, ty0 = (int)((tile / tiles_x) % tiles_y) * T;
+    const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
+    float num[4], den[4];
+    bilateral_packed_core<SrcT, K>(src + n * ssn, ssh, g.h, g.w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
+    const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
+    uint8_t* ip = idx + n * (int64_t)g.h * g.w + (int64_t)(ty0 + ly0) * g.w + tx0 + lx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float b = __fdiv_rn(num[k], den[k]);
+        ip[(int64_t)8 * k * g.w] = (uint8_t)(fast_idx_bits<false>(b) & 0xFFu);
+        hist_add_nobranch(s_hist, fast_bin<false>(b));    // slot 256 swallows what torch.histc would ignore
+    }
+    __syncthreads();
+    uint32_t* gh_ = hist + ((n * g.gh + ty0 / g.th) * (int64_t)g.gw + tx0 / g.tw) * kBins;
+    const int v = s_hist[threadIdx.x];
+    if (v) atomicAdd(gh_ + threadIdx.x, (uint32_t)v);
+}
+
+// Tile histograms (global, uint32) -> LUT bytes: one warp per tile, the clip / redistribute / scan of chain_fast.cuh.
+__global__ void __launch_bounds__(256)
+hist_to_lut_kernel(const uint32_t* __restrict__ hist, uint8_t* __restrict__ luts, LutParams lp, int64_t tiles) {
+    __shared__ __align__(16) int s_tot[8][kBins + 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t t = (int64_t)blockIdx.x * 8 + warp;
+    if (t >= tiles) return;
+    const uint4* src = reinterpret_cast<const uint4*>(hist + t * kBins);
+    const uint4 a = __ldg(src + 2 * lane), b = __ldg(src + 2 * lane + 1);
+    *reinterpret_cast<uint4*>(&s_tot[warp][8 * lane]) = a;
+    *reinterpret_cast<uint4*>(&s_tot[warp][8 * lane + 4]) = b;
+    __syncwarp();
+    warp_build_lut<false>(s_tot[warp], lp, luts + t * kBins, lane);
 }
 
 template <typename SrcT, typename DstT>
@@ -254,14 +313,108 @@ int bilateral_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h,
     return check_launch();
 }
 
+int launch_clahe_apply_index(const uint8_t* idx, void* dst, int dd, int64_t n, int64_t dsn, int64_t dsh, const ClaheGeom& g,
+                             const uint8_t* luts, void* cells, cudaStream_t st);   // clahe_fast.cu
+size_t clahe_cells_bytes(int64_t n, int gh, int gw);
+
+static inline size_t bc_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static bool bilateral_clahe_fused_ok(const ClaheGeom& g, int k, int sd, float lo, float hi) {
+    if (k != 3 && k != 5 && k != 7 && k != 9) return false;
+    if (g.hp != g.h || g.wp != g.w) return false;
+    if ((g.th % 32) || (g.tw % 32)) return false;
+    if ((g.w & 3) || g.w > 4096 || g.gw > 32) return false;    // interpolation kernel: one block spans a row
+    if (!default_range_c(sd, lo, hi)) return false;
+    if ((int64_t)g.th * g.tw >= (1 << 24)) return false;
+    return true;
+}
+
 }  // namespace mie
 
 using namespace mie;
 
-extern "C" int mie_bilateral(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t n, int h, int w,
+extern "C" {
+
+size_t mie_bilateral_clahe_workspace_bytes(int64_t n, int h, int w, int gh, int gw) {
+    if (n <= 0 || h <= 0 || w <= 0 || gh <= 0 || gw <= 0) return 0;
+    const size_t tiles = (size_t)n * gh * gw;
+    return bc_align(tiles * kBins * sizeof(uint32_t)) + bc_align(tiles * kBins) + bc_align((size_t)n * h * w) +
+           bc_align(clahe_cells_bytes(n, gh, gw));
+}
+
+int mie_bilateral_clahe_is_fused(int h, int w, int gh, int gw, int k, int dtype) {
+    ClaheGeom g;
+    if (make_clahe_geom(h, w, gh, gw, MIE_CLAHE_KORNIA, &g)) return 0;
+    float lo = 0.f, hi = 1.f;
+    if (dtype == MIE_U8) hi = 255.f; else if (dtype == MIE_U16) hi = 65535.f; else if (dtype == MIE_I16) { lo = -32768.f; hi = 32767.f; }
+    return bilateral_clahe_fused_ok(g, k, dtype, lo, hi) ? 1 : 0;
+}
+
+int mie_bilateral_clahe(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t n, int h, int w,
+                        int64_t src_stride_n, int64_t src_stride_h, int64_t dst_stride_n, int64_t dst_stride_h,
+                        const float* wspace, int k, float sigma_color, int border, int gh, int gw, double clip_limit,
+                        float lo, float hi, int stages, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = check_planes(src, dst, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h);
+    if (rc) return rc;
+    rc = check_dtypes(src_dtype, dst_dtype, lo, hi);
+    if (rc) return rc;
+    if (!wspace) return MIE_E_NULL;
+    if (k <= 0 || !(k & 1) || k > 9) return MIE_E_KERNEL;
+    if (border < MIE_BORDER_CONSTANT || border > MIE_BORDER_CIRCULAR) return MIE_E_BORDER;
+    if (border == MIE_BORDER_REFLECT && (k / 2 >= w || k / 2 >= h)) return MIE_E_BORDER;
+    if (!(sigma_color > 0.0f)) return MIE_E_RANGE;
+    if (stages < 1 || stages > 7) return MIE_E_UNSUPPORTED;
+    ClaheGeom g;
+    rc = make_clahe_geom(h, w, gh, gw, MIE_CLAHE_KORNIA, &g);
+    if (rc) return rc;
+    if (!bilateral_clahe_fused_ok(g, k, src_dtype, lo, hi)) return MIE_E_UNSUPPORTED;
+    if (n == 0) return MIE_OK;
+    if (!workspace) return MIE_E_NULL;
+    if ((uintptr_t)workspace % 256) return MIE_E_ALIGN;
+    if (workspace_bytes < mie_bilateral_clahe_workspace_bytes(n, h, w, gh, gw)) return MIE_E_WORKSPACE;
+    const int64_t tiles = n * gh * gw;
+    const int tiles_x = w / 32, tiles_y = h / 32;
+    const int64_t blocks = n * tiles_x * tiles_y;
+    if (blocks > 2147483647LL || tiles > 2147483647LL) return MIE_E_SHAPE;
+    uint8_t* ws = (uint8_t*)workspace;
+    uint32_t* hist = (uint32_t*)ws;
+    uint8_t* luts = ws + bc_align((size_t)tiles * kBins * sizeof(uint32_t));
+    uint8_t* idx = luts + bc_align((size_t)tiles * kBins);
+    void* cells = idx + bc_align((size_t)n * h * w);
+    if (stages & 1) {   // bilateral -> index plane + tile histograms
+        cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)tiles * kBins * sizeof(uint32_t), st);
+        if (e != cudaSuccess) return (int)e;
+        SpaceW2 sw;
+        for (int i = 0; i < 81; ++i) sw.w[i] = i < k * k ? wspace[i] : 0.f;
+        const float coef = (float)(-0.5 * 1.4426950408889634 / ((double)sigma_color * (double)sigma_color));
+        const float rg = hi - lo;
+#define MIE_BIDX(K_)                                                                                                      case K_:                                                                                                                  MIE_DISPATCH_SRC(src_dtype, (bilateral_index_kernel<SrcT, K_><<<(unsigned)blocks, 256, 0, st>>>(                                                      (const SrcT*)src, idx, hist, src_stride_n, src_stride_h, g, tiles_x, tiles_y,                                         coef, border, lo, rg, sw)));                                                          break;
+        switch (k) {
+            MIE_BIDX(3) MIE_BIDX(5) MIE_BIDX(7) MIE_BIDX(9)
+            default: return MIE_E_KERNEL;
+        }
+#undef MIE_BIDX
+        rc = check_launch();
+        if (rc) return rc;
+    }
+    if (stages & 2) {   // histograms -> LUTs
+        const LutParams lp = make_lut_params(g, clip_limit, MIE_CLAHE_KORNIA);
+        hist_to_lut_kernel<<<(unsigned)((tiles + 7) / 8), 256, 0, st>>>(hist, luts, lp, tiles);
+        rc = check_launch();
+        if (rc) return rc;
+    }
+    if (stages & 4)     // index plane -> CLAHE blend -> quantise
+        return launch_clahe_apply_index(idx, dst, dst_dtype, n, dst_stride_n, dst_stride_h, g, luts, cells, st);
+    return MIE_OK;
+}
+
+int mie_bilateral(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t n, int h, int w,
                              int64_t src_stride_n, int64_t src_stride_h, int64_t dst_stride_n, int64_t dst_stride_h,
                              const float* wspace, int ky, int kx, float sigma_color, int border, float lo, float hi,
                              void* stream) {
     return bilateral_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n,
                           dst_stride_h, wspace, ky, kx, sigma_color, border, lo, hi, (cudaStream_t)stream);
 }
+
+}  // extern "C"

@@ -298,4 +298,36 @@ int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t 
     return check_launch();
 }
 
+// Interpolation pass of the fused bilateral -> CLAHE chain: the source is the 1-byte lookup-index plane (the index IS
+// the byte: Codes<uint8_t>), the destination any pixel dtype in its default range.
+int launch_clahe_apply_index(const uint8_t* idx, void* dst, int dd, int64_t n, int64_t dsn, int64_t dsh, const ClaheGeom& g,
+                             const uint8_t* luts, void* cells, cudaStream_t st) {
+    if (n == 0) return MIE_OK;
+    int rc = launch_pack_cells(luts, cells, n, g.gh, g.gw, st);
+    if (rc) return rc;
+    ApplyFastArgs a;
+    a.luts = nullptr;
+    a.src = idx; a.dst = dst; a.ssn = (int64_t)g.h * g.w; a.ssh = g.w; a.dsn = dsn; a.dsh = dsh; a.g = g;
+    int rows = g.th / 2;
+    for (int d = 32; d >= 1; --d)
+        if ((g.th / 2) % d == 0) { rows = d; break; }
+    a.rows_per_block = rows;
+    a.blocks_per_image = g.h / rows;
+    const int64_t blocks = n * a.blocks_per_image;
+    if (blocks > 2147483647LL) return MIE_E_SHAPE;
+    const size_t smem = (size_t)(g.gw + 1) * kBins * 8;
+    const WinCvt cv = {};
+#define MIE_APPLY_IDX(D_)                                                                                  \
+    MIE_ENSURE_SMEM((clahe_apply_fast_kernel<uint8_t, D_, false, true>), 80 * 1024);                       \
+    clahe_apply_fast_kernel<uint8_t, D_, false, true><<<(unsigned)blocks, g.w / 4, smem, st>>>(a, (const uint2*)cells, cv)
+    switch (dd) {
+        case MIE_U8: MIE_APPLY_IDX(uint8_t); break;
+        case MIE_U16: MIE_APPLY_IDX(uint16_t); break;
+        case MIE_I16: MIE_APPLY_IDX(int16_t); break;
+        default: MIE_APPLY_IDX(float); break;
+    }
+#undef MIE_APPLY_IDX
+    return check_launch();
+}
+
 }  // namespace mie
