@@ -62,6 +62,10 @@ def main():
         out[name + "_ms_min"] = round(ts[0], 4)
     plan.run(3)
     torch.cuda.synchronize()
+    # bit-exactness against the independent tile kernels (MIE_CHAIN_PREFER_TILES) on the same input
+    y_tiles = M.enhance_chain(x, cfg, stages=3 | 8)
+    out["equals_tile_kernels"] = bool(torch.equal(y.view(torch.int16), y_tiles.view(torch.int16)))
+    out["differing_pixels"] = int((y.view(torch.int16) != y_tiles.view(torch.int16)).sum().item())
     out["checksum"] = int(y.view(torch.int16).to(torch.int64).sum().item() & 0xFFFFFFFF)
     px = x.numel()
     out["mpixel_s"] = round(px / out["all_ms_median"] / 1e3, 1)

@@ -93,17 +93,6 @@ bilateral_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t s
 // instruction per pair — same per-lane IEEE rounding, so the result is bit-identical — and the window
 // loops are unrolled at compile time.  Per pixel-tap: 6.5 packed + 1 scalar FMA-pipe instructions, 1 LDS,
 // 1 FMNMX, 1 exponent-field add: ~10.5 issue slots instead of 27; the FMA pipe becomes the limiter.
-__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 f2_dup(float v) { return f2_pack(v, v); }
 
 struct ExpConsts {
     f32x2 magic, c5, c4, c3, c2, c1, one;

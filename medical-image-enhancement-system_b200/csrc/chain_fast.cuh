@@ -74,6 +74,42 @@ __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint3
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
+// Packed f32x2 values held as ONE 64-bit register pair.  The CUDA float2 intrinsics re-pack their
+// operands at every call; when the two halves come from different producers (the marching kernels'
+// register ring) ptxas then copies them into an aligned pair at every use.  Packing once and keeping
+// the 64-bit value costs the two copies once.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_dup(float v) { return f2_pack(v, v); }
+
 // ---------------------------------------------------------------- exact default-range pixel mapping
 template <typename T>
 struct Fast;
@@ -108,11 +144,34 @@ struct Fast<uint16_t> {
         const float c = __saturatef(y);   // == fminf(fmaxf(y, 0), 1) incl. NaN -> 0; folds into the producer as .SAT
         return __float_as_uint(__fadd_rn(__fmul_rn(c, 65535.0f), 8388608.0f));
     }
+    // The same for two values at once.  The product is rounded BEFORE the magic add, as in quant(): written as
+    // mul.rn.f32x2 followed by fma.rn.f32x2 (m * 1 + 2^23), which ptxas keeps as FMUL2 + FFMA2 — a mul + add pair it
+    // would contract into one FFMA2 with a single rounding.
+    static __device__ __forceinline__ f32x2 quant2(float y0, float y1) {
+        const f32x2 m = f2_mul(f2_pack(__saturatef(y0), __saturatef(y1)), f2_pack(65535.0f, 65535.0f));
+        return f2_fma(m, f2_pack(1.0f, 1.0f), f2_pack(8388608.0f, 8388608.0f));
+    }
+    static __device__ __forceinline__ uint32_t quant2_u16x2(float y0, float y1) {
+        float a, b;
+        f2_unpack(quant2(y0, y1), a, b);
+        return __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x5410);
+    }
     static __device__ __forceinline__ void store4(uint16_t* p, const float* y) {
         uint2 o;
-        o.x = __byte_perm(quant(y[0]), quant(y[1]), 0x5410);
-        o.y = __byte_perm(quant(y[2]), quant(y[3]), 0x5410);
+        o.x = quant2_u16x2(y[0], y[1]);
+        o.y = quant2_u16x2(y[2], y[3]);
         *reinterpret_cast<uint2*>(p) = o;
+    }
+    // rows s and s + 1 of the thread's four columns (raw words a, b) -> packed (row s, row s + 1) pairs
+    static __device__ __forceinline__ f32x2 from_bits2(uint32_t m0, uint32_t m1) {
+        const f32x2 t = f2_sub(f2_pack(__uint_as_float(m0), __uint_as_float(m1)), f2_pack(128.0f, 128.0f));
+        return f2_fma(t, f2_pack(kC, kC), t);
+    }
+    static __device__ __forceinline__ void cvt_pair4(raw4 a, raw4 b, f32x2* xp) {
+        xp[0] = from_bits2(__byte_perm(a.x, 0x43000000u, 0x7610), __byte_perm(b.x, 0x43000000u, 0x7610));
+        xp[1] = from_bits2(__byte_perm(a.x, 0x43000000u, 0x7632), __byte_perm(b.x, 0x43000000u, 0x7632));
+        xp[2] = from_bits2(__byte_perm(a.y, 0x43000000u, 0x7610), __byte_perm(b.y, 0x43000000u, 0x7610));
+        xp[3] = from_bits2(__byte_perm(a.y, 0x43000000u, 0x7632), __byte_perm(b.y, 0x43000000u, 0x7632));
     }
 };
 
@@ -138,9 +197,13 @@ struct Fast<int16_t> {
     }
     static __device__ __forceinline__ void store4(int16_t* p, const float* y) {
         uint2 o;
-        o.x = __byte_perm(Fast<uint16_t>::quant(y[0]), Fast<uint16_t>::quant(y[1]), 0x5410) ^ 0x80008000u;
-        o.y = __byte_perm(Fast<uint16_t>::quant(y[2]), Fast<uint16_t>::quant(y[3]), 0x5410) ^ 0x80008000u;
+        o.x = Fast<uint16_t>::quant2_u16x2(y[0], y[1]) ^ 0x80008000u;
+        o.y = Fast<uint16_t>::quant2_u16x2(y[2], y[3]) ^ 0x80008000u;
         *reinterpret_cast<uint2*>(p) = o;
+    }
+    static __device__ __forceinline__ void cvt_pair4(raw4 a, raw4 b, f32x2* xp) {
+        a.x ^= 0x80008000u; a.y ^= 0x80008000u; b.x ^= 0x80008000u; b.y ^= 0x80008000u;   // v + 32768
+        Fast<uint16_t>::cvt_pair4(a, b, xp);
     }
 };
 
@@ -235,35 +298,21 @@ __device__ __forceinline__ void col4_f32x2(const float4* win, int j, const Taps&
     g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
 }
 
-// Packed f32x2 values held as ONE 64-bit register pair.  The CUDA float2 intrinsics re-pack their
-// operands at every call; when the two halves come from different producers (the marching kernels'
-// register ring) ptxas then copies them into an aligned pair at every use.  Packing once and keeping
-// the 64-bit value costs the two copies once.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
-    f32x2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-
 // x / 255, correctly rounded (Markstein: y = RN(1/b), q0 = RN(a*y), r = a - b*q0 exact, RN(q0 + r*y)).
 __device__ __forceinline__ float div255(float x) {
     constexpr float r = 0.003921568859368563f;
     const float q0 = __fmul_rn(x, r);
     return __fmaf_rn(__fmaf_rn(-255.0f, q0, x), r, q0);
+}
+
+// x / 255 on a packed pair in TWO operations: 1/255 = r + r2 with r = RN(1/255), r2 = RN(1/255 - r); q = fma(x, r,
+// RN(x * r2)).  Equal to the correctly rounded quotient for EVERY float with 7.7e-34 < |x| <= 256 and for 0
+// (exhaustive host check: profiles/microbench/div255_check.c, 1 132 462 081 inputs; the failures of the two-operation
+// form all lie in [1.2e-38, 7.7e-34], where x * r2 underflows).  A CLAHE blend is 0 or at least 2^-60 in magnitude: its
+// operands are multiples of 2^-30 (integers times k/63 weights).
+__device__ __forceinline__ f32x2 div255_x2(f32x2 x) {
+    const f32x2 r = f2_dup(0.003921568859368563f), r2 = f2_dup(-2.3191758240217e-10f);
+    return f2_fma(x, r, f2_mul(x, r2));
 }
 
 // Histogram increment.  atomicAdd(p, 1) with an unused result compiles to ATOMS.POPC.INC.32, which
@@ -385,6 +434,19 @@ __device__ __forceinline__ float clahe_px(uint2 e, float wxv, float wyv) {
     const float t = __fmaf_rn(wxv, dt, tr);
     const float b = __fmaf_rn(wxv, db, br);
     return div255(__fmaf_rn(wyv, __fsub_rn(t, b), b));
+}
+
+// The same for the pixels of rows s and s + 1 of one column as a packed pair (entries e0, e1; column weight wx2 =
+// (wx, wx), row weights wy2 = (wy_s, wy_s+1)): one packed instruction per step instead of two scalar ones — the same
+// IEEE operations per lane, so the same bits as clahe_px.
+__device__ __forceinline__ f32x2 clahe_px2(uint2 e0, uint2 e1, f32x2 wx2, f32x2 wy2) {
+    const f32x2 dt = f2_pack(__uint_as_float(__byte_perm(e0.x, 0u, 0x1044)), __uint_as_float(__byte_perm(e1.x, 0u, 0x1044)));
+    const f32x2 tr = f2_pack(__uint_as_float(e0.x & 0xFFFF0000u), __uint_as_float(e1.x & 0xFFFF0000u));
+    const f32x2 db = f2_pack(__uint_as_float(__byte_perm(e0.y, 0u, 0x1044)), __uint_as_float(__byte_perm(e1.y, 0u, 0x1044)));
+    const f32x2 br = f2_pack(__uint_as_float(e0.y & 0xFFFF0000u), __uint_as_float(e1.y & 0xFFFF0000u));
+    const f32x2 t = f2_fma(wx2, dt, tr);
+    const f32x2 b = f2_fma(wx2, db, br);
+    return div255_x2(f2_fma(wy2, f2_sub(t, b), b));
 }
 
 // Interpolation weight of the upper / left tile for haloed index k (tile position p = k - 4):

@@ -98,15 +98,34 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
     const char* my_raw = reinterpret_cast<const char*>(s_raw) + 4 * tid * (int)sizeof(SrcT);
 
     // rows 2p, 2p+1 (ring slots rslot, rslot + 1); p even = first use of batch p / 2
-    auto convert = [&](const int p, const int rslot, float* x0, float* x1) {
+    // -> packed (row 2p, row 2p + 1) pairs of the thread's four columns: the layout of the pair buffer
+    auto convert = [&](const int p, const int rslot, f32x2* xp) {
         if (p % 2 == 0) mbar_wait(bar32 + 8 * ((p / 2) % kRawBars), (uint32_t)((p / 2 / kRawBars) & 1));
         const raw4 r0 = *reinterpret_cast<const raw4*>(my_raw + (rslot % kRawRows) * row_bytes);
         const raw4 r1 = *reinterpret_cast<const raw4*>(my_raw + ((rslot + 1) % kRawRows) * row_bytes);
-        PixIO<SrcT, WIN>::cvt_raw4(r0, x0, cv);
-        PixIO<SrcT, WIN>::cvt_raw4(r1, x1, cv);
-        if (BORDER == MIE_BORDER_CONSTANT) {
-            if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
-            if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
+        if constexpr (sizeof(SrcT) == 2 && !WIN) {
+            Fast<SrcT>::cvt_pair4(r0, r1, xp);   // 16-bit default range: the conversion itself runs packed
+            if (BORDER == MIE_BORDER_CONSTANT) {
+                const bool z0 = s_off[2 * p] < 0, z1 = s_off[2 * p + 1] < 0;
+                if (z0 || z1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float a, b;
+                        f2_unpack(xp[k], a, b);
+                        xp[k] = f2_pack(z0 ? 0.0f : a, z1 ? 0.0f : b);
+                    }
+                }
+            }
+        } else {
+            float x0[4], x1[4];
+            PixIO<SrcT, WIN>::cvt_raw4(r0, x0, cv);
+            PixIO<SrcT, WIN>::cvt_raw4(r1, x1, cv);
+            if (BORDER == MIE_BORDER_CONSTANT) {
+                if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
+                if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xp[k] = f2_pack(x0[k], x1[k]);
         }
     };
     // after the barrier of an odd row pair p its batch (p - 1) / 2 is consumed: refill the slots
@@ -134,13 +153,13 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
     // ---- prologue: row pairs 0..3 fill ring slots 0..7
 #pragma unroll
     for (int p = 0; p < kMPro; ++p) {
-        float x0[4], x1[4];
-        convert(p, 2 * p, x0, x1);
+        f32x2 xp[4];
+        convert(p, 2 * p, xp);
         float* buf = s_buf + (p % 2) * pbuf;
-        pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+        pair_store_packed<BORDER>(buf, T, tid, first_warp, last_warp, xp);
         __syncthreads();
         if (p % 2 == 1) refill(p);
-        pair_row_pass(buf, T, tid, wx, ring, 2 * p);
+        pair_row_pass(buf, T, tid, wx, ring, 2 * p, xp);
     }
     // ---- main loop: 4 x 8 row pairs; pair q of an iteration = rows 8 + 16 i + 2q (+1) -> ring slots
     //      8 + 2q (+1); the two rows that become complete are the ones eight rows above
@@ -148,13 +167,13 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
 #pragma unroll
         for (int q = 0; q < kMUnroll; ++q) {
             const int p = p0 + q;
-            float x0[4], x1[4];
-            convert(p, 2 * kMPro + 2 * q, x0, x1);
+            f32x2 xp[4];
+            convert(p, 2 * kMPro + 2 * q, xp);
             float* buf = s_buf + (q % 2) * pbuf;
-            pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+            pair_store_packed<BORDER>(buf, T, tid, first_warp, last_warp, xp);
             __syncthreads();
             if (q % 2 == 1) refill(p);
-            pair_row_pass(buf, T, tid, wx, ring, 2 * kMPro + 2 * q);
+            pair_row_pass(buf, T, tid, wx, ring, 2 * kMPro + 2 * q, xp);
             float g[4];
             march_col_pass(ring, 2 * q, wy, g);
             emit(g);
@@ -236,44 +255,53 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
     const int dsh = (int)a.dsh;
     f32x2 ring[kMRing][2];
 
-    auto clahe_row = [&](const uint32_t tb, const uint32_t iw, const float wyv, float* x) {
-        x[0] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4440) << 3)), wxv[0], wyv);
-        x[1] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4441) << 3)), wxv[1], wyv);
-        x[2] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4442) << 3)), wxv[2], wyv);
-        x[3] = clahe_px(lds64(tb + (__byte_perm(iw, 0u, 0x4443) << 3)), wxv[3], wyv);
-    };
-    auto clahe_pair = [&](const int p, const int pslot, float* x0, float* x1) {
-        // both rows of a pair lie in the same cell row (the switch is at band row 36)
+    // both rows of a pair lie in the same cell row (the switch is at band row 36); the two rows of column k are blended
+    // as one packed pair — which is also the layout of the pair buffer
+    f32x2 wx2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wx2[k] = f2_pack(wxv[k], wxv[k]);
+    auto clahe_pair = [&](const int p, const int pslot, f32x2* xp) {
         const uint32_t tb = tb0 + (2 * p >= kTile / 2 + kMR ? tb_step : 0u);
-        clahe_row(tb, raw[pslot][0], aw.w[2 * p], x0);
-        clahe_row(tb, raw[pslot][1], aw.w[2 * p + 1], x1);
+        const uint32_t i0 = raw[pslot][0], i1 = raw[pslot][1];
+        const f32x2 wy2 = f2_pack(aw.w[2 * p], aw.w[2 * p + 1]);
+        xp[0] = clahe_px2(lds64(tb + (__byte_perm(i0, 0u, 0x4440) << 3)), lds64(tb + (__byte_perm(i1, 0u, 0x4440) << 3)), wx2[0], wy2);
+        xp[1] = clahe_px2(lds64(tb + (__byte_perm(i0, 0u, 0x4441) << 3)), lds64(tb + (__byte_perm(i1, 0u, 0x4441) << 3)), wx2[1], wy2);
+        xp[2] = clahe_px2(lds64(tb + (__byte_perm(i0, 0u, 0x4442) << 3)), lds64(tb + (__byte_perm(i1, 0u, 0x4442) << 3)), wx2[2], wy2);
+        xp[3] = clahe_px2(lds64(tb + (__byte_perm(i0, 0u, 0x4443) << 3)), lds64(tb + (__byte_perm(i1, 0u, 0x4443) << 3)), wx2[3], wy2);
         if (BORDER == MIE_BORDER_CONSTANT) {
-            if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
-            if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
+            const bool z0 = s_off[2 * p] < 0, z1 = s_off[2 * p + 1] < 0;
+            if (z0 || z1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float a, b;
+                    f2_unpack(xp[k], a, b);
+                    xp[k] = f2_pack(z0 ? 0.0f : a, z1 ? 0.0f : b);
+                }
+            }
         }
     };
 
 #pragma unroll
     for (int p = 0; p < kMPro; ++p) {
         if (p % 2 == 0) fetch_pairs(p + 6, (p + 6) % 8);
-        float x0[4], x1[4];
-        clahe_pair(p, p % 8, x0, x1);
+        f32x2 xp[4];
+        clahe_pair(p, p % 8, xp);
         float* buf = s_buf + (p % 4) * pbuf;
-        pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+        pair_store_packed<BORDER>(buf, T, tid, first_warp, last_warp, xp);
         __syncthreads();
-        pair_row_pass(buf, T, tid, wx, ring, 2 * p);
+        pair_row_pass(buf, T, tid, wx, ring, 2 * p, xp);
     }
     for (int p0 = kMPro; p0 < kMPairs; p0 += kMUnroll) {
 #pragma unroll
         for (int q = 0; q < kMUnroll; ++q) {
             const int p = p0 + q;
             if (q % 2 == 0) fetch_pairs(p + 6, (kMPro + q + 6) % 8);
-            float x0[4], x1[4];
-            clahe_pair(p, (kMPro + q) % 8, x0, x1);
+            f32x2 xp[4];
+            clahe_pair(p, (kMPro + q) % 8, xp);
             float* buf = s_buf + (q % 4) * pbuf;
-            pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+            pair_store_packed<BORDER>(buf, T, tid, first_warp, last_warp, xp);
             __syncthreads();
-            pair_row_pass(buf, T, tid, wx, ring, 2 * kMPro + 2 * q);
+            pair_row_pass(buf, T, tid, wx, ring, 2 * kMPro + 2 * q, xp);
             // centre pixels of the two completed rows: rows (2p - 4, 2p - 3) = pair p - 2
             const float* cbuf = s_buf + ((q + 2) % 4) * pbuf;
             const float4 ca = *reinterpret_cast<const float4*>(cbuf + 4 * (tid + 1));

@@ -88,6 +88,41 @@ __device__ __forceinline__ void pair_store(float* buf, int T, int tid, bool firs
     }
 }
 
+// The same from packed (row s, row s + 1) pairs xp[k] of the thread's four columns: the buffer layout IS that pairing,
+// so the two 16-byte stores need no register shuffling.
+template <int BORDER>
+__device__ __forceinline__ void pair_store_packed(float* buf, int T, int tid, bool first_warp, bool last_warp,
+                                                  const f32x2* xp) {
+    float* A = buf;
+    float* B = buf + 4 * (T + 2);
+    *reinterpret_cast<ulonglong2*>(A + 4 * (tid + 1)) = make_ulonglong2(xp[0], xp[1]);
+    *reinterpret_cast<ulonglong2*>(B + 4 * (tid + 1)) = make_ulonglong2(xp[2], xp[3]);
+    if (first_warp) {  // columns -4..-1 mirror onto 4, 3, 2, 1
+        f32x2 nb = 0ull;
+        if (BORDER == MIE_BORDER_REFLECT) nb = __shfl_down_sync(0xffffffffu, xp[0], 1);
+        if (tid == 0) {
+            ulonglong2 a, b;
+            if (BORDER == MIE_BORDER_REFLECT) { a = make_ulonglong2(nb, xp[3]); b = make_ulonglong2(xp[2], xp[1]); }
+            else if (BORDER == MIE_BORDER_REPLICATE) a = b = make_ulonglong2(xp[0], xp[0]);
+            else a = b = make_ulonglong2(0ull, 0ull);
+            *reinterpret_cast<ulonglong2*>(A) = a;
+            *reinterpret_cast<ulonglong2*>(B) = b;
+        }
+    }
+    if (last_warp) {  // columns W..W+3 mirror onto W-2, W-3, W-4, W-5
+        f32x2 nb = 0ull;
+        if (BORDER == MIE_BORDER_REFLECT) nb = __shfl_up_sync(0xffffffffu, xp[3], 1);
+        if (tid == T - 1) {
+            ulonglong2 a, b;
+            if (BORDER == MIE_BORDER_REFLECT) { a = make_ulonglong2(xp[2], xp[1]); b = make_ulonglong2(xp[0], nb); }
+            else if (BORDER == MIE_BORDER_REPLICATE) a = b = make_ulonglong2(xp[3], xp[3]);
+            else a = b = make_ulonglong2(0ull, 0ull);
+            *reinterpret_cast<ulonglong2*>(A + 4 * (T + 1)) = a;
+            *reinterpret_cast<ulonglong2*>(B + 4 * (T + 1)) = b;
+        }
+    }
+}
+
 // Horizontal 9-tap pass of both rows of a pair for the thread's four columns, written straight into
 // the register ring.  Tap order and rounding as everywhere else (acc = w0 x0; acc = fma(w_t, x_t, acc)).
 // The window comes out of shared memory already packed — a 16-byte load is two (row s, row s+1)
@@ -95,13 +130,19 @@ __device__ __forceinline__ void pair_store(float* buf, int T, int tid, bool firs
 // their results are fresh registers, which lets ptxas place (column c, column c+1) of one row in an
 // aligned pair for the vertical pass at no cost (re-pairing the halves of packed results instead costs
 // two register copies at every one of their nine uses).
+// `own` (optional): the thread's own four pairs, still in registers from the store — the middle third of the window
+// then costs no shared-memory loads.
 __device__ __forceinline__ void pair_row_pass(const float* buf, int T, int tid, const Taps& wx,
-                                              f32x2 (&ring)[kMRing][2], const int slot) {
+                                              f32x2 (&ring)[kMRing][2], const int slot, const f32x2* own = nullptr) {
     const ulonglong2* A = reinterpret_cast<const ulonglong2*>(buf) + tid;
     const ulonglong2* B = reinterpret_cast<const ulonglong2*>(buf + 4 * (T + 2)) + tid;
     f32x2 win[12];
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
+        if (q == 1 && own) {
+            win[4] = own[0]; win[5] = own[1]; win[6] = own[2]; win[7] = own[3];
+            continue;
+        }
         const ulonglong2 a = A[q], b = B[q];
         win[4 * q] = a.x; win[4 * q + 1] = a.y; win[4 * q + 2] = b.x; win[4 * q + 3] = b.y;
     }
