@@ -12,7 +12,9 @@ import os
 import torch
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libmie_b200.so")
+# MIE_B200_LIB: path of an alternative BUILD of the same library (kernel-development A/B runs under benchmarks/dev);
+# it selects a file, not a code path — every build exports the same ABI and has no fallback either.
+LIB_PATH = os.environ.get("MIE_B200_LIB") or os.path.join(PKG_DIR, "libmie_b200.so")
 
 MIE_U8, MIE_U16, MIE_I16, MIE_F32, MIE_F64 = 0, 1, 2, 3, 4
 BORDER = {"constant": 0, "reflect": 1, "replicate": 2, "circular": 3, "symmetric": 4}

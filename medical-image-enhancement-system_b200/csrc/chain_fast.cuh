@@ -344,6 +344,29 @@ __device__ __forceinline__ void hist_add_le1(uint32_t base32, float g) {
 __device__ __forceinline__ uint32_t fast_idx_bits_le1(float g) {
     return __float_as_uint(__fadd_rd(__fmul_rn(g, 255.0f), 8388608.0f));
 }
+// The two LE1 rules on a packed pair of blurred values (same per-lane operations and rounding modes as
+// fast_idx_bits_le1 / hist_add_le1; ptxas keeps mul.rn + add.rm apart because the rounding modes differ).
+__device__ __forceinline__ f32x2 f2_add_rm(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 f2_fma_rm(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ void idx_bits_le1_x2(f32x2 g, uint32_t& b0, uint32_t& b1) {
+    float a, b;
+    f2_unpack(f2_add_rm(f2_mul(g, f2_pack(255.0f, 255.0f)), f2_pack(8388608.0f, 8388608.0f)), a, b);
+    b0 = __float_as_uint(a); b1 = __float_as_uint(b);
+}
+__device__ __forceinline__ void hist_add_le1_x2(uint32_t base32, f32x2 g) {
+    float a, b;
+    f2_unpack(f2_fma_rm(g, f2_pack(256.0f, 256.0f), f2_pack(8388608.0f, 8388608.0f)), a, b);
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base32 + (__float_as_uint(a) << 2)) : "memory");
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(base32 + (__float_as_uint(b) << 2)) : "memory");
+}
 
 // Clip / redistribute / cumulate -> 256 LUT bytes, computed by ONE warp from the
 // block-total histogram in shared memory (lane L owns bins 8L..8L+7).

@@ -21,6 +21,10 @@
 #include "march.cuh"
 #include "window.cuh"
 
+#ifndef MIE_B_AHEAD
+#define MIE_B_AHEAD 6
+#endif
+
 namespace mie {
 
 // ================================================================ chain_a (marching)
@@ -135,11 +139,13 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
     };
     auto emit = [&](const float* g) {
         if (LE1) {
-            *reinterpret_cast<uint32_t*>(ip) =
-                pack_low_bytes(fast_idx_bits_le1(g[0]), fast_idx_bits_le1(g[1]), fast_idx_bits_le1(g[2]),
-                               fast_idx_bits_le1(g[3]));
-#pragma unroll
-            for (int k = 0; k < 4; ++k) hist_add_le1(my_hist32, g[k]);
+            const f32x2 ga = f2_pack(g[0], g[1]), gb = f2_pack(g[2], g[3]);   // as the column pass produced them
+            uint32_t b0, b1, b2, b3;
+            idx_bits_le1_x2(ga, b0, b1);
+            idx_bits_le1_x2(gb, b2, b3);
+            *reinterpret_cast<uint32_t*>(ip) = pack_low_bytes(b0, b1, b2, b3);
+            hist_add_le1_x2(my_hist32, ga);
+            hist_add_le1_x2(my_hist32, gb);
         } else {
             *reinterpret_cast<uint32_t*>(ip) =
                 pack_low_bytes(fast_idx_bits<NN>(g[0]), fast_idx_bits<NN>(g[1]), fast_idx_bits<NN>(g[2]),
@@ -209,6 +215,7 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
     uint2* s_tab = reinterpret_cast<uint2*>(smem);            // 2 x (gw+1) x 256 entries
     float* s_buf = smem + 2 * (gw + 1) * kBins * 2;           // 4 pair buffers
     int* s_off = reinterpret_cast<int*>(s_buf + 4 * pbuf);    // kMOffRows
+    unsigned long long* s_tbar = reinterpret_cast<unsigned long long*>(s_off + kMOffRows);   // 1 mbarrier (8-byte aligned)
 
     const int tid = threadIdx.x, warp = tid >> 5, nwarps = T >> 5;
     const int ty = (int)(blockIdx.x % gh);
@@ -217,32 +224,54 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
     const bool first_warp = warp == 0, last_warp = warp == nwarps - 1;
 
     fill_row_offsets<BORDER>(s_off, ty0, h, W, tid, T);
-    {
-        const uint4* src = reinterpret_cast<const uint4*>(cells + (n * (gh + 1) + ty) * (int64_t)(gw + 1) * kBins);
-        uint4* dst4 = reinterpret_cast<uint4*>(s_tab);
-        const int total = 2 * (gw + 1) * kBins / 2;  // 16-byte pieces
-        for (int i = tid; i < total; i += T) dst4[i] = __ldg(src + i);
+    // The band's two rows of cell tables are contiguous in the workspace (36.9 KB for gw = 8): ONE bulk copy (TMA) by one
+    // thread brings them in while the block computes its row offsets and issues its first index loads.  The
+    // LDG -> STS loop it replaces cost every thread 18 load / store round trips before the walk could start (8 % of
+    // the kernel's stall samples, profiles/r2_ncu_full_chain_kernels_v7.txt).
+    const uint32_t tbar32 = (uint32_t)__cvta_generic_to_shared(s_tbar);
+    if (tid == 0) {
+        mbar_init(tbar32, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t bytes = (uint32_t)(2 * (gw + 1) * kBins * 8);
+        mbar_expect_tx(tbar32, bytes);
+        // bulk copies are limited to sizes the hardware counter can hold; chunks of 16 KB keep every size legal
+        const char* src = reinterpret_cast<const char*>(cells + (n * (gh + 1) + ty) * (int64_t)(gw + 1) * kBins);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tab);
+        for (uint32_t o = 0; o < bytes; o += 16384u)
+            bulk_g2s(dst + o, src + o, min(16384u, bytes - o), tbar32);
     }
     __syncthreads();
 
     const uint8_t* iplane = a.idx + n * (int64_t)h * W + 4 * tid;
-    // raw[p % 8][j] = index word of row 2p + j, loaded 6..7 row pairs ahead of its use (one register
-    // per row, so depth is cheap here; at 4..5 pairs one use still showed 6 % long-scoreboard stalls)
-    uint32_t raw[8][2];
-    auto fetch_pairs = [&](const int p, const int slot) {
+    // raw[p % kRawSlots][j] = index word of row 2p + j, loaded kAhead row pairs ahead of its use.
+    // ptxas tracks ALL of this kernel's global loads on ONE scoreboard (SASS control words: every LDG of the loop
+    // writes barrier 5), and a scoreboard is a counter: the first read of ANY loaded word waits until EVERY
+    // outstanding load has landed, including a group issued a few instructions earlier — which exposed the full
+    // memory latency four times per loop iteration however far ahead the loads were issued (ncu: long_scoreboard was
+    // the top stall, 1.02 warps per issue).  So the order is forced: first DRAIN (read one word of the group that is
+    // due: everything outstanding is at least two row pairs old by then), and only then issue the next group, whose
+    // addresses depend on the drained word through `zero` — a value that is always 0 (threadIdx.y of a 1-D block) but
+    // that the compiler cannot know — so the loads cannot be hoisted above the drain.
+    constexpr int kAhead = MIE_B_AHEAD;   // row pairs between an index load and its use (even)
+    constexpr int kRawSlots = kAhead <= 2 ? 4 : 8;
+    uint32_t raw[kRawSlots][2];
+    const uint32_t zero = threadIdx.y;
+    auto fetch_pairs = [&](const int p, const int slot, const uint32_t dep) {
         const int4 o = *reinterpret_cast<const int4*>(s_off + 2 * p);
         const int off[4] = {o.x, o.y, o.z, o.w};
+        const uint8_t* base = iplane + dep;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t v = 0u;
             if (BORDER != MIE_BORDER_CONSTANT || off[j] >= 0)
-                v = __ldg(reinterpret_cast<const uint32_t*>(iplane + (unsigned)off[j]));
-            raw[(slot + j / 2) % 8][j & 1] = v;
+                v = __ldg(reinterpret_cast<const uint32_t*>(base + (unsigned)off[j]));
+            raw[(slot + j / 2) % kRawSlots][j & 1] = v;
         }
     };
-    fetch_pairs(0, 0);
-    fetch_pairs(2, 2);
-    fetch_pairs(4, 4);
+    // drain: a real read of the due word; the result is always 0
+    auto drain = [&](const int slot) -> uint32_t { return raw[slot][0] & zero; };
+#pragma unroll
+    for (int p = 0; p < kAhead; p += 2) fetch_pairs(p, p % kRawSlots, 0u);
 
     // cells of this thread's columns: column cell (4t + 32) / 64; row cell 0 (rows above the tile
     // centre line ty0 + 32, i.e. band rows < 36) or 1.  Shared-window byte addresses: lookup = LEA + LDS.64.
@@ -254,6 +283,7 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
     DstT* op = (DstT*)a.dst + n * a.dsn + (int64_t)ty0 * a.dsh + 4 * tid;
     const int dsh = (int)a.dsh;
     f32x2 ring[kMRing][2];
+    mbar_wait(tbar32, 0u);   // cell tables have landed
 
     // both rows of a pair lie in the same cell row (the switch is at band row 36); the two rows of column k are blended
     // as one packed pair — which is also the layout of the pair buffer
@@ -283,9 +313,9 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
 
 #pragma unroll
     for (int p = 0; p < kMPro; ++p) {
-        if (p % 2 == 0) fetch_pairs(p + 6, (p + 6) % 8);
+        if (p % 2 == 0) fetch_pairs(p + kAhead, (p + kAhead) % kRawSlots, drain(p % kRawSlots));
         f32x2 xp[4];
-        clahe_pair(p, p % 8, xp);
+        clahe_pair(p, p % kRawSlots, xp);
         float* buf = s_buf + (p % 4) * pbuf;
         pair_store_packed<BORDER>(buf, T, tid, first_warp, last_warp, xp);
         __syncthreads();
@@ -295,9 +325,9 @@ chain_b_march_kernel(ChainBArgs a, const uint2* __restrict__ cells, AxisWeights 
 #pragma unroll
         for (int q = 0; q < kMUnroll; ++q) {
             const int p = p0 + q;
-            if (q % 2 == 0) fetch_pairs(p + 6, (kMPro + q + 6) % 8);
+            if (q % 2 == 0) fetch_pairs(p + kAhead, (kMPro + q + kAhead) % kRawSlots, drain((kMPro + q) % kRawSlots));
             f32x2 xp[4];
-            clahe_pair(p, (kMPro + q) % 8, xp);
+            clahe_pair(p, (kMPro + q) % kRawSlots, xp);
             float* buf = s_buf + (q % 4) * pbuf;
             pair_store_packed<BORDER>(buf, T, tid, first_warp, last_warp, xp);
             __syncthreads();
@@ -335,7 +365,7 @@ static size_t march_a_smem(const ClaheGeom& g, int elem_bytes) {
            (size_t)kRawRows * g.w * elem_bytes;
 }
 static size_t march_b_smem(const ClaheGeom& g) {
-    return (size_t)(2 * (g.gw + 1) * kBins * 2 + 4 * 8 * (g.w / 4 + 2) + kMOffRows) * 4;
+    return (size_t)(2 * (g.gw + 1) * kBins * 2 + 4 * 8 * (g.w / 4 + 2) + kMOffRows) * 4 + 8;
 }
 
 // Blur of an all-ones image in the kernels' operation order.  Every fma is monotone in its data

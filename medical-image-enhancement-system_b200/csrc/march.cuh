@@ -130,22 +130,9 @@ __device__ __forceinline__ void pair_store_packed(float* buf, int T, int tid, bo
 // their results are fresh registers, which lets ptxas place (column c, column c+1) of one row in an
 // aligned pair for the vertical pass at no cost (re-pairing the halves of packed results instead costs
 // two register copies at every one of their nine uses).
-// `own` (optional): the thread's own four pairs, still in registers from the store — the middle third of the window
-// then costs no shared-memory loads.
-__device__ __forceinline__ void pair_row_pass(const float* buf, int T, int tid, const Taps& wx,
-                                              f32x2 (&ring)[kMRing][2], const int slot, const f32x2* own = nullptr) {
-    const ulonglong2* A = reinterpret_cast<const ulonglong2*>(buf) + tid;
-    const ulonglong2* B = reinterpret_cast<const ulonglong2*>(buf + 4 * (T + 2)) + tid;
-    f32x2 win[12];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        if (q == 1 && own) {
-            win[4] = own[0]; win[5] = own[1]; win[6] = own[2]; win[7] = own[3];
-            continue;
-        }
-        const ulonglong2 a = A[q], b = B[q];
-        win[4 * q] = a.x; win[4 * q + 1] = a.y; win[4 * q + 2] = b.x; win[4 * q + 3] = b.y;
-    }
+// Row-pass arithmetic on a ready window: win[j] = (row s, row s + 1) pair of haloed column j (12 columns for the
+// thread's four outputs).
+__device__ __forceinline__ void row_pass_window(const f32x2* win, const Taps& wx, f32x2 (&ring)[kMRing][2], const int slot) {
     f32x2 acc[4];
     const f32x2 w0 = f2_pack(wx.w[0], wx.w[0]);
 #pragma unroll
@@ -169,6 +156,25 @@ __device__ __forceinline__ void pair_row_pass(const float* buf, int T, int tid, 
     ring[slot % kMRing][1] = f2_pack(m0[2], m0[3]);
     ring[(slot + 1) % kMRing][0] = f2_pack(m1[0], m1[1]);
     ring[(slot + 1) % kMRing][1] = f2_pack(m1[2], m1[3]);
+}
+
+// `own` (optional): the thread's own four pairs, still in registers from the store — the middle third of the window
+// then costs no shared-memory loads.
+__device__ __forceinline__ void pair_row_pass(const float* buf, int T, int tid, const Taps& wx,
+                                              f32x2 (&ring)[kMRing][2], const int slot, const f32x2* own = nullptr) {
+    const ulonglong2* A = reinterpret_cast<const ulonglong2*>(buf) + tid;
+    const ulonglong2* B = reinterpret_cast<const ulonglong2*>(buf + 4 * (T + 2)) + tid;
+    f32x2 win[12];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if (q == 1 && own) {
+            win[4] = own[0]; win[5] = own[1]; win[6] = own[2]; win[7] = own[3];
+            continue;
+        }
+        const ulonglong2 a = A[q], b = B[q];
+        win[4 * q] = a.x; win[4 * q + 1] = a.y; win[4 * q + 2] = b.x; win[4 * q + 3] = b.y;
+    }
+    row_pass_window(win, wx, ring, slot);
 }
 
 // Vertical 9-tap pass out of the register ring; OLDEST = ring slot of the topmost tap (a constant
