@@ -17,9 +17,9 @@ for name, fn in (("h2d", lambda: xd.copy_(x_host, non_blocking=True)), ("d2h", l
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print(name, round(ms, 3), "ms", round(134.2 / ms, 1), "GB/s")
-for chunk in (64, 32, 16, 8, 4, 2):
-    for depth in (3, 4):
-        pipe = HostSlicePipeline(dev, (512, 512), torch.uint16, chunk=chunk, depth=depth)
+for chunk in (64, 32, 16):
+    for depth, taper in ((3, False), (3, True), (4, True)):
+        pipe = HostSlicePipeline(dev, (512, 512), torch.uint16, chunk=chunk, depth=depth, taper=taper)
         for _ in range(2): pipe.run(x_host, y_host)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -29,4 +29,4 @@ for chunk in (64, 32, 16, 8, 4, 2):
         e1.record(); torch.cuda.synchronize()
         ok = bool((y_host == ref).all()) if "ref" in globals() else None
         if "ref" not in globals(): ref = y_host.clone()
-        print("chunk", chunk, "depth", depth, "same-as-first", ok, round(e0.elapsed_time(e1) / 5, 3), "ms; wall", round((time.perf_counter() - t0) / 5 * 1e3, 3))
+        print("chunk", chunk, "depth", depth, "taper", taper, "same-as-first", ok, round(e0.elapsed_time(e1) / 5, 3), "ms; wall", round((time.perf_counter() - t0) / 5 * 1e3, 3))

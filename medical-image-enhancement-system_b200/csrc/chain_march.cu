@@ -21,6 +21,9 @@
 #include "march.cuh"
 #include "window.cuh"
 
+#ifndef MIE_A_MINB
+#define MIE_A_MINB 5
+#endif
 #ifndef MIE_B_AHEAD
 #define MIE_B_AHEAD 6
 #endif
@@ -399,8 +402,8 @@ static int launch_a_march_tbl(const ChainAArgs& a, const Taps& wx, const Taps& w
     // W <= 512: 128 threads per block, registers capped so that five blocks fit on an SM (4 and 6 measured slower)
     const size_t smem = march_a_smem(a.g, (int)sizeof(SrcT));
     if (a.g.w <= 512) {
-        MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5>), 100 * 1024);
-        chain_a_march_kernel<SrcT, BORDER, LE1, 128, 5><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
+        MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 128, MIE_A_MINB>), 100 * 1024);
+        chain_a_march_kernel<SrcT, BORDER, LE1, 128, MIE_A_MINB><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
     } else {
         MIE_ENSURE_SMEM((chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2>), 100 * 1024);
         chain_a_march_kernel<SrcT, BORDER, LE1, 256, 2><<<blocks, a.g.w / 4, smem, st>>>(a, wx, wy, cv);
