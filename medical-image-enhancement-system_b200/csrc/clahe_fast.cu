@@ -193,8 +193,14 @@ clahe_apply_fast_kernel(ApplyFastArgs a, const uint2* __restrict__ cells, WinCvt
         if constexpr (IDX) {   // default-range integers: the lookup index is an integer function of the code
             uint32_t u[4];
             Codes<SrcT>::load4(sp, u);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) y[k] = clahe_px(lds64_(tb + Codes<SrcT>::entry_offset(u[k])), wxv[k], wyv);
+            // two neighbouring pixels per packed instruction (same per-lane operations as clahe_px)
+            const f32x2 wy2 = f2_pack(wyv, wyv);
+            const f32x2 ya = clahe_px2(lds64_(tb + Codes<SrcT>::entry_offset(u[0])), lds64_(tb + Codes<SrcT>::entry_offset(u[1])),
+                                       f2_pack(wxv[0], wxv[1]), wy2);
+            const f32x2 yb = clahe_px2(lds64_(tb + Codes<SrcT>::entry_offset(u[2])), lds64_(tb + Codes<SrcT>::entry_offset(u[3])),
+                                       f2_pack(wxv[2], wxv[3]), wy2);
+            f2_unpack(ya, y[0], y[1]);
+            f2_unpack(yb, y[2], y[3]);
         } else {
             float x[4];
             PixIO<SrcT, WIN>::load4(sp, x, cv);

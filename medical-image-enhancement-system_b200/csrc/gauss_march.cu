@@ -20,8 +20,8 @@ struct GaussMarchArgs {
 
 // WIN: integer value_range window (csrc/window.cuh) — the divide-free windowed conversion on the way in and the
 // windowed quantisation on the way out; everything in between is the same fp32 arithmetic.
-template <typename SrcT, typename DstT, int BORDER, bool UNSHARP, bool WIN>
-__global__ void __launch_bounds__(256, 2)
+template <typename SrcT, typename DstT, int BORDER, bool UNSHARP, bool WIN, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy, WinCvt cv) {
     typedef typename Fast<SrcT>::raw4 raw4;
     extern __shared__ __align__(16) float smem[];
@@ -73,15 +73,35 @@ gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy, WinCvt cv) {
     }
     f32x2 ring[kMRing][2];
     const char* my_raw = reinterpret_cast<const char*>(s_raw) + 4 * tid * (int)sizeof(SrcT);
-    auto convert = [&](const int p, const int rslot, float* x0, float* x1) {
+    // -> packed (row 2p, row 2p + 1) pairs of the thread's four columns (the layout of the pair buffer); 16-bit pixels in
+    // their default range are converted packed as well (chain_fast.cuh: cvt_pair4)
+    auto convert = [&](const int p, const int rslot, f32x2* xp) {
         if (p % 2 == 0) mbar_wait(bar32 + 8 * ((p / 2) % kRawBars), (uint32_t)((p / 2 / kRawBars) & 1));
         const raw4 r0 = *reinterpret_cast<const raw4*>(my_raw + (rslot % kRawRows) * row_bytes);
         const raw4 r1 = *reinterpret_cast<const raw4*>(my_raw + ((rslot + 1) % kRawRows) * row_bytes);
-        PixIO<SrcT, WIN>::cvt_raw4(r0, x0, cv);
-        PixIO<SrcT, WIN>::cvt_raw4(r1, x1, cv);
-        if (BORDER == MIE_BORDER_CONSTANT) {
-            if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
-            if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
+        if constexpr (sizeof(SrcT) == 2 && !WIN) {
+            Fast<SrcT>::cvt_pair4(r0, r1, xp);
+            if (BORDER == MIE_BORDER_CONSTANT) {
+                const bool z0 = s_off[2 * p] < 0, z1 = s_off[2 * p + 1] < 0;
+                if (z0 || z1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float lo_, hi_;
+                        f2_unpack(xp[k], lo_, hi_);
+                        xp[k] = f2_pack(z0 ? 0.0f : lo_, z1 ? 0.0f : hi_);
+                    }
+                }
+            }
+        } else {
+            float x0[4], x1[4];
+            PixIO<SrcT, WIN>::cvt_raw4(r0, x0, cv);
+            PixIO<SrcT, WIN>::cvt_raw4(r1, x1, cv);
+            if (BORDER == MIE_BORDER_CONSTANT) {
+                if (s_off[2 * p] < 0) x0[0] = x0[1] = x0[2] = x0[3] = 0.0f;
+                if (s_off[2 * p + 1] < 0) x1[0] = x1[1] = x1[2] = x1[3] = 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xp[k] = f2_pack(x0[k], x1[k]);
         }
     };
     auto refill = [&](const int p) {
@@ -93,25 +113,25 @@ gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy, WinCvt cv) {
 
 #pragma unroll
     for (int p = 0; p < kMPro; ++p) {
-        float x0[4], x1[4];
-        convert(p, 2 * p, x0, x1);
+        f32x2 xp[4];
+        convert(p, 2 * p, xp);
         float* buf = s_buf + (p % 4) * pbuf;
-        pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+        pair_store_packed<BORDER>(buf, T, tid, first_warp, last_warp, xp);
         __syncthreads();
         if (p % 2 == 1) refill(p);
-        pair_row_pass(buf, T, tid, wx, ring, 2 * p);
+        pair_row_pass(buf, T, tid, wx, ring, 2 * p, xp);
     }
     for (int p0 = kMPro; p0 < kMPairs; p0 += kMUnroll) {
 #pragma unroll
         for (int q = 0; q < kMUnroll; ++q) {
             const int p = p0 + q;
-            float x0[4], x1[4];
-            convert(p, 2 * kMPro + 2 * q, x0, x1);
+            f32x2 xp[4];
+            convert(p, 2 * kMPro + 2 * q, xp);
             float* buf = s_buf + (q % 4) * pbuf;
-            pair_store<BORDER>(buf, T, tid, first_warp, last_warp, x0, x1);
+            pair_store_packed<BORDER>(buf, T, tid, first_warp, last_warp, xp);
             __syncthreads();
             if (q % 2 == 1) refill(p);
-            pair_row_pass(buf, T, tid, wx, ring, 2 * kMPro + 2 * q);
+            pair_row_pass(buf, T, tid, wx, ring, 2 * kMPro + 2 * q, xp);
             float g[4], c0[4], c1[4];
             if (UNSHARP) {  // centre pixels of rows (2p - 8, 2p - 7) + 4 = pair p - 2
                 const float* cbuf = s_buf + ((q + 2) % 4) * pbuf;
@@ -160,13 +180,18 @@ static int launch_gm_b(const GaussMarchArgs& a, const Taps& wx, const Taps& wy, 
                        const WinCvt& cv, cudaStream_t st) {
     const int T = a.w / 4;
     const size_t smem = (size_t)(4 * 8 * (T + 2) + kMOffRows) * 4 + kRawBars * 8 + (size_t)kRawRows * a.w * sizeof(SrcT);
-    if (unsharp) {
-        MIE_ENSURE_SMEM((gauss_march_kernel<SrcT, DstT, BORDER, true, WIN>), 100 * 1024);
-        gauss_march_kernel<SrcT, DstT, BORDER, true, WIN><<<blocks, T, smem, st>>>(a, wx, wy, cv);
-    } else {
-        MIE_ENSURE_SMEM((gauss_march_kernel<SrcT, DstT, BORDER, false, WIN>), 100 * 1024);
-        gauss_march_kernel<SrcT, DstT, BORDER, false, WIN><<<blocks, T, smem, st>>>(a, wx, wy, cv);
-    }
+#ifndef MIE_G_MINB
+#define MIE_G_MINB 5
+#endif
+    // W <= 512: 128 threads per block with the registers capped for MIE_G_MINB resident blocks per SM
+#define MIE_GM_LAUNCH(U_, MAXT_, MINB_)                                                                        \
+    do {                                                                                                       \
+        MIE_ENSURE_SMEM((gauss_march_kernel<SrcT, DstT, BORDER, U_, WIN, MAXT_, MINB_>), 100 * 1024);          \
+        gauss_march_kernel<SrcT, DstT, BORDER, U_, WIN, MAXT_, MINB_><<<blocks, T, smem, st>>>(a, wx, wy, cv); \
+    } while (0)
+    if (a.w <= 512) { if (unsharp) MIE_GM_LAUNCH(true, 128, MIE_G_MINB); else MIE_GM_LAUNCH(false, 128, MIE_G_MINB); }
+    else { if (unsharp) MIE_GM_LAUNCH(true, 256, 2); else MIE_GM_LAUNCH(false, 256, 2); }
+#undef MIE_GM_LAUNCH
     return check_launch();
 }
 
