@@ -164,14 +164,23 @@ struct Fast<uint16_t> {
     }
     // rows s and s + 1 of the thread's four columns (raw words a, b) -> packed (row s, row s + 1) pairs
     static __device__ __forceinline__ f32x2 from_bits2(uint32_t m0, uint32_t m1) {
-        const f32x2 t = f2_sub(f2_pack(__uint_as_float(m0), __uint_as_float(m1)), f2_pack(128.0f, 128.0f));
+        // m - 128 written as fma(m, 1, -128): the same exact difference, but FFMA2 takes broadcast scalar / immediate
+        // operands where FADD2 needs both constants materialised as a register pair (two MOVs per use)
+        const f32x2 t = f2_fma(f2_pack(__uint_as_float(m0), __uint_as_float(m1)), f2_pack(1.0f, 1.0f), f2_pack(-128.0f, -128.0f));
         return f2_fma(t, f2_pack(kC, kC), t);
     }
-    static __device__ __forceinline__ void cvt_pair4(raw4 a, raw4 b, f32x2* xp) {
-        xp[0] = from_bits2(__byte_perm(a.x, 0x43000000u, 0x7610), __byte_perm(b.x, 0x43000000u, 0x7610));
-        xp[1] = from_bits2(__byte_perm(a.x, 0x43000000u, 0x7632), __byte_perm(b.x, 0x43000000u, 0x7632));
-        xp[2] = from_bits2(__byte_perm(a.y, 0x43000000u, 0x7610), __byte_perm(b.y, 0x43000000u, 0x7610));
-        xp[3] = from_bits2(__byte_perm(a.y, 0x43000000u, 0x7632), __byte_perm(b.y, 0x43000000u, 0x7632));
+    // PRMT takes ONE immediate: with the exponent pattern 0x43000000 and the selector both constant, ptxas keeps the
+    // selectors in uniform registers and copies one into a vector register before every PRMT (8 MOVs per row pair in the
+    // marching kernels).  exp_magic() hands the pattern over as an opaque register value instead, so that the selectors
+    // can be the immediates (ptxas folds a plain `mov` of the constant back in, hence the runtime zero).
+    static __device__ __forceinline__ uint32_t exp_magic() {
+        return 0x43000000u | (blockDim.y - 1u);   // blockDim.y == 1 for every launch of these kernels: a runtime 0
+    }
+    static __device__ __forceinline__ void cvt_pair4(raw4 a, raw4 b, f32x2* xp, uint32_t magic = 0x43000000u) {
+        xp[0] = from_bits2(__byte_perm(a.x, magic, 0x7610), __byte_perm(b.x, magic, 0x7610));
+        xp[1] = from_bits2(__byte_perm(a.x, magic, 0x7632), __byte_perm(b.x, magic, 0x7632));
+        xp[2] = from_bits2(__byte_perm(a.y, magic, 0x7610), __byte_perm(b.y, magic, 0x7610));
+        xp[3] = from_bits2(__byte_perm(a.y, magic, 0x7632), __byte_perm(b.y, magic, 0x7632));
     }
 };
 
@@ -201,9 +210,10 @@ struct Fast<int16_t> {
         o.y = Fast<uint16_t>::quant2_u16x2(y[2], y[3]) ^ 0x80008000u;
         *reinterpret_cast<uint2*>(p) = o;
     }
-    static __device__ __forceinline__ void cvt_pair4(raw4 a, raw4 b, f32x2* xp) {
+    static __device__ __forceinline__ uint32_t exp_magic() { return Fast<uint16_t>::exp_magic(); }
+    static __device__ __forceinline__ void cvt_pair4(raw4 a, raw4 b, f32x2* xp, uint32_t magic = 0x43000000u) {
         a.x ^= 0x80008000u; a.y ^= 0x80008000u; b.x ^= 0x80008000u; b.y ^= 0x80008000u;   // v + 32768
-        Fast<uint16_t>::cvt_pair4(a, b, xp);
+        Fast<uint16_t>::cvt_pair4(a, b, xp, magic);
     }
 };
 
@@ -358,7 +368,8 @@ __device__ __forceinline__ f32x2 f2_fma_rm(f32x2 a, f32x2 b, f32x2 c) {
 }
 __device__ __forceinline__ void idx_bits_le1_x2(f32x2 g, uint32_t& b0, uint32_t& b1) {
     float a, b;
-    f2_unpack(f2_add_rm(f2_mul(g, f2_pack(255.0f, 255.0f)), f2_pack(8388608.0f, 8388608.0f)), a, b);
+    // RD(RN(g * 255) * 1 + 2^23): the add written as an fma with multiplicand 1 (exact), see from_bits2
+    f2_unpack(f2_fma_rm(f2_mul(g, f2_pack(255.0f, 255.0f)), f2_pack(1.0f, 1.0f), f2_pack(8388608.0f, 8388608.0f)), a, b);
     b0 = __float_as_uint(a); b1 = __float_as_uint(b);
 }
 __device__ __forceinline__ void hist_add_le1_x2(uint32_t base32, f32x2 g) {

@@ -106,12 +106,14 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
 
     // rows 2p, 2p+1 (ring slots rslot, rslot + 1); p even = first use of batch p / 2
     // -> packed (row 2p, row 2p + 1) pairs of the thread's four columns: the layout of the pair buffer
+    uint32_t exp_magic = 0u;
+    if constexpr (sizeof(SrcT) == 2 && !WIN) exp_magic = Fast<SrcT>::exp_magic();
     auto convert = [&](const int p, const int rslot, f32x2* xp) {
         if (p % 2 == 0) mbar_wait(bar32 + 8 * ((p / 2) % kRawBars), (uint32_t)((p / 2 / kRawBars) & 1));
         const raw4 r0 = *reinterpret_cast<const raw4*>(my_raw + (rslot % kRawRows) * row_bytes);
         const raw4 r1 = *reinterpret_cast<const raw4*>(my_raw + ((rslot + 1) % kRawRows) * row_bytes);
         if constexpr (sizeof(SrcT) == 2 && !WIN) {
-            Fast<SrcT>::cvt_pair4(r0, r1, xp);   // 16-bit default range: the conversion itself runs packed
+            Fast<SrcT>::cvt_pair4(r0, r1, xp, exp_magic);   // 16-bit default range: the conversion itself runs packed
             if (BORDER == MIE_BORDER_CONSTANT) {
                 const bool z0 = s_off[2 * p] < 0, z1 = s_off[2 * p + 1] < 0;
                 if (z0 || z1) {

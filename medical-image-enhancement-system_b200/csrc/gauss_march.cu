@@ -75,12 +75,14 @@ gauss_march_kernel(GaussMarchArgs a, Taps wx, Taps wy, WinCvt cv) {
     const char* my_raw = reinterpret_cast<const char*>(s_raw) + 4 * tid * (int)sizeof(SrcT);
     // -> packed (row 2p, row 2p + 1) pairs of the thread's four columns (the layout of the pair buffer); 16-bit pixels in
     // their default range are converted packed as well (chain_fast.cuh: cvt_pair4)
+    uint32_t exp_magic = 0u;
+    if constexpr (sizeof(SrcT) == 2 && !WIN) exp_magic = Fast<SrcT>::exp_magic();
     auto convert = [&](const int p, const int rslot, f32x2* xp) {
         if (p % 2 == 0) mbar_wait(bar32 + 8 * ((p / 2) % kRawBars), (uint32_t)((p / 2 / kRawBars) & 1));
         const raw4 r0 = *reinterpret_cast<const raw4*>(my_raw + (rslot % kRawRows) * row_bytes);
         const raw4 r1 = *reinterpret_cast<const raw4*>(my_raw + ((rslot + 1) % kRawRows) * row_bytes);
         if constexpr (sizeof(SrcT) == 2 && !WIN) {
-            Fast<SrcT>::cvt_pair4(r0, r1, xp);
+            Fast<SrcT>::cvt_pair4(r0, r1, xp, exp_magic);
             if (BORDER == MIE_BORDER_CONSTANT) {
                 const bool z0 = s_off[2 * p] < 0, z1 = s_off[2 * p + 1] < 0;
                 if (z0 || z1) {
