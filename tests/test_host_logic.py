@@ -224,3 +224,68 @@ def test_median25_selection_network():
         for i in range(6):
             m = np.minimum(m, np.maximum(w[i], y[5 - i]))
         assert np.array_equal(m, np.sort(v, axis=0)[12]), hi
+
+
+def test_loader_chunk_schedule_is_a_partition_with_tapered_ends():
+    """HostSlicePipeline.schedule: contiguous chunks covering [0, n) exactly once, none larger than `chunk`; with taper the
+    first and last chunks are a quarter / half of it (the exposed ends of the H2D / D2H overlap)."""
+    from mie_b200.loader import HostSlicePipeline
+
+    class P(HostSlicePipeline):
+        def __init__(self, chunk, taper):   # schedule() needs nothing else
+            self.chunk, self.taper = chunk, taper
+
+    for n in (0, 1, 7, 31, 32, 33, 64, 95, 96, 100, 256, 1000):
+        for chunk in (1, 4, 8, 32, 64):
+            for taper in (False, True):
+                spans = P(chunk, taper).schedule(n)
+                assert [a for a, _ in spans] == [0] * (1 if spans else 0) + [b for _, b in spans[:-1]]
+                assert (spans[-1][1] if spans else 0) == n
+                assert all(0 < b - a <= chunk for a, b in spans)
+    assert P(32, True).schedule(256)[0] == (0, 8) and P(32, True).schedule(256)[-1] == (248, 256)
+    assert P(32, False).schedule(256)[0] == (0, 32)
+    assert P(32, True).schedule(64) == [(0, 32), (32, 64)]          # too short to taper
+
+
+def test_loader_rejects_wrong_dtype_shape_and_device_before_touching_the_gpu():
+    """Round-1 advice: a dtype mismatch used to be converted silently by copy_ (a blocking CPU cast, wrong value range)."""
+    import torch
+    from mie_b200.loader import HostSlicePipeline
+
+    class P(HostSlicePipeline):
+        def __init__(self):
+            self.h, self.w, self.dtype, self.out_dtype = 16, 24, torch.uint16, torch.uint16
+
+    p = P()
+    good = torch.zeros(3, 16, 24, dtype=torch.uint16)
+    p._validate(good, good.clone())
+    p._validate(good.reshape(3, 1, 16, 24), good.clone())
+    with pytest.raises(TypeError):
+        p._validate(good.to(torch.int16), good)
+    with pytest.raises(TypeError):
+        p._validate(good, good.to(torch.float32))
+    with pytest.raises(ValueError):
+        p._validate(torch.zeros(3, 16, 25, dtype=torch.uint16), good)
+    with pytest.raises(ValueError):
+        p._validate(good, torch.zeros(2, 16, 24, dtype=torch.uint16))
+    with pytest.raises(ValueError):
+        p._validate(good.transpose(0, 1).transpose(0, 1)[:, ::2], good)
+    with pytest.raises(TypeError):
+        p._validate(good.numpy(), good)
+
+
+def test_two_operation_division_by_255_matches_the_quotient_on_a_sample():
+    """div255_x2 (csrc/chain_fast.cuh): q = fma(x, r, RN(x * r2)), r = RN(1/255), r2 = RN(1/255 - r).  The exhaustive
+    check over every float in [0, 256] is profiles/microbench/div255_check.c (log beside it); here a sample of blend-like
+    values is re-evaluated with exact rational arithmetic."""
+    from fractions import Fraction
+
+    r = np.float32(1.0) / np.float32(255.0)
+    r2 = np.float32(1.0 / 255.0 - float(r))
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([np.arange(0, 256, dtype=np.float32), rng.random(3000).astype(np.float32) * np.float32(255.0),
+                         np.float32([2.0 ** -60, 2.0 ** -30, 1e-8, 254.99998, 255.0, 256.0])])
+    for x in xs:
+        p = np.float32(x * r2)                                                       # RN(x * r2)
+        q = np.float32(Fraction(float(x)) * Fraction(float(r)) + Fraction(float(p)))  # fma: one rounding
+        assert q == np.float32(x) / np.float32(255.0), float(x)
