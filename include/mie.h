@@ -241,6 +241,18 @@ int mie_nlm(const void* src, void* dst, int src_dtype, int dst_dtype,
             int patch_size, int patch_distance, float h_param, float sigma,
             float lo, float hi, void* stream);
 
+/* The same function with fast_mode=False: skimage's _nl_means_denoising_2d [RECALLED] — Gaussian patch weights
+ * exp(-(di^2 + dj^2) / (2 ((s-1)/4)^2)) normalised by their sum and h^2, image reflect-padded by the patch radius
+ * only, search window clipped at the image, cut-off test (distance > 5 -> weight 0) before every patch row.
+ * float64 arithmetic in upstream's order.  dst_dtype: the source dtype, MIE_F32 or MIE_F64.  patch_size <= 15,
+ * patch_distance <= 32 (MIE_E_KERNEL beyond).                                                              */
+int mie_nlm_slow(const void* src, void* dst, int src_dtype, int dst_dtype,
+                 int64_t n, int h, int w,
+                 int64_t src_stride_n, int64_t src_stride_h,
+                 int64_t dst_stride_n, int64_t dst_stride_h,
+                 int patch_size, int patch_distance, double h_param, double sigma,
+                 float lo, float hi, void* stream);
+
 /* ------------------------------------------------------------------ quality metrics
  * Device-side reductions behind sewar.full_ref.mse / rmse / psnr / ssim (reference pyproject.toml:13,
  * pin uv.lock:692-700: sewar 0.4.6, numpy/scipy code, not installable here — semantics RECALLED).

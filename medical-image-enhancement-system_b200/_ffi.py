@@ -52,6 +52,7 @@ SIGNATURES = {
     "mie_median3d": ([_p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _i64, _p, _p, _i, _p], _i),
     "mie_bilateral": ([_p, _p, _i, _i, *_planes, _p, _i, _i, _f, _i, _f, _f, _p], _i),
     "mie_nlm": ([_p, _p, _i, _i, *_planes, _i, _i, _f, _f, _f, _f, _p], _i),
+    "mie_nlm_slow": ([_p, _p, _i, _i, *_planes, _i, _i, _d, _d, _f, _f, _p], _i),
     "mie_metric_workspace_bytes": ([_i64, _i, _i, _i], _sz),
     "mie_sqdiff_sums": ([_p, _p, _i, *_planes, _p, _p, _sz, _p], _i),
     "mie_ssim_sums": ([_p, _p, _i, *_planes, _i, _d, _d, _p, _p, _sz, _p], _i),

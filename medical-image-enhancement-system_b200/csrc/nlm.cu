@@ -17,6 +17,8 @@
 // instead of ~110 for the direct 36-term patch distance.  exp() is ex2.approx (MUFU): the result is
 // within the north star's fp32 tolerance (rel 1e-5) of the float64 oracle, not bit-exact.
 
+#include <cmath>
+
 #include "mie_common.cuh"
 
 namespace mie {
@@ -278,6 +280,133 @@ int nlm_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w
     return check_launch();
 }
 
+
+// ================================================================ slow mode (fast_mode=False)
+// skimage's _nl_means_denoising_2d / patch_distance_2d [RECALLED; SURVEY.md Appendix B4, oracle/mie_oracle.c
+// orc_nlm_slow]: Gaussian patch weights, the image reflect-padded by the patch radius only, the search window
+// clipped at the image, and the running distance tested against the cut-off 5 before every patch ROW — which is why
+// this mode cannot use the separable sliding sums above: the test makes the result depend on the order of the sum.
+// The arithmetic is float64 in upstream's order (B200 runs DFMA at half the FFMA rate), so the kernel agrees with the
+// float64 oracle to the last bits of exp(); one thread per pixel, the block's neighbourhood as doubles in shared memory.
+constexpr int kNlmSlowTile = 16;
+constexpr int kNlmSlowMaxS = 15;   // patch size <= 15: the weights travel as a kernel parameter
+constexpr int kNlmSlowMaxD = 32;
+
+struct NlmSlowArgs {
+    int h, w, tiles_x, tiles_y;
+    int s, d;
+    double var2;    // 2 sigma^2
+    float lo, rg;
+    double wgt[kNlmSlowMaxS * kNlmSlowMaxS];   // w[i][j] / (sum(w) h^2), row-major s x s
+};
+
+template <typename DstT> struct SlowOut {
+    static __device__ __forceinline__ DstT put(double y, float lo, float rg) { return Px<DstT>::from01((float)y, lo, rg); }
+};
+template <> struct SlowOut<double> {
+    static __device__ __forceinline__ double put(double y, float, float) { return y; }
+};
+
+template <typename SrcT, typename DstT>
+__global__ void __launch_bounds__(256)
+nlm_slow_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn, int64_t dsh,
+                const __grid_constant__ NlmSlowArgs a) {
+    extern __shared__ __align__(16) double dsm[];
+    constexpr int T = kNlmSlowTile;
+    const int s = a.s, o = s / 2, d = a.d, R = o + d;
+    const int E = T + 2 * R, pitch = E | 1;
+    double* S = dsm;                 // E x pitch
+    double* W = dsm + E * pitch;     // s x s
+    const int64_t tile = blockIdx.x;
+    const int tx0 = (int)(tile % a.tiles_x) * T, ty0 = (int)((tile / a.tiles_x) % a.tiles_y) * T;
+    const int64_t n = tile / ((int64_t)a.tiles_x * a.tiles_y);
+    const SrcT* plane = src + n * ssn;
+    for (int i = threadIdx.x; i < E * E; i += 256) {
+        const int r = i / E, c = i - r * E;
+        const int sy = border_index(ty0 - R + r, a.h, MIE_BORDER_REFLECT);
+        const int sx = border_index(tx0 - R + c, a.w, MIE_BORDER_REFLECT);
+        S[r * pitch + c] = (double)Px<SrcT>::to01(plane[(int64_t)sy * ssh + sx], a.lo, a.rg);
+    }
+    for (int i = threadIdx.x; i < s * s; i += 256) W[i] = a.wgt[i];
+    __syncthreads();
+    const int lx = threadIdx.x & (T - 1), ly = threadIdx.x / T;
+    const int col = tx0 + lx, row = ty0 + ly;
+    if (col >= a.w || row >= a.h) return;
+    const int i0 = row - min(d, row), i1 = row + min(d + 1, a.h - row);
+    const int j0 = col - min(d, col), j1 = col + min(d + 1, a.w - col);
+    // top-left corner of the central patch in tile coordinates
+    const double* P1 = S + (ly + R - o) * pitch + (lx + R - o);
+    double num = 0.0, den = 0.0;
+    for (int ci = i0; ci < i1; ++ci) {
+        for (int cj = j0; cj < j1; ++cj) {
+            const double* P2 = S + (ci - ty0 + R - o) * pitch + (cj - tx0 + R - o);
+            double dist = 0.0;
+            bool cut = false;
+            for (int pi = 0; pi < s; ++pi) {
+                if (dist > 5.0) { cut = true; break; }
+                const double* r1 = P1 + pi * pitch;
+                const double* r2 = P2 + pi * pitch;
+                const double* wr = W + pi * s;
+                for (int pj = 0; pj < s; ++pj) {
+                    const double df = __dsub_rn(r1[pj], r2[pj]);
+                    dist = __dadd_rn(dist, __dmul_rn(wr[pj], __dsub_rn(__dmul_rn(df, df), a.var2)));
+                }
+            }
+            if (!cut) {
+                const double weight = exp(-fmax(0.0, dist));
+                den = __dadd_rn(den, weight);
+                num = __dadd_rn(num, __dmul_rn(weight, P2[o * pitch + o]));
+            }
+        }
+    }
+    dst[n * dsn + (int64_t)row * dsh + col] = SlowOut<DstT>::put(num / den, a.lo, a.rg);
+}
+
+static int nlm_slow_impl(const void* src, void* dst, int sd, int dd, int64_t n, int h, int w, int64_t ssn, int64_t ssh,
+                         int64_t dsn, int64_t dsh, int patch_size, int patch_distance, double hpar, double sigma, float lo,
+                         float hi, cudaStream_t st) {
+    int rc = check_planes(src, dst, n, h, w, ssn, ssh, dsn, dsh);
+    if (rc) return rc;
+    if (!valid_dtype(sd) || !(dd == sd || dd == MIE_F32 || dd == MIE_F64)) return MIE_E_DTYPE;
+    if (sd != MIE_F32 && !(hi > lo)) return MIE_E_RANGE;
+    if (patch_size <= 0 || patch_distance < 0) return MIE_E_KERNEL;
+    const int s = patch_size + (patch_size % 2 == 0 ? 1 : 0);
+    const int o = s / 2;
+    if (o < 1 || s > kNlmSlowMaxS || patch_distance > kNlmSlowMaxD) return MIE_E_KERNEL;
+    if (!(hpar > 0.0) || sigma < 0.0) return MIE_E_RANGE;
+    if (o >= h || o >= w) return MIE_E_BORDER;   // np.pad(mode='reflect') by o needs o < size
+    if (n == 0) return MIE_OK;
+    NlmSlowArgs a;
+    a.h = h; a.w = w; a.tiles_x = ceil_div(w, kNlmSlowTile); a.tiles_y = ceil_div(h, kNlmSlowTile);
+    a.s = s; a.d = patch_distance; a.var2 = 2.0 * sigma * sigma; a.lo = lo; a.rg = hi - lo;
+    {   // the patch weights exactly as upstream forms them (and as orc_nlm_patch_weights does): host libm, float64
+        const double A = ((double)s - 1.0) / 4.0;
+        double sum = 0.0;
+        for (int i = 0; i < s; ++i)
+            for (int j = 0; j < s; ++j) {
+                const double di = (double)(i - o), dj = (double)(j - o);
+                a.wgt[i * s + j] = std::exp(-(di * di + dj * dj) / (2.0 * A * A));
+                sum += a.wgt[i * s + j];
+            }
+        const double scale = 1.0 / (sum * hpar * hpar);
+        for (int i = 0; i < s * s; ++i) a.wgt[i] *= scale;
+    }
+    const int64_t blocks = n * a.tiles_x * a.tiles_y;
+    if (blocks > 2147483647LL) return MIE_E_SHAPE;
+    const int E = kNlmSlowTile + 2 * (o + patch_distance);
+    const size_t smem = (size_t)(E * (E | 1) + s * s) * 8;
+    constexpr int kMaxE = kNlmSlowTile + 2 * (kNlmSlowMaxS / 2 + kNlmSlowMaxD);
+    constexpr size_t kMaxSmem = (size_t)(kMaxE * (kMaxE | 1) + kNlmSlowMaxS * kNlmSlowMaxS) * 8;
+#define MIE_NLM_SLOW(D_)                                                                                               \
+    MIE_ENSURE_SMEM((nlm_slow_kernel<SrcT, D_>), kMaxSmem);                                                            \
+    nlm_slow_kernel<SrcT, D_><<<(unsigned)blocks, 256, smem, st>>>((const SrcT*)src, (D_*)dst, ssn, ssh, dsn, dsh, a)
+    if (dd == MIE_F64) { MIE_DISPATCH_SRC(sd, MIE_NLM_SLOW(double)); }
+    else if (dd == MIE_F32) { MIE_DISPATCH_SRC(sd, MIE_NLM_SLOW(float)); }
+    else { MIE_DISPATCH_SRC(sd, MIE_NLM_SLOW(SrcT)); }
+#undef MIE_NLM_SLOW
+    return check_launch();
+}
+
 }  // namespace mie
 
 using namespace mie;
@@ -288,4 +417,12 @@ extern "C" int mie_nlm(const void* src, void* dst, int src_dtype, int dst_dtype,
                        void* stream) {
     return nlm_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h,
                     patch_size, patch_distance, h_param, sigma, lo, hi, (cudaStream_t)stream);
+}
+
+extern "C" int mie_nlm_slow(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t n, int h, int w,
+                            int64_t src_stride_n, int64_t src_stride_h, int64_t dst_stride_n, int64_t dst_stride_h,
+                            int patch_size, int patch_distance, double h_param, double sigma, float lo, float hi,
+                            void* stream) {
+    return nlm_slow_impl(src, dst, src_dtype, dst_dtype, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h,
+                         patch_size, patch_distance, h_param, sigma, lo, hi, (cudaStream_t)stream);
 }

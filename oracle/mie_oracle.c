@@ -542,6 +542,74 @@ int orc_nlm_fast(const double* in, double* out, int64_t n, int h, int w, int pat
     return 0;
 }
 
+/* ------------------------------------------------------------------ non-local means (skimage slow mode)
+ * skimage.restoration.denoise_nl_means(image, patch_size, patch_distance, h, fast_mode=False, sigma)
+ * — scikit-image 0.26.0 (reference pyproject.toml:12); restates _nl_means_denoising_2d and its helper
+ * patch_distance_2d [RECALLED] in float64:
+ *   s = patch_size (+1 if even), o = s / 2;  image reflect-padded by o only;
+ *   patch weights  w[i][j] = exp(-(di^2 + dj^2) / (2 A^2)),  A = (s - 1) / 4,  then  w *= 1 / (sum(w) h^2);
+ *   the search window of pixel (row, col) holds the centres i in [row - min(d, row), row + min(d + 1, H - row)),
+ *   j likewise: it is CLIPPED at the image, not padded (unlike fast mode);
+ *   distance = sum over patch rows, then columns, of w * ((p1 - p2)^2 - 2 sigma^2); before every patch ROW the
+ *   running distance is tested against the cut-off 5 and the weight is 0 if it is exceeded;
+ *   weight = exp(-max(0, distance));  out = sum(weight * centre pixel) / sum(weight).
+ * `wgt` (s*s doubles, row-major) is filled by orc_nlm_patch_weights so that the CUDA host code and this function
+ * can be fed the very same numbers.                                                                          */
+int orc_nlm_patch_weights(int patch_size, double hpar, double* wgt) {
+    int s = patch_size + (patch_size % 2 == 0 ? 1 : 0);
+    const int o = s / 2;
+    const double A = ((double)s - 1.0) / 4.0;
+    double sum = 0.0;
+    for (int i = 0; i < s; ++i)
+        for (int j = 0; j < s; ++j) {
+            const double di = (double)(i - o), dj = (double)(j - o);
+            wgt[i * s + j] = exp(-(di * di + dj * dj) / (2.0 * A * A));
+            sum += wgt[i * s + j];
+        }
+    const double scale = 1.0 / (sum * hpar * hpar);
+    for (int i = 0; i < s * s; ++i) wgt[i] *= scale;
+    return s;
+}
+
+int orc_nlm_slow(const double* in, double* out, int64_t n, int h, int w, int patch_size, int patch_distance,
+                 double hpar, double sigma) {
+    int s = patch_size + (patch_size % 2 == 0 ? 1 : 0);
+    const int o = s / 2, d = patch_distance;
+    if (o < 1 || s > 33 || d < 0 || !(hpar > 0.0) || o >= h || o >= w) return -7;
+    double wgt[33 * 33];
+    orc_nlm_patch_weights(patch_size, hpar, wgt);
+    const double var2 = 2.0 * sigma * sigma;
+#pragma omp parallel for schedule(dynamic, 1) collapse(2)
+    for (int64_t i = 0; i < n; ++i) {
+        for (int row = 0; row < h; ++row) {
+            const double* img = in + (size_t)i * h * w;
+            const int i0 = row - (d < row ? d : row), i1 = row + (d + 1 < h - row ? d + 1 : h - row);
+            for (int col = 0; col < w; ++col) {
+                const int j0 = col - (d < col ? d : col), j1 = col + (d + 1 < w - col ? d + 1 : w - col);
+                double num = 0.0, den = 0.0;
+                for (int ci = i0; ci < i1; ++ci)
+                    for (int cj = j0; cj < j1; ++cj) {
+                        double dist = 0.0, weight = -1.0;
+                        for (int pi = 0; pi < s; ++pi) {
+                            if (dist > 5.0) { weight = 0.0; break; }
+                            const int ay = border_index(row - o + pi, h, B_REFLECT), by = border_index(ci - o + pi, h, B_REFLECT);
+                            for (int pj = 0; pj < s; ++pj) {
+                                const int ax = border_index(col - o + pj, w, B_REFLECT), bx = border_index(cj - o + pj, w, B_REFLECT);
+                                const double df = img[(size_t)ay * w + ax] - img[(size_t)by * w + bx];
+                                dist += wgt[pi * s + pj] * (df * df - var2);
+                            }
+                        }
+                        if (weight < 0.0) weight = exp(-(dist > 0.0 ? dist : 0.0));
+                        den += weight;
+                        num += weight * img[(size_t)ci * w + cj];
+                    }
+                out[(size_t)i * h * w + (size_t)row * w + col] = num / den;
+            }
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ median (pure selection)
  * 2-D: kornia.filters.median_blur (zero padding; torch.median = lower median, the
  * true median for odd windows) / skimage.filters.median 2-D ('nearest');

@@ -57,6 +57,8 @@ class _Sig:
     orc_clahe_apply_opencv_u8 = ([_p, _p, _i64, _i, _i, _i, _i, _p], _i)
     orc_clahe_opencv_u16 = ([_p, _p, _i64, _i, _i, _i, _i, _d, _p], _i)
     orc_nlm_fast = ([_p, _p, _i64, _i, _i, _i, _i, _d, _d], _i)
+    orc_nlm_slow = ([_p, _p, _i64, _i, _i, _i, _i, _d, _d], _i)
+    orc_nlm_patch_weights = ([_i, _d, _p], _i)
     orc_median2d = ([_p, _p, _i64, _i, _i, _i, _i, _i], _i)
     orc_median3d = ([_p, _p, _i, _i, _i, _p, _p, _i], _i)
     orc_exp = ([_p, _p, _i64], None)
@@ -323,6 +325,62 @@ def nlm_fast_literal(image, patch_size=7, patch_distance=11, h=0.1, sigma=0.0) -
                     result[row + t_row, col + t_col] += wgt * padded[row, col]
     out = result[pad:-pad, pad:-pad] / weights[pad:-pad, pad:-pad]
     return out
+
+
+def denoise_nl_means_slow(x01, patch_size=7, patch_distance=11, h=0.1, sigma=0.0) -> np.ndarray:
+    """skimage.restoration.denoise_nl_means(fast_mode=False) on (..., H, W) planes of [0,1] data; float64."""
+    x, n, hh, ww = _planes(np.asarray(x01), np.float64)
+    out = np.empty_like(x)
+    rc = lib().orc_nlm_slow(_ptr(x), _ptr(out), n, hh, ww, int(patch_size), int(patch_distance), float(h), float(sigma))
+    if rc:
+        raise ValueError("invalid non-local-means parameters (patch too large for the image?)")
+    return out
+
+
+def nlm_slow_literal(image, patch_size=7, patch_distance=11, h=0.1, sigma=0.0) -> np.ndarray:
+    """Literal transcription of skimage's _nl_means_denoising_2d / patch_distance_2d loops [RECALLED] (np.pad by the
+    patch radius, meshgrid Gaussian patch weights, search window clipped at the image, cut-off test before every
+    patch row), single 2-D image, float64.  Slow: for pinning orc_nlm_slow on small images only."""
+    image = np.asarray(image, np.float64)
+    s = patch_size + (1 if patch_size % 2 == 0 else 0)
+    d = patch_distance
+    n_row, n_col = image.shape
+    offset = s // 2
+    padded = np.ascontiguousarray(np.pad(image, ((offset, offset), (offset, offset)), mode="reflect"))
+    result = np.empty_like(image)
+    A = (s - 1.0) / 4.0
+    range_vals = np.arange(-offset, offset + 1, dtype=np.float64)
+    xg_row, xg_col = np.meshgrid(range_vals, range_vals, indexing="ij")
+    w = np.ascontiguousarray(np.exp(-(xg_row * xg_row + xg_col * xg_col) / (2 * A * A)))
+    w *= 1.0 / (np.sum(w) * h * h)
+    var = 2.0 * sigma * sigma
+
+    def patch_distance_2d(p1, p2):
+        distance = 0.0
+        for i in range(s):
+            if distance > 5.0:
+                return 0.0
+            for j in range(s):
+                tmp_diff = p1[i, j] - p2[i, j]
+                distance += w[i, j] * (tmp_diff * tmp_diff - var)
+        return np.exp(-max(0.0, distance))
+
+    for row in range(n_row):
+        i_start = row - min(d, row)
+        i_end = row + min(d + 1, n_row - row)
+        for col in range(n_col):
+            new_value = 0.0
+            weight_sum = 0.0
+            j_start = col - min(d, col)
+            j_end = col + min(d + 1, n_col - col)
+            central_patch = padded[row:row + s, col:col + s]
+            for i in range(i_start, i_end):
+                for j in range(j_start, j_end):
+                    weight = patch_distance_2d(central_patch, padded[i:i + s, j:j + s])
+                    weight_sum += weight
+                    new_value += weight * padded[i + offset, j + offset]
+            result[row, col] = new_value / weight_sum
+    return result
 
 
 # ------------------------------------------------------------------ median / bilateral / equalize

@@ -316,14 +316,50 @@ def test_nlm_within_tolerance_of_float64_oracle(dev, case):
     assert np.abs(gff - ref).max() <= 1e-5
 
 
+@pytest.mark.parametrize("case", [
+    dict(shape=(2, 1, 40, 52), ps=7, pd=11, h=0.1, sigma=0.0),       # skimage defaults; windows clipped on every side
+    dict(shape=(1, 1, 48, 48), ps=5, pd=6, h=0.08, sigma=0.04),
+    dict(shape=(1, 2, 33, 21), ps=3, pd=2, h=0.05, sigma=0.01),      # ragged 16x16 tile grid
+    dict(shape=(1, 1, 32, 40), ps=8, pd=4, h=0.3, sigma=0.0),        # even patch size -> 9; large h: few cut-offs
+])
+def test_nlm_slow_mode_matches_float64_oracle(dev, case):
+    """fast_mode=False: float64 kernel in upstream's operation order (Gaussian patch weights, clipped search window,
+    cut-off test before every patch row) vs the float64 oracle — only exp() may differ, by an ulp."""
+    import mie_b200 as M
+    import oracle as O
+    from mie_b200 import synthetic
+
+    x = synthetic.phantom(case["shape"], np.uint16, seed=7)
+    x = (x.astype(np.float64) * (65535.0 / 4095.0)).clip(0, 65535).astype(np.uint16)
+    kw = dict(patch_size=case["ps"], patch_distance=case["pd"], h=case["h"], sigma=case["sigma"], fast_mode=False)
+    ref = O.denoise_nl_means_slow(O.to01(x).astype(np.float64), case["ps"], case["pd"], case["h"], case["sigma"])
+    g64 = cpu(M.denoise_nl_means(gpu(x, dev), out_dtype=torch.float64, **kw))
+    assert g64.dtype == np.float64 and np.abs(g64 - ref).max() <= 1e-13, float(np.abs(g64 - ref).max())
+    g32 = cpu(M.denoise_nl_means(gpu(x, dev), out_dtype=torch.float32, **kw))
+    assert np.array_equal(g32, ref.astype(np.float32)) or np.abs(g32 - ref).max() <= 6e-8
+    gq = cpu(M.denoise_nl_means(gpu(x, dev), **kw)).astype(np.int64)
+    rq = np.rint(np.clip(ref.astype(np.float32), 0, 1) * np.float32(65535.0)).astype(np.int64)
+    assert np.abs(gq - rq).max() <= 1 and (gq != rq).mean() < 1e-3
+    xf = O.to01(x)
+    gff = cpu(M.denoise_nl_means(gpu(xf, dev), **kw))
+    assert gff.dtype == np.float32 and np.abs(gff - ref).max() <= 6e-8
+    # the two modes are different filters: make sure the slow one is not silently the fast one
+    fast = O.denoise_nl_means(O.to01(x).astype(np.float64), case["ps"], case["pd"], case["h"], case["sigma"])
+    assert np.abs(fast - ref).max() > 1e-4
+
+
 def test_nlm_argument_errors(dev):
     import mie_b200 as M
 
     x = torch.zeros((1, 1, 64, 64), dtype=torch.float32, device=dev)
     with pytest.raises(NotImplementedError):
-        M.denoise_nl_means(x, fast_mode=False)
+        M.denoise_nl_means(x, channel_axis=-1)
     with pytest.raises((ValueError, RuntimeError)):
         M.denoise_nl_means(x, patch_size=11)
+    with pytest.raises((ValueError, RuntimeError)):
+        M.denoise_nl_means(x, patch_size=17, fast_mode=False)            # slow mode: patch size <= 15
+    with pytest.raises(TypeError):
+        M.denoise_nl_means(x.to(torch.float32), fast_mode=False, out_dtype=torch.int16)
     with pytest.raises((ValueError, RuntimeError)):
         M.denoise_nl_means(torch.zeros((1, 1, 12, 12), device=dev))      # padding would exceed the image
 

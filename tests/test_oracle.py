@@ -292,6 +292,37 @@ def test_nlm_closed_form_equals_literal_upstream_loops(ps, pd, h, sigma):
     assert np.abs(a - b).max() < 1e-12
 
 
+@pytest.mark.parametrize("ps,pd,h,sigma", [(3, 4, 0.08, 0.05), (5, 3, 0.1, 0.0), (7, 6, 0.05, 0.0), (4, 2, 0.15, 0.02)])
+def test_nlm_slow_mode_equals_literal_upstream_loops(ps, pd, h, sigma):
+    """orc_nlm_slow vs a literal transcription of skimage's _nl_means_denoising_2d / patch_distance_2d (np.pad by the
+    patch radius, meshgrid Gaussian weights, clipped search window, cut-off before every patch row)."""
+    rng = np.random.default_rng(3)
+    img = np.clip(0.5 + 0.2 * rng.standard_normal((14, 17)), 0, 1)
+    img[:6, :8] += 0.3
+    a = O.denoise_nl_means_slow(img, ps, pd, h, sigma)
+    b = O.nlm_slow_literal(img, ps, pd, h, sigma)
+    assert np.abs(a - b).max() < 1e-14
+    # the row-wise cut-off matters: h small enough that many patches are cut
+    if h <= 0.05:
+        assert (np.abs(a - img) < 1e-3).mean() > 0.2
+
+
+def test_nlm_slow_mode_properties():
+    const = np.full((20, 24), 0.3)
+    assert np.allclose(O.denoise_nl_means_slow(const, 5, 4, 0.1), 0.3, atol=1e-15)
+    rng = np.random.default_rng(1)
+    noisy = np.clip(0.5 + 0.05 * rng.normal(size=(32, 32)), 0, 1)
+    den = O.denoise_nl_means_slow(noisy, 5, 4, 0.1, sigma=0.05)
+    assert den.std() < 0.6 * noisy.std()
+    assert den.min() >= noisy.min() - 1e-12 and den.max() <= noisy.max() + 1e-12
+    import ctypes
+    w = np.zeros(49)
+    assert O.lib().orc_nlm_patch_weights(7, 0.1, w.ctypes.data_as(ctypes.c_void_p)) == 7
+    assert abs(w.sum() - 100.0) < 1e-9 and w[24] == w.max() and np.allclose(w.reshape(7, 7), w.reshape(7, 7).T)
+    with pytest.raises(ValueError):
+        O.denoise_nl_means_slow(np.zeros((3, 8)), 7, 2, 0.1)
+
+
 def test_nlm_properties():
     rng = np.random.default_rng(1)
     const = np.full((40, 40), 0.3)
