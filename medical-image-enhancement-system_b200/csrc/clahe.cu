@@ -15,10 +15,6 @@ int launch_clahe_lut_fast(const void* src, int sd, int64_t n, int64_t ssn, int64
 size_t clahe_cells_bytes(int64_t n, int gh, int gw);
 bool clahe_apply_fast_ok(const ClaheGeom& g, int sd, int dd, const void* src, const void* dst, int64_t ssn,
                          int64_t ssh, int64_t dsn, int64_t dsh, float lo, float hi);
-bool clahe_cluster_ok(const ClaheGeom& g, int sd, int dd, const void* src, const void* dst, int64_t n, int64_t ssn,
-                      int64_t ssh, int64_t dsn, int64_t dsh, float lo, float hi);
-int launch_clahe_cluster(const void* src, void* dst, int sd, int dd, int64_t n, int64_t ssn, int64_t ssh, int64_t dsn,
-                         int64_t dsh, const ClaheGeom& g, const LutParams& lp, uint8_t* luts, cudaStream_t st);
 int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t n, int64_t ssn, int64_t ssh,
                             int64_t dsn, int64_t dsh, const ClaheGeom& g, const uint8_t* luts, void* cells,
                             float lo, float hi, cudaStream_t st);
@@ -249,17 +245,6 @@ int mie_clahe(const void* src, void* dst, int src_dtype, int dst_dtype, int64_t 
     }
     if (!workspace) return MIE_E_NULL;
     if (workspace_bytes < mie_clahe_workspace_bytes(n, h, w, gh, gw)) return MIE_E_WORKSPACE;
-    if (semantics == MIE_CLAHE_KORNIA && dst && n > 0 && n <= 65535) {   // one launch: a thread-block cluster per image
-        ClaheGeom g;
-        if (clahe_common_checks(src, src_dtype, n, h, w, src_stride_n, src_stride_h, gh, gw, semantics, lo, hi, &g) == MIE_OK &&
-            check_dtypes(src_dtype, dst_dtype, lo, hi) == MIE_OK &&
-            check_planes(src, dst, n, h, w, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h) == MIE_OK &&
-            clahe_cluster_ok(g, src_dtype, dst_dtype, src, dst, n, src_stride_n, src_stride_h, dst_stride_n, dst_stride_h,
-                             lo, hi))
-            return launch_clahe_cluster(src, dst, src_dtype, dst_dtype, n, src_stride_n, src_stride_h, dst_stride_n,
-                                        dst_stride_h, g, make_lut_params(g, clip_limit, semantics), (uint8_t*)workspace,
-                                        (cudaStream_t)stream);
-    }
     int rc = clahe_luts_impl(src, src_dtype, n, h, w, src_stride_n, src_stride_h, gh, gw, clip_limit, semantics, lo,
                              hi, nullptr, (uint8_t*)workspace, (cudaStream_t)stream);
     if (rc) return rc;

@@ -21,7 +21,7 @@ def test_policy_word_is_host_state_and_rejects_unknown_bits():
             assert L.mie_get_kernel_policy() == 32 | 128 | 1
         assert L.mie_get_kernel_policy() == 32 | 128
     assert L.mie_get_kernel_policy() == 0
-    assert sum(_ffi.POLICY.values()) == 4095      # MIE_POLICY_ALL: every bit has a Python name
+    assert sum(_ffi.POLICY.values()) == 2047      # MIE_POLICY_ALL: every bit has a Python name
 
 
 def test_no_getenv_left_in_the_library_sources():
@@ -50,8 +50,6 @@ def test_tuned_and_generic_kernels_agree_bit_for_bit(dev, dtype):
         ("generic_gauss", lambda: M.unsharp_mask(x, 9, 1.0)),
         ("generic_clahe", lambda: M.equalize_clahe(x, 2.0, (4, 8))),
         ("clahe_float_rules", lambda: M.equalize_clahe(x, 2.0, (4, 8))),
-        ("clahe_two_pass", lambda: M.equalize_clahe(x, 2.0, (4, 8))),
-        ("clahe_two_pass", lambda: M.equalize_clahe(x, 40.0, (8, 16), out_dtype=torch.float32)),
         ("generic_equalize", lambda: M.equalize(x)),
         ("equalize_float_rules", lambda: M.equalize(x)),
         ("equalize_three_pass", lambda: M.equalize(x)),
