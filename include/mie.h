@@ -94,7 +94,8 @@ enum mie_kernel_policy {
     MIE_POLICY_CLAHE16_NO_CLUSTER = 256,   /* 65 536-bin CLAHE: one CTA per tile instead of a 2-CTA cluster */
     MIE_POLICY_CLAHE16_TWO_SWEEP = 512,    /* 65 536-bin CLAHE: the two-sweep kernel of tiles >= 65 536 pixels */
     MIE_POLICY_EQUALIZE_THREE_PASS = 1024, /* equalize: histogram / LUT / apply launches instead of the one-launch cluster kernel */
-    MIE_POLICY_ALL = 2047
+    MIE_POLICY_BILATERAL_EXACT_EXP = 2048, /* bilateral: the reproducible polynomial 2^t (bit-exact against the oracle) instead of MUFU.EX2 */
+    MIE_POLICY_ALL = 4095
 };
 int mie_set_kernel_policy(unsigned mask);
 unsigned mie_get_kernel_policy(void);

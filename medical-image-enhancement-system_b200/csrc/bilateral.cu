@@ -9,6 +9,8 @@
 // oracle/mie_oracle.c:mie_exp2n, so the result is reproducible bit for bit.  This op is FMA-pipe bound
 // (81 taps x 14 FMA-pipe operations), not HBM bound.
 
+#include <cmath>
+
 #include "chain_fast.cuh"
 #include "window.cuh"
 
@@ -141,7 +143,21 @@ struct SpaceW2 {   // spatial weights, row-major K x K
 // Stages the haloed tile and evaluates the window for the thread's four pixels (rows ly0 + 8 k, column lx):
 // num[k] / den[k] is the filter output.  Shared by the pixel-output kernel and the index-plane kernel of the fused
 // bilateral -> CLAHE chain.
-template <typename SrcT, int K>
+// APPROX (the default; MIE_POLICY_BILATERAL_EXACT_EXP selects the other one): the colour weight is ONE MUFU.EX2
+// (ex2.approx.ftz, max rel err 2^-22) of t = c2 d^2 + log2(ws) — `sw` then holds log2 of the spatial weights — so a
+// pixel-tap costs five FMA-pipe operations and one XU operation instead of fourteen FMA-pipe operations, and the XU pipe
+// (16 lanes per clock and SM) becomes the limiter: 5.93 -> 3.35 ms per 8 x 4096^2 (XU floor 2.35 ms).  Handing every
+// third / fourth / sixth tap to the polynomial to unload the XU pipe was measured slower (3.87 / 3.70 / 3.36 ms: the
+// kernel then runs out of issue slots).  The result is within rel 1e-6 of the exact-polynomial kernel — inside the north
+// star's 1e-5 for floating-point filters — but not reproducible bit for bit on a CPU: that is what the exact mode is
+// kept for.
+__device__ __forceinline__ float ex2_approx(float t) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
+    return y;
+}
+
+template <typename SrcT, int K, bool APPROX>
 __device__ __forceinline__ void bilateral_packed_core(const SrcT* __restrict__ plane, int64_t ssh, int h, int w, int tx0,
                                                       int ty0, float coef, int border, float lo, float rg,
                                                       const SpaceW2& sw, float* smem, float* num, float* den) {
@@ -169,8 +185,19 @@ __device__ __forceinline__ void bilateral_packed_core(const SrcT* __restrict__ p
             const f32x2 vA = f2_pack(p[0], p[8 * PITCH]);
             const f32x2 vB = f2_pack(p[16 * PITCH], p[24 * PITCH]);
             const f32x2 dA = f2_sub(vA, ctrA), dB = f2_sub(vB, ctrB);
-            const f32x2 wA = weight_x2(f2_mul(coef2, f2_mul(dA, dA)), ws, kc);
-            const f32x2 wB = weight_x2(f2_mul(coef2, f2_mul(dB, dB)), ws, kc);
+            f32x2 wA, wB;
+            if constexpr (APPROX) {
+                const f32x2 lws2 = f2_dup(ws);   // log2 of the spatial weight
+                const f32x2 tA = f2_fma(f2_mul(dA, coef2), dA, lws2), tB = f2_fma(f2_mul(dB, coef2), dB, lws2);
+                float a0, a1, b0, b1;
+                f2_unpack(tA, a0, a1);
+                f2_unpack(tB, b0, b1);
+                wA = f2_pack(ex2_approx(a0), ex2_approx(a1));
+                wB = f2_pack(ex2_approx(b0), ex2_approx(b1));
+            } else {
+                wA = weight_x2(f2_mul(coef2, f2_mul(dA, dA)), ws, kc);
+                wB = weight_x2(f2_mul(coef2, f2_mul(dB, dB)), ws, kc);
+            }
             numA = f2_fma(wA, vA, numA); denA = f2_add(denA, wA);
             numB = f2_fma(wB, vB, numB); denB = f2_add(denB, wB);
         }
@@ -179,7 +206,7 @@ __device__ __forceinline__ void bilateral_packed_core(const SrcT* __restrict__ p
     f2_unpack(denA, den[0], den[1]); f2_unpack(denB, den[2], den[3]);
 }
 
-template <typename SrcT, typename DstT, int K>
+template <typename SrcT, typename DstT, int K, bool APPROX>
 __global__ void __launch_bounds__(256)
 bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
                         int64_t dsh, int h, int w, int tiles_x, int tiles_y, float coef, int border, float lo,
@@ -190,7 +217,7 @@ bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, in
     const int tx0 = (int)(tile % tiles_x) * T, ty0 = (int)((tile / tiles_x) % tiles_y) * T;
     const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
     float num[4], den[4];
-    bilateral_packed_core<SrcT, K>(src + n * ssn, ssh, h, w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
+    bilateral_packed_core<SrcT, K, APPROX>(src + n * ssn, ssh, h, w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
     const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
     const int x = tx0 + lx;
 #pragma unroll
@@ -205,7 +232,7 @@ bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, in
 // its CLAHE lookup index trunc(clamp(b * 255)) (one byte per pixel) is written, while its histogram bin floor(b * 256)
 // goes into a block histogram that is flushed with one global atomic per occupied bin.  Requires 32-pixel-aligned CLAHE
 // tiles without padding (checked on the host), so that a block's 32 x 32 pixels lie in ONE tile.
-template <typename SrcT, int K>
+template <typename SrcT, int K, bool APPROX>
 __global__ void __launch_bounds__(256)
 bilateral_index_kernel(const SrcT* __restrict__ src, uint8_t* __restrict__ idx, uint32_t* __restrict__ hist, int64_t ssn,
                        int64_t ssh, ClaheGeom g, int tiles_x, int tiles_y, float coef, int border, float lo, float rg,
@@ -218,7 +245,7 @@ bilateral_index_kernel(const SrcT* __restrict__ src, uint8_t* __restrict__ idx, 
     const int tx0 = (int)(tile % tiles_x) * T, ty0 = (int)((tile / tiles_x) % tiles_y) * T;
     const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
     float num[4], den[4];
-    bilateral_packed_core<SrcT, K>(src + n * ssn, ssh, g.h, g.w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
+    bilateral_packed_core<SrcT, K, APPROX>(src + n * ssn, ssh, g.h, g.w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
     const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
     uint8_t* ip = idx + n * (int64_t)g.h * g.w + (int64_t)(ty0 + ly0) * g.w + tx0 + lx;
 #pragma unroll
@@ -248,17 +275,37 @@ hist_to_lut_kernel(const uint32_t* __restrict__ hist, uint8_t* __restrict__ luts
     warp_build_lut<false>(s_tot[warp], lp, luts + t * kBins, lane);
 }
 
+// The approximate-exponential kernels need log2 of every spatial weight: all of them must be positive and normal.
+static bool bilateral_approx_ok(const float* wspace, int k) {
+    if (kernel_policy(MIE_POLICY_BILATERAL_EXACT_EXP)) return false;
+    for (int i = 0; i < k * k; ++i)
+        if (!(wspace[i] >= 1.1754944e-38f) || !(wspace[i] < 3.0e38f)) return false;
+    return true;
+}
+static void fill_space_weights(SpaceW2& sw, const float* wspace, int k, bool approx) {
+    for (int i = 0; i < 81; ++i) {
+        if (i >= k * k) sw.w[i] = 0.f;
+        else sw.w[i] = approx ? (float)std::log2((double)wspace[i]) : wspace[i];
+    }
+}
+
 template <typename SrcT, typename DstT>
 static int launch_bilateral_packed(int k, const void* src, void* dst, int64_t ssn, int64_t ssh, int64_t dsn,
                                    int64_t dsh, int h, int w, int tiles_x, int tiles_y, unsigned blocks, float coef,
                                    int border, float lo, float rg, const float* wspace, cudaStream_t st) {
+    const bool approx = bilateral_approx_ok(wspace, k);
     SpaceW2 sw;
-    for (int i = 0; i < 81; ++i) sw.w[i] = i < k * k ? wspace[i] : 0.f;
+    fill_space_weights(sw, wspace, k, approx);
 #define MIE_BIL(K_)                                                                                          \
     case K_:                                                                                                 \
-        bilateral_packed_kernel<SrcT, DstT, K_><<<blocks, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, dsn, \
-                                                                        dsh, h, w, tiles_x, tiles_y, coef, border,  \
-                                                                        lo, rg, sw);                             \
+        if (approx)                                                                                          \
+            bilateral_packed_kernel<SrcT, DstT, K_, true><<<blocks, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, \
+                                                                                  dsn, dsh, h, w, tiles_x, tiles_y, coef, \
+                                                                                  border, lo, rg, sw);       \
+        else                                                                                                 \
+            bilateral_packed_kernel<SrcT, DstT, K_, false><<<blocks, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, \
+                                                                                   dsn, dsh, h, w, tiles_x, tiles_y, coef, \
+                                                                                   border, lo, rg, sw);      \
         break;
     switch (k) {
         MIE_BIL(3) MIE_BIL(5) MIE_BIL(7) MIE_BIL(9)
@@ -374,11 +421,23 @@ int mie_bilateral_clahe(const void* src, void* dst, int src_dtype, int dst_dtype
     if (stages & 1) {   // bilateral -> index plane + tile histograms
         cudaError_t e = cudaMemsetAsync(hist, 0, (size_t)tiles * kBins * sizeof(uint32_t), st);
         if (e != cudaSuccess) return (int)e;
+        const bool approx = bilateral_approx_ok(wspace, k);
         SpaceW2 sw;
-        for (int i = 0; i < 81; ++i) sw.w[i] = i < k * k ? wspace[i] : 0.f;
+        fill_space_weights(sw, wspace, k, approx);
         const float coef = (float)(-0.5 * 1.4426950408889634 / ((double)sigma_color * (double)sigma_color));
         const float rg = hi - lo;
-#define MIE_BIDX(K_)                                                                                                      case K_:                                                                                                                  MIE_DISPATCH_SRC(src_dtype, (bilateral_index_kernel<SrcT, K_><<<(unsigned)blocks, 256, 0, st>>>(                                                      (const SrcT*)src, idx, hist, src_stride_n, src_stride_h, g, tiles_x, tiles_y,                                         coef, border, lo, rg, sw)));                                                          break;
+#define MIE_BIDX(K_)                                                                                                   \
+    case K_:                                                                                                           \
+        if (approx) {                                                                                                  \
+            MIE_DISPATCH_SRC(src_dtype, (bilateral_index_kernel<SrcT, K_, true><<<(unsigned)blocks, 256, 0, st>>>(     \
+                                            (const SrcT*)src, idx, hist, src_stride_n, src_stride_h, g, tiles_x, tiles_y, \
+                                            coef, border, lo, rg, sw)));                                                \
+        } else {                                                                                                       \
+            MIE_DISPATCH_SRC(src_dtype, (bilateral_index_kernel<SrcT, K_, false><<<(unsigned)blocks, 256, 0, st>>>(    \
+                                            (const SrcT*)src, idx, hist, src_stride_n, src_stride_h, g, tiles_x, tiles_y, \
+                                            coef, border, lo, rg, sw)));                                                \
+        }                                                                                                              \
+        break;
         switch (k) {
             MIE_BIDX(3) MIE_BIDX(5) MIE_BIDX(7) MIE_BIDX(9)
             default: return MIE_E_KERNEL;

@@ -1,5 +1,6 @@
 """Fused bilateral -> CLAHE chain (BASELINE.json config 4; include/mie.h mie_bilateral_clahe): bit-exact against the
-oracle composition from01(equalize_clahe(bilateral_blur(to01(x)))) and against the unfused CUDA operators."""
+oracle composition from01(equalize_clahe(bilateral_blur(to01(x)))) and against the unfused CUDA operators in the
+reproducible mode (kernel policy bilateral_exact_exp); statistically close in the default MUFU.EX2 mode."""
 import numpy as np
 import pytest
 import torch
@@ -38,13 +39,22 @@ def test_fused_bilateral_clahe_matches_oracle(dev, case, dtype):
         ref01 = O.equalize_clahe(b, clip, grid)
         ref = O.from01(ref01, dtype)
         xt = torch.from_numpy(x).to(dev)
-        got = M.bilateral_clahe(xt, k, 0.1, (1.5, 1.5), clip, grid, border).cpu().numpy()
-        assert np.array_equal(got, ref), (kind, int((got != ref).sum()))
-        gf = M.bilateral_clahe(xt, k, 0.1, (1.5, 1.5), clip, grid, border, out_dtype=torch.float32).cpu().numpy()
-        assert np.array_equal(gf, ref01)
-        # and the unfused CUDA operators give the same float image
-        u = M.equalize_clahe(M.bilateral_blur(xt, k, 0.1, (1.5, 1.5), border, out_dtype=torch.float32), clip, grid)
-        assert np.array_equal(u.cpu().numpy(), ref01)
+        with M.kernel_policy("bilateral_exact_exp"):   # reproducible colour weights: every stage bit for bit
+            got = M.bilateral_clahe(xt, k, 0.1, (1.5, 1.5), clip, grid, border).cpu().numpy()
+            assert np.array_equal(got, ref), (kind, int((got != ref).sum()))
+            gf = M.bilateral_clahe(xt, k, 0.1, (1.5, 1.5), clip, grid, border, out_dtype=torch.float32).cpu().numpy()
+            assert np.array_equal(gf, ref01)
+            # and the unfused CUDA operators give the same float image
+            u = M.equalize_clahe(M.bilateral_blur(xt, k, 0.1, (1.5, 1.5), border, out_dtype=torch.float32), clip, grid)
+            assert np.array_equal(u.cpu().numpy(), ref01)
+        # default colour weights (MUFU.EX2, rel 6e-7): CLAHE is discontinuous — a blurred value that crosses a bin or
+        # lookup boundary moves a pixel by whole LUT steps — so the statement is statistical:
+        # very few pixels differ, and the mean deviation is a small fraction of one LUT step
+        fast = M.bilateral_clahe(xt, k, 0.1, (1.5, 1.5), clip, grid, border, out_dtype=torch.float32).cpu().numpy()
+        d = np.abs(fast.astype(np.float64) - ref01.astype(np.float64)) * 255.0     # in LUT steps
+        assert (d > 1e-3).mean() <= 5e-3 and d.mean() <= 5e-3, (kind, float((d > 1e-3).mean()), float(d.mean()))
+        fq = M.bilateral_clahe(xt, k, 0.1, (1.5, 1.5), clip, grid, border).cpu().numpy()
+        assert (fq != ref).mean() <= 5e-3
 
 
 def test_fused_path_refuses_what_it_does_not_cover(dev):

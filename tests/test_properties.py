@@ -104,7 +104,10 @@ def test_config4_full_image_properties(dev):
 
     x = synthetic.phantom((2, 1, 4096, 4096), np.uint16, seed=0)
     xt = torch.from_numpy(x).to(dev)
-    b = M.bilateral_blur(xt, 9, 0.1, (1.5, 1.5), out_dtype=torch.float32)
+    bfast = M.bilateral_blur(xt, 9, 0.1, (1.5, 1.5), out_dtype=torch.float32)       # default: MUFU.EX2 colour weights
+    with M.kernel_policy("bilateral_exact_exp"):                                     # reproducible: the oracle's bits
+        b = M.bilateral_blur(xt, 9, 0.1, (1.5, 1.5), out_dtype=torch.float32)
+    assert float(((bfast - b).abs() / b.abs().clamp_min(1e-3)).max()) <= 1e-5
     x01 = O.to01(x)
     for (i, y0, x0) in [(0, 0, 0), (1, 2000, 1900), (0, 3896, 3896), (1, 0, 3900)]:
         ya, yb, xa, xb = max(y0 - 4, 0), min(y0 + 200 + 4, 4096), max(x0 - 4, 0), min(x0 + 200 + 4, 4096)
