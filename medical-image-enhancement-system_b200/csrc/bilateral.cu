@@ -143,21 +143,7 @@ struct SpaceW2 {   // spatial weights, row-major K x K
 // Stages the haloed tile and evaluates the window for the thread's four pixels (rows ly0 + 8 k, column lx):
 // num[k] / den[k] is the filter output.  Shared by the pixel-output kernel and the index-plane kernel of the fused
 // bilateral -> CLAHE chain.
-// APPROX (the default; MIE_POLICY_BILATERAL_EXACT_EXP selects the other one): the colour weight is ONE MUFU.EX2
-// (ex2.approx.ftz, max rel err 2^-22) of t = c2 d^2 + log2(ws) — `sw` then holds log2 of the spatial weights — so a
-// pixel-tap costs five FMA-pipe operations and one XU operation instead of fourteen FMA-pipe operations, and the XU pipe
-// (16 lanes per clock and SM) becomes the limiter: 5.93 -> 3.35 ms per 8 x 4096^2 (XU floor 2.35 ms).  Handing every
-// third / fourth / sixth tap to the polynomial to unload the XU pipe was measured slower (3.87 / 3.70 / 3.36 ms: the
-// kernel then runs out of issue slots).  The result is within rel 1e-6 of the exact-polynomial kernel — inside the north
-// star's 1e-5 for floating-point filters — but not reproducible bit for bit on a CPU: that is what the exact mode is
-// kept for.
-__device__ __forceinline__ float ex2_approx(float t) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
-    return y;
-}
-
-template <typename SrcT, int K, bool APPROX>
+template <typename SrcT, int K>
 __device__ __forceinline__ void bilateral_packed_core(const SrcT* __restrict__ plane, int64_t ssh, int h, int w, int tx0,
                                                       int ty0, float coef, int border, float lo, float rg,
                                                       const SpaceW2& sw, float* smem, float* num, float* den) {
@@ -185,19 +171,8 @@ __device__ __forceinline__ void bilateral_packed_core(const SrcT* __restrict__ p
             const f32x2 vA = f2_pack(p[0], p[8 * PITCH]);
             const f32x2 vB = f2_pack(p[16 * PITCH], p[24 * PITCH]);
             const f32x2 dA = f2_sub(vA, ctrA), dB = f2_sub(vB, ctrB);
-            f32x2 wA, wB;
-            if constexpr (APPROX) {
-                const f32x2 lws2 = f2_dup(ws);   // log2 of the spatial weight
-                const f32x2 tA = f2_fma(f2_mul(dA, coef2), dA, lws2), tB = f2_fma(f2_mul(dB, coef2), dB, lws2);
-                float a0, a1, b0, b1;
-                f2_unpack(tA, a0, a1);
-                f2_unpack(tB, b0, b1);
-                wA = f2_pack(ex2_approx(a0), ex2_approx(a1));
-                wB = f2_pack(ex2_approx(b0), ex2_approx(b1));
-            } else {
-                wA = weight_x2(f2_mul(coef2, f2_mul(dA, dA)), ws, kc);
-                wB = weight_x2(f2_mul(coef2, f2_mul(dB, dB)), ws, kc);
-            }
+            const f32x2 wA = weight_x2(f2_mul(coef2, f2_mul(dA, dA)), ws, kc);
+            const f32x2 wB = weight_x2(f2_mul(coef2, f2_mul(dB, dB)), ws, kc);
             numA = f2_fma(wA, vA, numA); denA = f2_add(denA, wA);
             numB = f2_fma(wB, vB, numB); denB = f2_add(denB, wB);
         }
@@ -206,7 +181,7 @@ __device__ __forceinline__ void bilateral_packed_core(const SrcT* __restrict__ p
     f2_unpack(denA, den[0], den[1]); f2_unpack(denB, den[2], den[3]);
 }
 
-template <typename SrcT, typename DstT, int K, bool APPROX>
+template <typename SrcT, typename DstT, int K>
 __global__ void __launch_bounds__(256)
 bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
                         int64_t dsh, int h, int w, int tiles_x, int tiles_y, float coef, int border, float lo,
@@ -217,7 +192,7 @@ bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, in
     const int tx0 = (int)(tile % tiles_x) * T, ty0 = (int)((tile / tiles_x) % tiles_y) * T;
     const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
     float num[4], den[4];
-    bilateral_packed_core<SrcT, K, APPROX>(src + n * ssn, ssh, h, w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
+    bilateral_packed_core<SrcT, K>(src + n * ssn, ssh, h, w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
     const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
     const int x = tx0 + lx;
 #pragma unroll
@@ -232,7 +207,7 @@ bilateral_packed_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, in
 // its CLAHE lookup index trunc(clamp(b * 255)) (one byte per pixel) is written, while its histogram bin floor(b * 256)
 // goes into a block histogram that is flushed with one global atomic per occupied bin.  Requires 32-pixel-aligned CLAHE
 // tiles without padding (checked on the host), so that a block's 32 x 32 pixels lie in ONE tile.
-template <typename SrcT, int K, bool APPROX>
+template <typename SrcT, int K>
 __global__ void __launch_bounds__(256)
 bilateral_index_kernel(const SrcT* __restrict__ src, uint8_t* __restrict__ idx, uint32_t* __restrict__ hist, int64_t ssn,
                        int64_t ssh, ClaheGeom g, int tiles_x, int tiles_y, float coef, int border, float lo, float rg,
@@ -245,7 +220,7 @@ bilateral_index_kernel(const SrcT* __restrict__ src, uint8_t* __restrict__ idx, 
     const int tx0 = (int)(tile % tiles_x) * T, ty0 = (int)((tile / tiles_x) % tiles_y) * T;
     const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
     float num[4], den[4];
-    bilateral_packed_core<SrcT, K, APPROX>(src + n * ssn, ssh, g.h, g.w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
+    bilateral_packed_core<SrcT, K>(src + n * ssn, ssh, g.h, g.w, tx0, ty0, coef, border, lo, rg, sw, smem, num, den);
     const int lx = threadIdx.x & 31, ly0 = threadIdx.x >> 5;
     uint8_t* ip = idx + n * (int64_t)g.h * g.w + (int64_t)(ty0 + ly0) * g.w + tx0 + lx;
 #pragma unroll
@@ -254,6 +229,135 @@ bilateral_index_kernel(const SrcT* __restrict__ src, uint8_t* __restrict__ idx, 
         ip[(int64_t)8 * k * g.w] = (uint8_t)(fast_idx_bits<false>(b) & 0xFFu);
         hist_add_nobranch(s_hist, fast_bin<false>(b));    // slot 256 swallows what torch.histc would ignore
     }
+    __syncthreads();
+    uint32_t* gh_ = hist + ((n * g.gh + ty0 / g.th) * (int64_t)g.gw + tx0 / g.tw) * kBins;
+    const int v = s_hist[threadIdx.x];
+    if (v) atomicAdd(gh_ + threadIdx.x, (uint32_t)v);
+}
+
+// ---------------------------------------------------------------- default mode: MUFU.EX2 colour weights
+// (MIE_POLICY_BILATERAL_EXACT_EXP selects the reproducible kernels above.)  The colour weight is ONE MUFU.EX2
+// (ex2.approx.ftz, max rel err 2^-22) of t = c2 d^2 + log2(ws) — `sw` holds log2 of the spatial weights — so a pixel-tap
+// costs five FMA-pipe operations and one XU operation instead of fourteen FMA-pipe operations, and the XU pipe (16
+// lanes per clock and SM) becomes the limiter.  The result is within rel 1e-6 of the exact-polynomial kernel — inside
+// the north star's 1e-5 for floating-point filters — but not reproducible bit for bit on a CPU: that is what the exact
+// mode is kept for.
+//
+// With the arithmetic that cheap the loads matter, so the tile is laid out for them: P[r][c] = (v(r, c), v(r + 1, c)) as
+// one 64-bit word for EVERY r (each value is stored twice), and a thread owns a 2 x 2 block of pixels — two vertical
+// pairs.  For a window row dy the ten words P[2 ty + dy][2 tx .. 2 tx + 9] are five conflict-free 16-byte loads and
+// already ARE the packed (row, row + 1) operands of all nine taps of both columns: 0.14 loads per pixel-tap instead
+// of 1, no register shuffling.  Per 8 x 4096^2 images: exact kernel 5.93 ms, MUFU on the exact kernel's row-strided
+// layout 3.27 ms, this kernel 2.90 ms (XU floor: 2.35 ms).  Handing every fourth / fifth / sixth / eighth tap to the
+// polynomial to unload the XU pipe was measured and does not pay (3.18 / 3.05 / 2.98 / 2.90 ms).
+__device__ __forceinline__ float ex2_approx(float t) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(t));
+    return y;
+}
+
+template <int K>
+struct LeanGeom {
+    static constexpr int T = 32, R = K / 2, EW = (T + 2 * R + 2) & ~1, EH = T + 2 * R;   // even pitch: 16-byte rows
+    static constexpr int WORDS = (EH - 1) * EW;                                         // 64-bit words
+};
+
+// num[k] / den[k] for the thread's pixels (2 ty + (k & 1), 2 tx + (k >> 1)) of the 32 x 32 tile.
+template <typename SrcT, int K>
+__device__ __forceinline__ void bilateral_lean_core(const SrcT* __restrict__ plane, int64_t ssh, int h, int w, int tx0,
+                                                    int ty0, float coef, int border, float lo, float rg,
+                                                    const SpaceW2& lsw, float2* P, float* num, float* den) {
+    using G = LeanGeom<K>;
+    constexpr int R = G::R, EW = G::EW, EH = G::EH, CW = G::T + 2 * R;
+    for (int i = threadIdx.x; i < EH * CW; i += 256) {
+        const int r = i / CW, c = i - r * CW;
+        const int sy = border_index(ty0 - R + r, h, border), sx = border_index(tx0 - R + c, w, border);
+        const float v = (sy < 0 || sx < 0) ? 0.0f : Px<SrcT>::to01(plane[(int64_t)sy * ssh + sx], lo, rg);
+        if (r < EH - 1) P[r * EW + c].x = v;
+        if (r > 0) P[(r - 1) * EW + c].y = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const float2* base = P + (2 * ty) * EW + 2 * tx;
+    const f32x2 coef2 = f2_dup(coef);
+    const ulonglong2 cw = *reinterpret_cast<const ulonglong2*>(base + R * EW + (R & ~1));
+    const f32x2 ctrA = (R & 1) ? cw.y : cw.x;
+    f32x2 ctrB;
+    if (R & 1) ctrB = *reinterpret_cast<const unsigned long long*>(base + R * EW + R + 1);
+    else ctrB = cw.y;
+    f32x2 numA = f2_dup(0.0f), denA = numA, numB = numA, denB = numA;
+#pragma unroll
+    for (int dy = 0; dy < K; ++dy) {
+        f32x2 win[K + 1];
+#pragma unroll
+        for (int q = 0; q < (K + 1) / 2; ++q) {
+            const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(base + dy * EW + 2 * q);
+            win[2 * q] = v.x; win[2 * q + 1] = v.y;
+        }
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+            const f32x2 lws2 = f2_dup(lsw.w[dy * K + dx]);
+            const f32x2 vA = win[dx], vB = win[dx + 1];
+            const f32x2 dA = f2_sub(vA, ctrA), dB = f2_sub(vB, ctrB);
+            const f32x2 tA = f2_fma(f2_mul(dA, coef2), dA, lws2), tB = f2_fma(f2_mul(dB, coef2), dB, lws2);
+            float a0, a1, b0, b1;
+            f2_unpack(tA, a0, a1);
+            f2_unpack(tB, b0, b1);
+            const f32x2 wA = f2_pack(ex2_approx(a0), ex2_approx(a1));
+            const f32x2 wB = f2_pack(ex2_approx(b0), ex2_approx(b1));
+            numA = f2_fma(wA, vA, numA); denA = f2_add(denA, wA);
+            numB = f2_fma(wB, vB, numB); denB = f2_add(denB, wB);
+        }
+    }
+    f2_unpack(numA, num[0], num[1]); f2_unpack(numB, num[2], num[3]);
+    f2_unpack(denA, den[0], den[1]); f2_unpack(denB, den[2], den[3]);
+}
+
+template <typename SrcT, typename DstT, int K>
+__global__ void __launch_bounds__(256)
+bilateral_lean_kernel(const SrcT* __restrict__ src, DstT* __restrict__ dst, int64_t ssn, int64_t ssh, int64_t dsn,
+                      int64_t dsh, int h, int w, int tiles_x, int tiles_y, float coef, int border, float lo, float rg,
+                      SpaceW2 lsw) {
+    __shared__ __align__(16) float2 P[LeanGeom<K>::WORDS];
+    const int64_t tile = blockIdx.x;
+    const int tx0 = (int)(tile % tiles_x) * 32, ty0 = (int)((tile / tiles_x) % tiles_y) * 32;
+    const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
+    float num[4], den[4];
+    bilateral_lean_core<SrcT, K>(src + n * ssn, ssh, h, w, tx0, ty0, coef, border, lo, rg, lsw, P, num, den);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int y = ty0 + 2 * ty + (k & 1), x = tx0 + 2 * tx + (k >> 1);
+        if (y < h && x < w)
+            dst[n * dsn + (int64_t)y * dsh + x] = Px<DstT>::from01(__fdiv_rn(num[k], den[k]), lo, rg);
+    }
+}
+
+template <typename SrcT, int K>
+__global__ void __launch_bounds__(256)
+bilateral_lean_index_kernel(const SrcT* __restrict__ src, uint8_t* __restrict__ idx, uint32_t* __restrict__ hist,
+                            int64_t ssn, int64_t ssh, ClaheGeom g, int tiles_x, int tiles_y, float coef, int border,
+                            float lo, float rg, SpaceW2 lsw) {
+    __shared__ __align__(16) float2 P[LeanGeom<K>::WORDS];
+    __shared__ int s_hist[kBins + 8];
+    for (int i = threadIdx.x; i < kBins + 8; i += 256) s_hist[i] = 0;
+    const int64_t tile = blockIdx.x;
+    const int tx0 = (int)(tile % tiles_x) * 32, ty0 = (int)((tile / tiles_x) % tiles_y) * 32;
+    const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
+    float num[4], den[4];
+    bilateral_lean_core<SrcT, K>(src + n * ssn, ssh, g.h, g.w, tx0, ty0, coef, border, lo, rg, lsw, P, num, den);
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    uint8_t* ip = idx + n * (int64_t)g.h * g.w + (int64_t)(ty0 + 2 * ty) * g.w + tx0 + 2 * tx;
+    uint32_t b4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float b = __fdiv_rn(num[k], den[k]);
+        b4[k] = fast_idx_bits<false>(b) & 0xFFu;
+        hist_add_nobranch(s_hist, fast_bin<false>(b));    // slot 256 swallows what torch.histc would ignore
+    }
+    // rows 2 ty and 2 ty + 1, two neighbouring columns each: one 16-bit store per row (tx0 and g.w are even)
+    *reinterpret_cast<uint16_t*>(ip) = (uint16_t)(b4[0] | (b4[2] << 8));
+    *reinterpret_cast<uint16_t*>(ip + g.w) = (uint16_t)(b4[1] | (b4[3] << 8));
     __syncthreads();
     uint32_t* gh_ = hist + ((n * g.gh + ty0 / g.th) * (int64_t)g.gw + tx0 / g.tw) * kBins;
     const int v = s_hist[threadIdx.x];
@@ -299,13 +403,13 @@ static int launch_bilateral_packed(int k, const void* src, void* dst, int64_t ss
 #define MIE_BIL(K_)                                                                                          \
     case K_:                                                                                                 \
         if (approx)                                                                                          \
-            bilateral_packed_kernel<SrcT, DstT, K_, true><<<blocks, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, \
-                                                                                  dsn, dsh, h, w, tiles_x, tiles_y, coef, \
-                                                                                  border, lo, rg, sw);       \
+            bilateral_lean_kernel<SrcT, DstT, K_><<<blocks, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, dsn, \
+                                                                          dsh, h, w, tiles_x, tiles_y, coef, border,   \
+                                                                          lo, rg, sw);                       \
         else                                                                                                 \
-            bilateral_packed_kernel<SrcT, DstT, K_, false><<<blocks, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, \
-                                                                                   dsn, dsh, h, w, tiles_x, tiles_y, coef, \
-                                                                                   border, lo, rg, sw);      \
+            bilateral_packed_kernel<SrcT, DstT, K_><<<blocks, 256, 0, st>>>((const SrcT*)src, (DstT*)dst, ssn, ssh, dsn, \
+                                                                            dsh, h, w, tiles_x, tiles_y, coef, border, \
+                                                                            lo, rg, sw);                     \
         break;
     switch (k) {
         MIE_BIL(3) MIE_BIL(5) MIE_BIL(7) MIE_BIL(9)
@@ -429,11 +533,11 @@ int mie_bilateral_clahe(const void* src, void* dst, int src_dtype, int dst_dtype
 #define MIE_BIDX(K_)                                                                                                   \
     case K_:                                                                                                           \
         if (approx) {                                                                                                  \
-            MIE_DISPATCH_SRC(src_dtype, (bilateral_index_kernel<SrcT, K_, true><<<(unsigned)blocks, 256, 0, st>>>(     \
+            MIE_DISPATCH_SRC(src_dtype, (bilateral_lean_index_kernel<SrcT, K_><<<(unsigned)blocks, 256, 0, st>>>(     \
                                             (const SrcT*)src, idx, hist, src_stride_n, src_stride_h, g, tiles_x, tiles_y, \
                                             coef, border, lo, rg, sw)));                                                \
         } else {                                                                                                       \
-            MIE_DISPATCH_SRC(src_dtype, (bilateral_index_kernel<SrcT, K_, false><<<(unsigned)blocks, 256, 0, st>>>(    \
+            MIE_DISPATCH_SRC(src_dtype, (bilateral_index_kernel<SrcT, K_><<<(unsigned)blocks, 256, 0, st>>>(    \
                                             (const SrcT*)src, idx, hist, src_stride_n, src_stride_h, g, tiles_x, tiles_y, \
                                             coef, border, lo, rg, sw)));                                                \
         }                                                                                                              \
