@@ -289,6 +289,13 @@ int launch_clahe_apply_fast(const void* src, void* dst, int sd, int dd, int64_t 
     int rows = g.th / 2;                        // rows of a block stay inside one cell row
     for (int d = 32; d >= 1; --d)
         if ((g.th / 2) % d == 0) { rows = d; break; }
+    if (in_kernel_cells) {
+        // latency path (a single slice): 32 rows per block would leave 16 blocks walking 32 rows each on a 148-SM
+        // machine; take the largest divisor that still gives ~120 blocks (below 4 rows the in-kernel table packing,
+        // 18 entries per thread, outweighs the pixels)
+        for (int d = rows; d >= 4; --d)
+            if ((g.th / 2) % d == 0) { rows = d; if (n * (int64_t)(g.h / d) >= 120) break; }
+    }
     a.rows_per_block = rows;
     a.blocks_per_image = g.h / rows;
     const int64_t blocks = n * a.blocks_per_image;
