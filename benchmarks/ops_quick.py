@@ -24,6 +24,7 @@ OPS = {
     "equalize": (lambda: M.equalize(x), "generic_equalize"),
     "median3": (lambda: M.median_blur(x, 3), "generic_median"),
     "median5": (lambda: M.median_blur(x, 5), "generic_median"),
+    "clahe16": (lambda: M.equalize_clahe(x, 2.0, (8, 8), semantics="opencv"), "clahe16_full_luts"),
 }
 
 

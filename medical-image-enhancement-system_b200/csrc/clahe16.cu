@@ -288,9 +288,14 @@ __device__ __forceinline__ int block_excl_scan_nw(int v, int* s_red, int* total)
     return warp_off + incl - v;
 }
 
+// `vmax` (optional): device word holding an upper bound of every pixel value of the batch (clahe16_max_kernel).  LUT
+// entries above it are never looked up, so threads whose 64 bins lie above it skip their sweeps and their 128-byte LUT
+// stores, and only the live part of the counters is zeroed: 12-bit data in a 16-bit container — the usual CT / MR
+// case — costs 1/16 of the sweeps and of the LUT traffic, and the interpolation pass then gathers from 8 KB per tile
+// instead of 128 KB.  The entries that ARE written are the same as without the bound (prefix sums only look down).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClThreads)
 clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, Lut16Params lp,
-                           uint16_t* __restrict__ luts) {
+                           uint16_t* __restrict__ luts, const uint32_t* __restrict__ vmax) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(16) int s_h[];   // 16384 + 512 words: this CTA's half of the grey range
@@ -303,20 +308,25 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
     const uint16_t* plane = src + n * ssn;
     const int tid = threadIdx.x;
     uint32_t* s_w = reinterpret_cast<uint32_t*>(s_h);
-    for (int i = tid; i < kHalf16 / 2 + kHalf16 / 64; i += kClThreads) s_w[i] = 0u;
+    // highest live bin of this half (local index; negative: the whole half lies above the bound)
+    const int lmax = min((int)(vmax ? min(__ldg(vmax), 65535u) : 65535u) - (int)rank * kHalf16, kHalf16 - 1);
+    const int live_threads = lmax < 0 ? 0 : lmax / 64 + 1;          // thread t owns local bins 64 t .. 64 t + 63
+    const bool live = tid < live_threads;
+    for (int i = tid; i < live_threads * 33; i += kClThreads) s_w[i] = 0u;
     __syncthreads();
     const int area = g.th * g.tw;
     const bool inside = (ty + 1) * g.th <= g.h && (tx + 1) * g.tw <= g.w;   // block-uniform: no reflect padding
-    for (int i = tid; i < area; i += kClThreads) {
-        const int yy = i / g.tw, xx = i - yy * g.tw;
-        int sy = ty * g.th + yy, sx = tx * g.tw + xx;
-        if (!inside) {
-            sy = border_index(sy, g.h, MIE_BORDER_REFLECT);
-            sx = border_index(sx, g.w, MIE_BORDER_REFLECT);
+    if (live_threads)
+        for (int i = tid; i < area; i += kClThreads) {
+            const int yy = i / g.tw, xx = i - yy * g.tw;
+            int sy = ty * g.th + yy, sx = tx * g.tw + xx;
+            if (!inside) {
+                sy = border_index(sy, g.h, MIE_BORDER_REFLECT);
+                sx = border_index(sx, g.w, MIE_BORDER_REFLECT);
+            }
+            const uint32_t v = plane[(int64_t)sy * ssh + sx];
+            if ((v >> 15) == rank) atomicAdd(&s_w[padw((int)((v & 0x7FFFu) >> 1))], (v & 1u) ? 0x10000u : 1u);
         }
-        const uint32_t v = plane[(int64_t)sy * ssh + sx];
-        if ((v >> 15) == rank) atomicAdd(&s_w[padw((int)((v & 0x7FFFu) >> 1))], (v & 1u) ? 0x10000u : 1u);
-    }
     __syncthreads();
 
     const uint32_t* mine = s_w + tid * 33;       // words 32 tid .. 32 tid + 31 of this half
@@ -324,11 +334,13 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
     int rb = 0, res = 0, step = 1;
     if (lp.clip > 0) {
         int local = 0;
+        if (live) {
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const uint32_t wv = mine[k];
-            const uint32_t c0 = wv & 0xFFFFu, c1 = wv >> 16;
-            local += (int)(c0 > clip ? c0 - clip : 0u) + (int)(c1 > clip ? c1 - clip : 0u);
+            for (int k = 0; k < 32; ++k) {
+                const uint32_t wv = mine[k];
+                const uint32_t c0 = wv & 0xFFFFu, c1 = wv >> 16;
+                local += (int)(c0 > clip ? c0 - clip : 0u) + (int)(c1 > clip ? c1 - clip : 0u);
+            }
         }
         const int mine_clipped = block_sum_nw<kClThreads / 32>(local, s_red);
         if (tid == 0) s_xchg[0] = mine_clipped;
@@ -351,14 +363,16 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
         return (int)c;
     };
     int sum = 0;
+    if (live) {
 #pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-        const uint32_t wv = mine[k];
-        sum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
-        sum += bin_value(wv >> 16, u0 + 2 * k + 1);
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t wv = mine[k];
+            sum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
+            sum += bin_value(wv >> 16, u0 + 2 * k + 1);
+        }
     }
     int total;
-    int cum = block_excl_scan_nw<kClThreads / 32>(sum, s_red, &total);
+    int cum = block_excl_scan_nw<kClThreads / 32>(sum, s_red, &total);   // dead threads add 0: prefixes only look down
     if (tid == 0) s_xchg[1] = total;
     cluster.sync();
     if (rank == 1) cum += *cluster.map_shared_rank(&s_xchg[1], 0u);   // the upper half continues the lower half's prefix
@@ -370,21 +384,43 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
         return min(r, 65535u);
     };
     uint4* dst = reinterpret_cast<uint4*>(luts + tile * (int64_t)kBins16 + u0);
+    if (live) {
 #pragma unroll 2
-    for (int k4 = 0; k4 < 8; ++k4) {
-        uint32_t packed[4];
+        for (int k4 = 0; k4 < 8; ++k4) {
+            uint32_t packed[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = 4 * k4 + j;
-            const uint32_t wv = mine[k];
-            cum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
-            const uint32_t e0 = lut_entry(cum);
-            cum += bin_value(wv >> 16, u0 + 2 * k + 1);
-            packed[j] = e0 | (lut_entry(cum) << 16);
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * k4 + j;
+                const uint32_t wv = mine[k];
+                cum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
+                const uint32_t e0 = lut_entry(cum);
+                cum += bin_value(wv >> 16, u0 + 2 * k + 1);
+                packed[j] = e0 | (lut_entry(cum) << 16);
+            }
+            dst[k4] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
-        dst[k4] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
     cluster.sync();   // the peer may still be reading this CTA's s_xchg
+}
+
+// Upper bound of the pixel values of a batch: one atomicMax per block into *vmax (zeroed by the caller).
+__global__ void __launch_bounds__(256)
+clahe16_max_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_t ssh, int64_t n, int h, int w, uint32_t* __restrict__ vmax) {
+    const int64_t rows = n * h;
+    uint32_t m = 0u;
+    for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+        const uint16_t* row = src + (r / h) * ssn + (r % h) * ssh;
+        for (int x = threadIdx.x & 31; x < w; x += 32) m = max(m, (uint32_t)row[x]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ uint32_t s_m[8];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = max(m, s_m[i]);
+        if (m) atomicMax(vmax, m);
+    }
 }
 
 // Interpolation pass (cv::CLAHE_Interpolation_Body, fp32 in OpenCV's operation order): 4 pixels per thread.
@@ -434,7 +470,7 @@ static Lut16Params make_lut16_params(const ClaheGeom& g, double clip_limit) {
 }
 
 int clahe16_luts_impl(const void* src, int64_t n, int h, int w, int64_t ssn, int64_t ssh, int gh, int gw,
-                      double clip_limit, uint16_t* luts, cudaStream_t st) {
+                      double clip_limit, uint16_t* luts, cudaStream_t st, uint32_t* vmax = nullptr) {
     if (n < 0 || h <= 0 || w <= 0) return MIE_E_SHAPE;
     if (n > 0 && (!src || !luts)) return MIE_E_NULL;
     if (ssh < w || (n > 1 && ssn < (int64_t)(h - 1) * ssh + w)) return MIE_E_STRIDE;
@@ -452,8 +488,17 @@ int clahe16_luts_impl(const void* src, int64_t n, int h, int w, int64_t ssn, int
         // counts fit 16 bits: single pass, one tile per cluster of two CTAs
         const size_t csmem = (size_t)(kHalf16 / 2 + kHalf16 / 64) * sizeof(int);
         MIE_ENSURE_SMEM(clahe16_lut_cluster_kernel, csmem);
+        if (vmax) {   // bound the LUTs by the largest pixel value of the batch (mie_clahe; the stage API returns full LUTs)
+            cudaError_t e = cudaMemsetAsync(vmax, 0, sizeof(uint32_t), st);
+            if (e != cudaSuccess) return (int)e;
+            const int64_t rows = n * h;
+            clahe16_max_kernel<<<(unsigned)(rows / 8 < 1 ? 1 : (rows / 8 > 4 * 148 ? 4 * 148 : rows / 8)), 256, 0, st>>>(
+                (const uint16_t*)src, ssn, ssh, n, h, w, vmax);
+            int rcm = check_launch();
+            if (rcm) return rcm;
+        }
         clahe16_lut_cluster_kernel<<<(unsigned)(2 * tiles), kClThreads, csmem, st>>>((const uint16_t*)src, ssn, ssh, g,
-                                                                                  make_lut16_params(g, clip_limit), luts);
+                                                                                  make_lut16_params(g, clip_limit), luts, vmax);
         return check_launch();
     }
     if ((int64_t)g.th * g.tw < 65536 && !no_small) {   // counts fit 16 bits: single-pass kernel
@@ -491,11 +536,18 @@ int clahe16_impl(const void* src, void* dst, int64_t n, int h, int w, int64_t ss
     if (workspace_bytes < per_image) return MIE_E_WORKSPACE;
     int64_t group = (int64_t)(workspace_bytes / per_image);
     if (group > 65535) group = 65535;
+    // 256 spare bytes behind the LUTs hold the batch's largest pixel value (see clahe16_lut_cluster_kernel)
+    uint32_t* vmax = nullptr;
+    // (a single slice is launch-latency bound: the two extra launches of the bound would cost what it saves)
+    if (!kernel_policy(MIE_POLICY_CLAHE16_FULL_LUTS) && n * gh * gw >= 2 * 148) {
+        if (workspace_bytes >= (size_t)group * per_image + 256) vmax = (uint32_t*)((char*)workspace + (size_t)group * per_image);
+        else if (group > 1) { --group; vmax = (uint32_t*)((char*)workspace + (size_t)group * per_image); }
+    }
     for (int64_t i0 = 0; i0 < n; i0 += group) {
         const int64_t m = (n - i0) < group ? (n - i0) : group;
         const uint16_t* s = (const uint16_t*)src + i0 * ssn;
         uint16_t* d = (uint16_t*)dst + i0 * dsn;
-        int rc = clahe16_luts_impl(s, m, h, w, ssn, ssh, gh, gw, clip_limit, (uint16_t*)workspace, st);
+        int rc = clahe16_luts_impl(s, m, h, w, ssn, ssh, gh, gw, clip_limit, (uint16_t*)workspace, st, vmax);
         if (rc) return rc;
         rc = clahe16_apply_impl(s, d, m, h, w, ssn, ssh, dsn, dsh, gh, gw, (const uint16_t*)workspace, st);
         if (rc) return rc;

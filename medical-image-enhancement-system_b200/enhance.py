@@ -72,7 +72,7 @@ def equalize_clahe(input: torch.Tensor, clip_limit: float = 40.0, grid_size: tup
     with torch.cuda.device(x.device):
         if semantics == "opencv" and x.dtype == torch.uint16:
             per_image = L.mie_clahe16_lut_bytes(gh, gw)
-            ws_bytes = per_image * max(1, min(n, CLAHE16_WORKSPACE_BYTES // max(per_image, 1)))
+            ws_bytes = per_image * max(1, min(n, CLAHE16_WORKSPACE_BYTES // max(per_image, 1))) + 256   # + the value bound
         else:
             ws_bytes = L.mie_clahe_workspace_bytes(n, h, w, gh, gw)
         ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=x.device)

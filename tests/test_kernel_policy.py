@@ -21,7 +21,7 @@ def test_policy_word_is_host_state_and_rejects_unknown_bits():
             assert L.mie_get_kernel_policy() == 32 | 128 | 1
         assert L.mie_get_kernel_policy() == 32 | 128
     assert L.mie_get_kernel_policy() == 0
-    assert sum(_ffi.POLICY.values()) == 4095      # MIE_POLICY_ALL: every bit has a Python name
+    assert sum(_ffi.POLICY.values()) == 8191      # MIE_POLICY_ALL: every bit has a Python name
 
 
 def test_no_getenv_left_in_the_library_sources():
@@ -85,7 +85,20 @@ def test_volume_median_and_clahe16_variants_agree(dev):
     assert torch.equal(a, b)
     x = _x(dev, (3, 1, 256, 256), np.uint16, seed=9)
     ref = M.equalize_clahe(x, 2.0, (4, 4), semantics="opencv").cpu()
-    for pol in ("clahe16_no_cluster", "clahe16_two_sweep"):
+    for pol in ("clahe16_no_cluster", "clahe16_two_sweep", "clahe16_full_luts"):
         with M.kernel_policy(pol):
             got = M.equalize_clahe(x, 2.0, (4, 4), semantics="opencv").cpu()
         assert torch.equal(ref.view(torch.int16), got.view(torch.int16)), pol
+    # LUTs bounded by the batch's largest pixel value (default) against full LUTs: bounds at 0, inside a thread's 64 bins,
+    # at the half boundary, above it, at 65535; geometries with padding
+    # (the bound is applied from 296 tiles on: batches of 5 .. 50 images here)
+    for shape, grid, clip, top in [((5, 1, 300, 500), (8, 8), 2.0, 4095), ((6, 1, 256, 250), (8, 8), 40.0, 32767),
+                                   ((50, 1, 64, 61), (2, 3), 3.0, 32768), ((20, 1, 128, 128), (4, 4), 2.0, 65535),
+                                   ((20, 1, 200, 136), (5, 3), 0.0, 100), ((5, 1, 128, 128), (8, 8), 4.0, 0),
+                                   ((19, 1, 128, 128), (4, 4), 4.0, 40000), ((5, 1, 128, 128), (8, 8), 2.0, 63)]:
+        rng = np.random.default_rng(top)
+        y = torch.from_numpy(rng.integers(0, top + 1, shape, dtype=np.uint16)).to(dev)
+        a = M.equalize_clahe(y, clip, grid, semantics="opencv").cpu()
+        with M.kernel_policy("clahe16_full_luts"):
+            b = M.equalize_clahe(y, clip, grid, semantics="opencv").cpu()
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), (shape, grid, clip, top)
