@@ -289,10 +289,10 @@ __device__ __forceinline__ int block_excl_scan_nw(int v, int* s_red, int* total)
 }
 
 // `vmax` (optional): device word holding an upper bound of every pixel value of the batch (clahe16_max_kernel).  LUT
-// entries above it are never looked up, so threads whose 64 bins lie above it skip their sweeps and their 128-byte LUT
-// stores, and only the live part of the counters is zeroed: 12-bit data in a 16-bit container — the usual CT / MR
-// case — costs 1/16 of the sweeps and of the LUT traffic, and the interpolation pass then gathers from 8 KB per tile
-// instead of 128 KB.  The entries that ARE written are the same as without the bound (prefix sums only look down).
+// entries above it are never looked up: only the live bins are zeroed, swept and written (spread over all threads of the
+// block), and a bound below 32 768 retires the upper-half CTA at once.  12-bit data in a 16-bit container — the usual
+// CT / MR case — costs 1/16 of the sweeps and of the LUT traffic, and the interpolation pass then gathers from 8 KB per
+// tile instead of 128 KB.  The entries that ARE written are the same as without the bound (prefix sums only look down).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kClThreads)
 clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_t ssh, ClaheGeom g, Lut16Params lp,
                            uint16_t* __restrict__ luts, const uint32_t* __restrict__ vmax) {
@@ -309,48 +309,60 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
     const int tid = threadIdx.x;
     uint32_t* s_w = reinterpret_cast<uint32_t*>(s_h);
     // highest live bin of this half (local index; negative: the whole half lies above the bound)
-    const int lmax = min((int)(vmax ? min(__ldg(vmax), 65535u) : 65535u) - (int)rank * kHalf16, kHalf16 - 1);
-    const int live_threads = lmax < 0 ? 0 : lmax / 64 + 1;          // thread t owns local bins 64 t .. 64 t + 63
-    const bool live = tid < live_threads;
-    for (int i = tid; i < live_threads * 33; i += kClThreads) s_w[i] = 0u;
+    const uint32_t bound = vmax ? min(__ldg(vmax), 65535u) : 65535u;
+    const bool both = bound >= (uint32_t)kHalf16;                    // cluster-uniform: does the upper half take part?
+    if (!both && rank == 1) return;                                  // (the lower half then skips the cluster barriers)
+    const int lmax = min((int)bound - (int)rank * kHalf16, kHalf16 - 1);
+    // the live bins are spread over ALL threads: thread t owns words t * wpt .. + wpt - 1 (two bins per word), wpt the
+    // smallest of 4 / 8 / 16 / 32 that covers them — 12-bit data: 8 bins per thread instead of 64 bins on 64 threads
+    const int live_bins = lmax + 1;
+    const int wpt = live_bins <= 4096 ? 4 : live_bins <= 8192 ? 8 : live_bins <= 16384 ? 16 : 32;
+    const int w0 = tid * wpt;
+    const bool live = 2 * w0 <= lmax;
+    {
+        const int live_words = ((lmax >> 1) / wpt + 1) * wpt;        // up to the end of the last live thread's words
+        for (int i = tid; i < padw(live_words - 1) + 1; i += kClThreads) s_w[i] = 0u;
+    }
     __syncthreads();
     const int area = g.th * g.tw;
     const bool inside = (ty + 1) * g.th <= g.h && (tx + 1) * g.tw <= g.w;   // block-uniform: no reflect padding
-    if (live_threads)
-        for (int i = tid; i < area; i += kClThreads) {
-            const int yy = i / g.tw, xx = i - yy * g.tw;
-            int sy = ty * g.th + yy, sx = tx * g.tw + xx;
-            if (!inside) {
-                sy = border_index(sy, g.h, MIE_BORDER_REFLECT);
-                sx = border_index(sx, g.w, MIE_BORDER_REFLECT);
-            }
-            const uint32_t v = plane[(int64_t)sy * ssh + sx];
-            if ((v >> 15) == rank) atomicAdd(&s_w[padw((int)((v & 0x7FFFu) >> 1))], (v & 1u) ? 0x10000u : 1u);
+    for (int i = tid; i < area; i += kClThreads) {
+        const int yy = i / g.tw, xx = i - yy * g.tw;
+        int sy = ty * g.th + yy, sx = tx * g.tw + xx;
+        if (!inside) {
+            sy = border_index(sy, g.h, MIE_BORDER_REFLECT);
+            sx = border_index(sx, g.w, MIE_BORDER_REFLECT);
         }
+        const uint32_t v = plane[(int64_t)sy * ssh + sx];
+        if ((v >> 15) == rank) atomicAdd(&s_w[padw((int)((v & 0x7FFFu) >> 1))], (v & 1u) ? 0x10000u : 1u);
+    }
     __syncthreads();
 
-    const uint32_t* mine = s_w + tid * 33;       // words 32 tid .. 32 tid + 31 of this half
+    const uint32_t* mine = s_w + padw(w0);       // wpt divides 32: the thread's words are contiguous behind the padding
     const uint32_t clip = (uint32_t)lp.clip;
     int rb = 0, res = 0, step = 1;
     if (lp.clip > 0) {
         int local = 0;
         if (live) {
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) {
+#pragma unroll 4
+            for (int k = 0; k < wpt; ++k) {
                 const uint32_t wv = mine[k];
                 const uint32_t c0 = wv & 0xFFFFu, c1 = wv >> 16;
                 local += (int)(c0 > clip ? c0 - clip : 0u) + (int)(c1 > clip ? c1 - clip : 0u);
             }
         }
         const int mine_clipped = block_sum_nw<kClThreads / 32>(local, s_red);
-        if (tid == 0) s_xchg[0] = mine_clipped;
-        cluster.sync();
-        const int clipped = mine_clipped + *cluster.map_shared_rank(&s_xchg[0], rank ^ 1u);
+        int clipped = mine_clipped;
+        if (both) {
+            if (tid == 0) s_xchg[0] = mine_clipped;
+            cluster.sync();
+            clipped += *cluster.map_shared_rank(&s_xchg[0], rank ^ 1u);
+        }
         rb = clipped / kBins16;
         res = clipped - rb * kBins16;
         step = res ? max(kBins16 / res, 1) : 1;
     }
-    const int u0 = (int)rank * kHalf16 + tid * 64;
+    const int u0 = (int)rank * kHalf16 + 2 * w0;
     int q = (u0 + step - 1) / step, next = q * step;
     auto bin_value = [&](uint32_t c, int u) {
         if (lp.clip > 0) {
@@ -364,8 +376,8 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
     };
     int sum = 0;
     if (live) {
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
+#pragma unroll 4
+        for (int k = 0; k < wpt; ++k) {
             const uint32_t wv = mine[k];
             sum += bin_value(wv & 0xFFFFu, u0 + 2 * k);
             sum += bin_value(wv >> 16, u0 + 2 * k + 1);
@@ -373,9 +385,11 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
     }
     int total;
     int cum = block_excl_scan_nw<kClThreads / 32>(sum, s_red, &total);   // dead threads add 0: prefixes only look down
-    if (tid == 0) s_xchg[1] = total;
-    cluster.sync();
-    if (rank == 1) cum += *cluster.map_shared_rank(&s_xchg[1], 0u);   // the upper half continues the lower half's prefix
+    if (both) {
+        if (tid == 0) s_xchg[1] = total;
+        cluster.sync();
+        if (rank == 1) cum += *cluster.map_shared_rank(&s_xchg[1], 0u);   // the upper half continues the lower half's prefix
+    }
     q = (u0 + step - 1) / step; next = q * step;
     const float scale = lp.lut_scale;
     auto lut_entry = [&](int c) {
@@ -385,8 +399,7 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
     };
     uint4* dst = reinterpret_cast<uint4*>(luts + tile * (int64_t)kBins16 + u0);
     if (live) {
-#pragma unroll 2
-        for (int k4 = 0; k4 < 8; ++k4) {
+        for (int k4 = 0; k4 < wpt / 4; ++k4) {
             uint32_t packed[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -400,7 +413,7 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
             dst[k4] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
     }
-    cluster.sync();   // the peer may still be reading this CTA's s_xchg
+    if (both) cluster.sync();   // the peer may still be reading this CTA's s_xchg
 }
 
 // Upper bound of the pixel values of a batch: one atomicMax per block into *vmax (zeroed by the caller).
