@@ -477,7 +477,8 @@ def sub_c4(M, dev, dist, world, rank, peak, with_cpu):
                        "CLAHE 16x16 clip 2.0, uint16 out", "n_gpus": world, "images": n_total, "scaling": "strong",
            "ms": round(ms, 3), "mpixel_s": round(px / ms / 1e3, 1), "stage_ms": plan.stage_ms(),
            "intermediate": "1-byte lookup-index plane + per-tile histograms (no fp32 image)",
-           "roofline": {"bound": "fma pipe (81 taps x exp), then hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
+           "colour_weight": "MUFU.EX2 (default mode, rel 6e-7 of the reproducible polynomial kernels = kernel policy bilateral_exact_exp)",
+           "roofline": {"bound": "XU pipe (81 MUFU.EX2 per pixel) + FMA pipe, then hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
                         "frac": frac, "basis": "4 B/px (uint16 in + uint16 out) / step time"}}
     if with_cpu:
         rec["cpu"] = _cpu_c4()
