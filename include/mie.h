@@ -96,7 +96,8 @@ enum mie_kernel_policy {
     MIE_POLICY_EQUALIZE_THREE_PASS = 1024, /* equalize: histogram / LUT / apply launches instead of the one-launch cluster kernel */
     MIE_POLICY_BILATERAL_EXACT_EXP = 2048, /* bilateral: the reproducible polynomial 2^t (bit-exact against the oracle) instead of MUFU.EX2 */
     MIE_POLICY_CLAHE16_FULL_LUTS = 4096,   /* 65 536-bin CLAHE: build all 65 536 LUT entries although the batch's largest pixel value is smaller */
-    MIE_POLICY_ALL = 8191
+    MIE_POLICY_EQUALIZE_SLAB = 8192,       /* equalize: the shared-memory slab (TMA) cluster kernel also for small planes (default: second read through L2) */
+    MIE_POLICY_ALL = 16383
 };
 int mie_set_kernel_policy(unsigned mask);
 unsigned mie_get_kernel_policy(void);

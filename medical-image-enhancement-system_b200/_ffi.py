@@ -110,7 +110,7 @@ def check(rc: int) -> None:
 POLICY = {"generic_gauss": 1, "generic_clahe": 2, "clahe_float_rules": 4, "generic_equalize": 8,
           "equalize_float_rules": 16, "generic_median": 32, "generic_bilateral": 64, "generic_nlm": 128,
           "clahe16_no_cluster": 256, "clahe16_two_sweep": 512, "equalize_three_pass": 1024,
-          "bilateral_exact_exp": 2048, "clahe16_full_luts": 4096}
+          "bilateral_exact_exp": 2048, "clahe16_full_luts": 4096, "equalize_slab": 8192}
 
 
 class kernel_policy:

@@ -21,7 +21,7 @@ def test_policy_word_is_host_state_and_rejects_unknown_bits():
             assert L.mie_get_kernel_policy() == 32 | 128 | 1
         assert L.mie_get_kernel_policy() == 32 | 128
     assert L.mie_get_kernel_policy() == 0
-    assert sum(_ffi.POLICY.values()) == 8191      # MIE_POLICY_ALL: every bit has a Python name
+    assert sum(_ffi.POLICY.values()) == 16383      # MIE_POLICY_ALL: every bit has a Python name
 
 
 def test_no_getenv_left_in_the_library_sources():
@@ -53,6 +53,8 @@ def test_tuned_and_generic_kernels_agree_bit_for_bit(dev, dtype):
         ("generic_equalize", lambda: M.equalize(x)),
         ("equalize_float_rules", lambda: M.equalize(x)),
         ("equalize_three_pass", lambda: M.equalize(x)),
+        ("equalize_slab", lambda: M.equalize(x)),
+        ("equalize_slab", lambda: M.equalize(x[:, :, :37].contiguous(), out_dtype=torch.float32)),
         ("generic_median", lambda: M.median_blur(x, 3)),
         ("generic_median", lambda: M.median_blur(x, 5)),
         ("generic_bilateral", lambda: M.bilateral_blur(x[:2], 5, 0.1, (1.5, 1.5))),
