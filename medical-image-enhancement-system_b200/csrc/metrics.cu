@@ -10,6 +10,8 @@
 // floating-point arithmetic is the float64 SSIM formula per window and the float64 sum of the maps.
 // Float planes accumulate in float64.  All reductions run in a fixed order (per-thread, warp tree,
 // block tree, then one block per plane over the block partials), so results are reproducible run to run.
+#include <type_traits>
+
 #include "mie_common.cuh"
 
 namespace mie {
@@ -61,6 +63,57 @@ sqdiff_partial_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t 
     const A t1 = block_tree_256(s1, s8);
     if (threadIdx.x == 0) {
         A* o = part + (n * gridDim.x + blockIdx.x) * 2;
+        o[0] = t2; o[1] = t1;
+    }
+}
+
+// The same for 8 / 16-bit planes whose rows are 16-byte aligned multiples of 16 bytes: one 128-bit load per image and
+// lane, (a - b)^2 accumulated exactly by 32 x 32 + 64-bit multiply-adds (|a - b| <= 65535, so the square fits 32 bits).
+// Integer sums are exact in any order: the result is the one of the scalar kernel, bit for bit.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sqdiff_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t asn, int64_t ash, int64_t bsn, int64_t bsh,
+                  int h, int w, int rows_per_block, long long* __restrict__ part) {
+    constexpr int PER = 16 / (int)sizeof(T);          // pixels per 128-bit load
+    __shared__ long long s8[8];
+    const int64_t n = blockIdx.y;
+    const int y0 = blockIdx.x * rows_per_block, y1 = min(y0 + rows_per_block, h);
+    const int vecs = w / PER, total = vecs * (y1 - y0);
+    unsigned long long s2 = 0ull, s1 = 0ull;
+    auto one = [&](int va, int vb) {
+        const int d = va - vb;
+        const unsigned ad = (unsigned)(d < 0 ? -d : d);
+        s2 += (unsigned long long)ad * ad;
+        s1 += ad;
+    };
+    (void)total;
+    for (int r = threadIdx.x >> 5; r < y1 - y0; r += 8) {
+        const uint4* ra = reinterpret_cast<const uint4*>(a + n * asn + (int64_t)(y0 + r) * ash);
+        const uint4* rb = reinterpret_cast<const uint4*>(b + n * bsn + (int64_t)(y0 + r) * bsh);
+#pragma unroll 4
+        for (int c = threadIdx.x & 31; c < vecs; c += 32) {
+        const uint4 qa = __ldg(ra + c);
+        const uint4 qb = __ldg(rb + c);
+        const uint32_t wa[4] = {qa.x, qa.y, qa.z, qa.w}, wb[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if constexpr (sizeof(T) == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) one((int)((wa[k] >> (8 * j)) & 0xFFu), (int)((wb[k] >> (8 * j)) & 0xFFu));
+            } else if constexpr (std::is_signed<T>::value) {
+                one((int)(short)(wa[k] & 0xFFFFu), (int)(short)(wb[k] & 0xFFFFu));
+                one((int)wa[k] >> 16, (int)wb[k] >> 16);
+            } else {
+                one((int)(wa[k] & 0xFFFFu), (int)(wb[k] & 0xFFFFu));
+                one((int)(wa[k] >> 16), (int)(wb[k] >> 16));
+            }
+        }
+        }
+    }
+    const long long t2 = block_tree_256((long long)s2, s8);
+    const long long t1 = block_tree_256((long long)s1, s8);
+    if (threadIdx.x == 0) {
+        long long* o = part + (n * gridDim.x + blockIdx.x) * 2;
         o[0] = t2; o[1] = t1;
     }
 }
@@ -120,8 +173,16 @@ ssim_partial_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t as
     for (int r = threadIdx.x >> 5; r < e; r += 8) {
         A s_a = 0, s_b = 0, s_aa = 0, s_bb = 0, s_ab = 0;
         for (int k = 0; k < ws; ++k) {
-            const A va = (A)sa[r * e + lx + k], vb = (A)sb[r * e + lx + k];
-            s_a += va; s_b += vb; s_aa += va * va; s_bb += vb * vb; s_ab += va * vb;
+            if constexpr (std::is_same<A, long long>::value) {
+                // |v| <= 65535: every product fits 32 bits (signed), so 32 x 32 + 64-bit multiply-adds are exact
+                const int va = sa[r * e + lx + k], vb = sb[r * e + lx + k];
+                s_a += va; s_b += vb;
+                s_aa += (long long)((unsigned)va * (unsigned)va); s_bb += (long long)((unsigned)vb * (unsigned)vb);   // v^2 < 2^32: exact mod 2^32
+                s_ab += (long long)va * vb;
+            } else {
+                const A va = (A)sa[r * e + lx + k], vb = (A)sb[r * e + lx + k];
+                s_a += va; s_b += vb; s_aa += va * va; s_bb += vb * vb; s_ab += va * vb;
+            }
         }
         A* o = hs + r * 32 + lx;
         o[0] = s_a; o[e * 32] = s_b; o[2 * e * 32] = s_aa; o[3 * e * 32] = s_bb; o[4 * e * 32] = s_ab;
@@ -195,9 +256,18 @@ int mie_sqdiff_sums(const void* a, const void* b, int dtype, int64_t n, int h, i
     const int rows = sqdiff_rows_per_block(n, h);
     const int count = ceil_div(h, rows);
     dim3 grid((unsigned)count, (unsigned)n);
+    static const int esz_[4] = {1, 2, 2, 4};
+    const int eb = esz_[dtype];
+    const bool vec = dtype != MIE_F32 && ((int64_t)w * eb) % 16 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 &&
+                     (a_stride_n * eb) % 16 == 0 && (a_stride_h * eb) % 16 == 0 && (b_stride_n * eb) % 16 == 0 &&
+                     (b_stride_h * eb) % 16 == 0;
 #define MIE_SQDIFF(T)                                                                                          \
-    sqdiff_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, a_stride_n, a_stride_h, b_stride_n, \
-                                                   b_stride_h, h, w, rows, (MetAcc<T>::type*)workspace);        \
+    if (vec && sizeof(T) != 4)                                                                                 \
+        sqdiff_vec_kernel<T><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, a_stride_n, a_stride_h, b_stride_n,   \
+                                                   b_stride_h, h, w, rows, (long long*)workspace);             \
+    else                                                                                                       \
+        sqdiff_partial_kernel<T><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, a_stride_n, a_stride_h, b_stride_n, \
+                                                       b_stride_h, h, w, rows, (MetAcc<T>::type*)workspace);    \
     rc = check_launch();                                                                                       \
     if (rc) return rc;                                                                                         \
     metric_finish_kernel<MetAcc<T>::type><<<(unsigned)n, 256, 0, st>>>((const MetAcc<T>::type*)workspace, count, out)
@@ -205,7 +275,13 @@ int mie_sqdiff_sums(const void* a, const void* b, int dtype, int64_t n, int h, i
         case MIE_U8: MIE_SQDIFF(uint8_t); break;
         case MIE_U16: MIE_SQDIFF(uint16_t); break;
         case MIE_I16: MIE_SQDIFF(int16_t); break;
-        default: MIE_SQDIFF(float); break;
+        default:
+            sqdiff_partial_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, a_stride_n, a_stride_h,
+                                                                b_stride_n, b_stride_h, h, w, rows, (double*)workspace);
+            rc = check_launch();
+            if (rc) return rc;
+            metric_finish_kernel<double><<<(unsigned)n, 256, 0, st>>>((const double*)workspace, count, out);
+            break;
     }
 #undef MIE_SQDIFF
     return check_launch();
