@@ -144,7 +144,8 @@ def test_bilateral_bit_exact_and_within_tolerance_of_true_exp(dev, dtype):
     import oracle as O
 
     for shape, k, sc, ss, border in [((2, 1, 70, 50), 9, 0.1, 1.5, "reflect"), ((1, 1, 33, 65), (5, 7), 0.2, (1.5, 1.2), "replicate"),
-                                     ((1, 1, 40, 40), 3, 0.05, 0.8, "constant"), ((1, 1, 64, 64), 15, 0.3, 3.0, "reflect")]:
+                                     ((1, 1, 40, 40), 3, 0.05, 0.8, "constant"), ((1, 1, 64, 64), 15, 0.3, 3.0, "reflect"),
+                                     ((1, 1, 45, 67), 5, 0.15, 1.0, "circular"), ((2, 1, 33, 31), 7, 0.08, 2.0, "replicate")]:
         x = rand(dtype, shape, 8)
         x01 = O.to01(x)
         ref = O.bilateral_blur(x01, k, sc, ss, border)
@@ -165,6 +166,30 @@ def test_bilateral_bit_exact_and_within_tolerance_of_true_exp(dev, dtype):
         if dtype != np.float32:
             q = cpu(M.bilateral_blur(gpu(x, dev), k, sc, ss, border)).astype(np.int64)
             assert np.abs(q - O.from01(ref, dtype).astype(np.int64)).max() <= 1
+
+
+# ---------------------------------------------------------------------------- equalisation: the three dispatch paths
+@pytest.mark.parametrize("shape,dtype", [((3, 1, 64, 128), np.uint16), ((2, 1, 200, 256), np.int16), ((5, 1, 512, 512), np.uint16),
+                                         ((1, 1, 100, 64), np.uint8), ((1, 1, 1024, 1024), np.uint16), ((2, 1, 37, 512), np.uint16),
+                                         ((1, 1, 9, 8), np.uint16), ((2, 1, 640, 2048), np.uint16)])
+def test_equalize_cluster_paths_agree_with_three_pass_and_oracle(dev, shape, dtype):
+    """One-launch cluster kernel without a slab (small planes: second read through L2), with a shared-memory slab (TMA;
+    larger planes, or forced by policy), and the three-pass path: same bits, and the oracle's."""
+    import mie_b200 as M
+    import oracle as O
+
+    x = rand(dtype, shape, 21)
+    x[0, 0, : shape[2] // 2] //= 9            # a skewed histogram in the first plane
+    xt = gpu(x, dev)
+    a = cpu(M.equalize(xt))
+    with M.kernel_policy("equalize_slab"):
+        b = cpu(M.equalize(xt))
+    with M.kernel_policy("equalize_three_pass"):
+        c = cpu(M.equalize(xt))
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert np.array_equal(a, O.from01(O.equalize(O.to01(x)), dtype))
+    k = gpu(np.full(shape, 77, dtype), dev)   # step == 0: v / 255 goes back unchanged
+    assert np.array_equal(cpu(M.equalize(k)), np.full(shape, 77, dtype))
 
 
 # ---------------------------------------------------------------------------- global equalisation
