@@ -349,6 +349,21 @@ int mie_halo_exchange_z(void* nccl_comm, int rank, int world,
                         const void* first_plane, const void* last_plane,
                         void* halo_lo, void* halo_hi, size_t plane_bytes, void* stream);
 
+/* Peer-load alternative to the exchange (one box, NVLink / NVSwitch): the halo pointers of mie_median3d may address the
+ * NEIGHBOUR RANK's slab directly — its memory mapped into this process by CUDA IPC (mie_ipc_* below; from Python:
+ * volume.PeerSlabPlan) — so the median kernel reads the two boundary planes over NVLink and no exchange is
+ * launched at all.  This call enables the current device's access to `peer_device` (cudaDeviceEnablePeerAccess;
+ * already-enabled is not an error); MIE_E_UNSUPPORTED when the two devices have no peer path. */
+int mie_enable_peer_access(int peer_device);
+/* CUDA IPC plumbing of the peer-load path (no torch types): mie_ipc_export writes the 64-byte cudaIpcMemHandle_t of the
+ * allocation that contains dev_ptr and the pointer's byte offset inside it (the allocation base is resolved with the
+ * driver's cuMemGetAddressRange, so pointers into a caching allocator's segment work); the handle travels to the
+ * neighbour process by any means; mie_ipc_open — called there with the READER's device current — maps the allocation
+ * (cudaIpcOpenMemHandle with lazy peer access) and returns its base; mie_ipc_close unmaps it. */
+int mie_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset_bytes);
+int mie_ipc_open(const void* handle64, void** base_out);
+int mie_ipc_close(void* base);
+
 /* ------------------------------------------------------------------ fused chain (BASELINE.json config 2)
  * Gaussian denoise -> CLAHE -> unsharp mask in two launches; equals
  * mie_gaussian2d -> mie_clahe -> mie_unsharp (F32 intermediates) bit for bit.

@@ -15,7 +15,7 @@ from .filters import bilateral_blur, denoise_nl_means, gaussian_blur2d, get_gaus
 from .loader import HostSlicePipeline, HostVolumePipeline, enhance_chain_host, median3d_clahe_host
 from .metrics import mae, mse, psnr, rmse, ssim
 from . import volume
-from .volume import SlabPlan, exchange_z_halos, median3d_clahe_slab, shard_range, start_z_halo_exchange
+from .volume import PeerSlabPlan, SlabPlan, exchange_z_halos, map_peer_halos, median3d_clahe_slab, shard_range, start_z_halo_exchange
 
 __version__ = "0.1.0"
 
@@ -26,5 +26,5 @@ __all__ = [
     "ChainConfig", "ChainPlan", "ChainRing", "enhance_chain", "chain_workspace_bytes", "bilateral_clahe", "BilateralClahePlan",
     "HostSlicePipeline", "enhance_chain_host", "HostVolumePipeline", "median3d_clahe_host",
     "mse", "rmse", "psnr", "ssim", "mae", "value_range_mode", "kernel_policy",
-    "shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab", "SlabPlan",
+    "shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab", "SlabPlan", "PeerSlabPlan", "map_peer_halos",
 ]

@@ -66,6 +66,10 @@ SIGNATURES = {
     "mie_sk_denoise_bilateral": ([_p, _p, _i, _i, *_planes, _i, _i, _i, _d, _p, _p, _p, _p], _i),
     "mie_halo_exchange_available": ([], _i),
     "mie_halo_exchange_z": ([_p, _i, _i, _p, _p, _p, _p, _sz, _p], _i),
+    "mie_enable_peer_access": ([_i], _i),
+    "mie_ipc_export": ([_p, _p, C.POINTER(_i64)], _i),
+    "mie_ipc_open": ([_p, C.POINTER(_p)], _i),
+    "mie_ipc_close": ([_p], _i),
     "mie_chain_workspace_bytes": ([_i64, _i, _i, _i, _i], _sz),
     "mie_chain_gauss_clahe_unsharp": (
         [_p, _p, _i, _i, *_planes, *_taps, _i, _i, _d, *_taps, _i, _f, _f, _i, _p, _sz, _p], _i),

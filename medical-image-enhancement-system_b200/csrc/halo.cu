@@ -11,6 +11,7 @@
 // created it.  The entry points are therefore resolved at first use from the libnccl.so.2 already loaded into the
 // process (dlopen RTLD_NOLOAD); without one the call returns MIE_E_UNSUPPORTED.
 #include <dlfcn.h>
+#include <cstring>
 
 #include <mutex>
 
@@ -55,6 +56,64 @@ using namespace mie;
 extern "C" {
 
 int mie_halo_exchange_available(void) { return nccl_api().ok ? 1 : 0; }
+
+// cudaIpcGetMemHandle wants the BASE of the allocation; a pointer into a caching allocator's segment is resolved with
+// the driver's cuMemGetAddressRange, taken from the libcuda.so.1 that is already loaded into the process.
+int mie_ipc_export(const void* dev_ptr, void* handle64, int64_t* offset_bytes) {
+    if (!dev_ptr || !handle64 || !offset_bytes) return MIE_E_NULL;
+    typedef int (*get_range_fn)(unsigned long long*, size_t*, unsigned long long);
+    static get_range_fn get_range = [] {
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libcuda.so.1", RTLD_NOW);
+        return h ? (get_range_fn)dlsym(h, "cuMemGetAddressRange_v2") : (get_range_fn) nullptr;
+    }();
+    if (!get_range) return MIE_E_UNSUPPORTED;
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (get_range(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0 || !base) return MIE_E_UNSUPPORTED;
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return (int)e; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    memcpy(handle64, &h, 64);
+    *offset_bytes = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+    return MIE_OK;
+}
+
+int mie_ipc_open(const void* handle64, void** base_out) {
+    if (!handle64 || !base_out) return MIE_E_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);   // current device = the reader
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return (int)e; }
+    *base_out = p;
+    return MIE_OK;
+}
+
+int mie_ipc_close(void* base) {
+    if (!base) return MIE_OK;
+    cudaError_t e = cudaIpcCloseMemHandle(base);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return (int)e; }
+    return MIE_OK;
+}
+
+int mie_enable_peer_access(int peer_device) {
+    int cur = -1, count = 0;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return (int)e;
+    if (peer_device < 0 || peer_device >= count) return MIE_E_SHAPE;
+    if (peer_device == cur) return MIE_OK;
+    int can = 0;
+    e = cudaDeviceCanAccessPeer(&can, cur, peer_device);
+    if (e != cudaSuccess) return (int)e;
+    if (!can) return MIE_E_UNSUPPORTED;
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { (void)cudaGetLastError(); return MIE_OK; }
+    return e == cudaSuccess ? MIE_OK : (int)e;
+}
 
 int mie_halo_exchange_z(void* nccl_comm, int rank, int world, const void* first_plane, const void* last_plane,
                         void* halo_lo, void* halo_hi, size_t plane_bytes, void* stream) {

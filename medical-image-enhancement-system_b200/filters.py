@@ -186,11 +186,12 @@ _MEDIAN_MODES = {"nearest": "replicate", "constant": "constant"}
 
 
 def median(image: torch.Tensor, footprint=None, out=None, mode: str = "nearest", cval: float = 0.0,
-           behavior: str = "ndimage", *, halo_lo=None, halo_hi=None) -> torch.Tensor:
+           behavior: str = "ndimage", *, halo_lo=None, halo_hi=None, peer_halos: bool = False) -> torch.Tensor:
     """skimage.filters.median on a 2-D image (3x3 default) or 3-D volume (3x3x3 default)
     -> scipy.ndimage.median_filter semantics (rank n//2).  Footprints: None or an all-ones
     box of the default size.  `halo_lo` / `halo_hi`: the neighbouring slab's boundary
-    plane when the volume is one z-slab of a sharded volume (see volume.py)."""
+    plane when the volume is one z-slab of a sharded volume (see volume.py); with `peer_halos=True` they may live on
+    another GPU of the box (the neighbour rank's slab mapped by CUDA IPC: the kernel reads them over NVLink)."""
     require_cuda(image)
     if behavior != "ndimage":
         raise NotImplementedError("behavior='rank' is not supported")
@@ -223,7 +224,7 @@ def median(image: torch.Tensor, footprint=None, out=None, mode: str = "nearest",
             d, h, w = x.shape
             for hp in (halo_lo, halo_hi):
                 if hp is not None and (hp.shape != (h, w) or hp.dtype != x.dtype or not hp.is_contiguous()
-                                       or hp.device != x.device):
+                                       or (hp.device != x.device and not (peer_halos and hp.is_cuda))):
                     raise ValueError("halo planes must be contiguous (H, W) tensors of the volume's dtype on its device")
             check(lib().mie_median3d(x.data_ptr(), dst.data_ptr(), DTYPE_CODE[x.dtype], d, h, w, h * w, w, h * w, w,
                                      halo_lo.data_ptr() if halo_lo is not None else None,

@@ -23,8 +23,8 @@ import torch.distributed as dist
 
 from ._ffi import check, lib
 
-__all__ = ["shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab", "SlabPlan", "world_info",
-           "nccl_comm_ptr", "close_all_plans"]
+__all__ = ["shard_range", "exchange_z_halos", "start_z_halo_exchange", "median3d_clahe_slab", "SlabPlan", "PeerSlabPlan",
+           "map_peer_halos", "PeerPlane", "world_info", "nccl_comm_ptr", "close_all_plans"]
 
 
 def world_info(group=None):
@@ -239,6 +239,140 @@ class SlabPlan:
             self.close()
         except Exception:
             pass
+
+
+class PeerPlane:
+    """One (H, W) plane of a neighbour rank's slab, mapped into this process by CUDA IPC: a raw device pointer with the
+    few tensor attributes filters.median() inspects."""
+
+    is_cuda = True
+
+    def __init__(self, ptr: int, shape, dtype, device):
+        self._ptr, self.shape, self.dtype, self.device = int(ptr), tuple(shape), dtype, device
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def is_contiguous(self) -> bool:
+        return True
+
+
+class _PeerMapping:
+    def __init__(self, base: int):
+        self.base = base
+
+    def close(self):
+        if self.base:
+            lib().mie_ipc_close(self.base)
+            self.base = 0
+
+
+def map_peer_halos(slab: torch.Tensor, group=None):
+    """Map the neighbour ranks' slabs into this process (CUDA IPC: mie_ipc_export / mie_ipc_open, include/mie.h) and
+    return (halo_lo, halo_hi, keep): the lower neighbour's LAST plane and the upper neighbour's FIRST plane as PeerPlane
+    objects — memory of the neighbours' GPUs, readable by this GPU's kernels over NVLink — and the mappings to close.
+    None at a volume face.  Collective: every rank of the group calls it with its contiguous (D, H, W) slab (D >= 1);
+    one box only.  The caller keeps `slab` alive and in place while a peer may read it."""
+    import ctypes as C
+
+    rank, world = world_info(group)
+    if world == 1:
+        return None, None, ()
+    if not slab.is_cuda or slab.dim() != 3 or not slab.is_contiguous() or slab.shape[0] < 1:
+        raise ValueError("map_peer_halos needs a contiguous, non-empty (D, H, W) CUDA slab")
+    handle = (C.c_ubyte * 64)()
+    off = C.c_int64(0)
+    with torch.cuda.device(slab.device):
+        check(lib().mie_ipc_export(slab.data_ptr(), handle, C.byref(off)))
+    mine = (bytes(handle), int(off.value), tuple(slab.shape), slab.device.index)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    lo = hi = None
+    keep = []
+    plane_bytes = slab.shape[1] * slab.shape[2] * slab.element_size()
+    with torch.cuda.device(slab.device):
+        for nb in (rank - 1, rank + 1):
+            if 0 <= nb < world:
+                hbytes, offset, shape, dev_index = gathered[nb]
+                if tuple(shape[1:]) != tuple(slab.shape[1:]):
+                    raise ValueError("neighbour slabs must have this slab's plane shape")
+                base = C.c_void_p(0)
+                buf = (C.c_ubyte * 64).from_buffer_copy(hbytes)
+                check(lib().mie_ipc_open(buf, C.byref(base)))
+                keep.append(_PeerMapping(base.value))
+                first = base.value + offset
+                if nb < rank:
+                    lo = PeerPlane(first + (shape[0] - 1) * plane_bytes, slab.shape[1:], slab.dtype, torch.device("cuda", dev_index))
+                else:
+                    hi = PeerPlane(first, slab.shape[1:], slab.dtype, torch.device("cuda", dev_index))
+    dist.barrier(group=group)                     # nobody frees or moves a slab before every neighbour has mapped it
+    return lo, hi, tuple(keep)
+
+
+class PeerSlabPlan:
+    """BASELINE.json config 3 on this rank's z-slab with the halos READ IN PLACE: the two neighbour slabs are mapped into
+    this process once (map_peer_halos), and the 3x3x3 median takes their boundary planes as its halo pointers — peer loads
+    over NVLink / NVSwitch inside the kernel.  No exchange launch, no split into interior and boundary planes: the step is
+    ONE median launch plus the CLAHE launches, captured into a CUDA graph.
+
+        plan = PeerSlabPlan(slab)        # collective: maps the neighbours, captures the step
+        slab.copy_(next_part); dist.barrier()   # the NEIGHBOURS' slabs must be complete before a replay reads them
+        out = plan.replay()
+
+    Synchronisation is the caller's: a replay reads the neighbours' INPUT slabs, so every rank must have finished
+    refilling its slab (and must not refill it again) while a neighbour's replay is in flight.  Results are bit-identical
+    to SlabPlan / the unsharded volume."""
+
+    def __init__(self, slab: torch.Tensor, clip_limit: float = 2.0, grid_size: tuple = (8, 8), *,
+                 mode: str = "nearest", value_range=None, group=None):
+        from .enhance import equalize_clahe
+        from .filters import median
+
+        if not slab.is_cuda or slab.dim() != 3 or not slab.is_contiguous() or slab.shape[0] < 1:
+            raise ValueError("PeerSlabPlan needs a contiguous, non-empty (D, H, W) CUDA slab")
+        self.slab = slab
+        self.graph = None
+        self.halo_lo, self.halo_hi, self._keep = map_peer_halos(slab, group)
+        self._group = group
+
+        def step():
+            med = median(slab, mode=mode, halo_lo=self.halo_lo, halo_hi=self.halo_hi, peer_halos=True)
+            return equalize_clahe(med.unsqueeze(1), clip_limit, grid_size, value_range=value_range).squeeze(1)
+
+        with torch.cuda.device(slab.device):
+            step()                                                   # lazy initialisations outside the capture
+            torch.cuda.synchronize(slab.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = step()
+            torch.cuda.synchronize(slab.device)
+
+    def replay(self) -> torch.Tensor:
+        if self.graph is None:
+            raise RuntimeError("PeerSlabPlan is closed")
+        self.graph.replay()
+        return self.out
+
+    def close(self) -> None:
+        """Collective: every rank finishes its replays, then the mappings of the neighbours' slabs are dropped."""
+        if self.graph is not None:
+            torch.cuda.synchronize(self.slab.device)
+            self.graph.reset()
+            self.graph = None
+            self.out = None
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier(group=self._group)                      # no neighbour is still reading this rank's slab
+            self.halo_lo = self.halo_hi = None
+            for m in self._keep:
+                m.close()
+            self._keep = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 _live_plans = weakref.WeakSet()

@@ -54,6 +54,21 @@ def _worker(rank, world, port, out_dir):
             vol2 = synthetic.phantom_volume((37, 128, 192), np.int16, seed=7)
             slab.copy_(torch.from_numpy(vol2[z0:z1].copy()).to(dev))
             np.save(os.path.join(out_dir, f"vol2_{rank}.npy"), plan.replay().cpu().numpy())
+        # peer-load variant: the neighbours' slabs mapped by CUDA IPC, their boundary planes read over NVLink by the median
+        # kernel itself (no exchange launch) — same bits, also after refilling the slabs
+        slab.copy_(torch.from_numpy(vol[z0:z1].copy()).to(dev))
+        torch.cuda.synchronize()
+        dist.barrier()
+        with M.PeerSlabPlan(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0)) as pplan:
+            assert torch.equal(pplan.replay(), out), "peer-load slab step differs from the NCCL one"
+            torch.cuda.synchronize()
+            dist.barrier()                                   # every neighbour has finished reading before the refill
+            slab.copy_(torch.from_numpy(vol2[z0:z1].copy()).to(dev))
+            torch.cuda.synchronize()
+            dist.barrier()                                   # ... and every slab is complete before anybody reads it
+            got2 = pplan.replay().cpu().numpy()
+            assert np.array_equal(got2, np.load(os.path.join(out_dir, f"vol2_{rank}.npy")))
+            torch.cuda.synchronize()
         # a plan nobody closes must not hang destroy_process_group() in the finally block below
         forgotten = M.SlabPlan(slab, 2.0, (2, 3), value_range=(-1024.0, 3071.0))
         forgotten.replay()
