@@ -430,10 +430,12 @@ def sub_c3(M, dev, dist, world, rank, peak, with_cpu):
     rec = {"workload": "configs[2]: 512x512x512 int16 volume, 3x3x3 median (nearest) + per-slice CLAHE 8x8 clip 2.0",
            "n_gpus": world, "scaling": "strong", "ms": round(msN, 4), "mvoxel_s": round(vox / msN / 1e3, 1),
            "ms_n1_same_gpu": round(ms1, 4), "efficiency_vs_n1": round(ms1 / (world * msN), 4),
-           "bit_identical_to_unsharded": same, "launch": "CUDA graph (SlabPlan: halo exchange + kernels captured)",
+           "bit_identical_to_unsharded": same, "launch": "CUDA graph (PeerSlabPlan: one median launch + CLAHE)" if peer_used else "CUDA graph (SlabPlan: halo exchange + kernels captured)",
            "ms_eager": eager, "halo_bytes_per_face": 512 * 512 * 2, "halo_messages_total": 2 * (world - 1) * 1,
-           "exchange": "mie_halo_exchange_z: ncclSend/ncclRecv group on the process group's communicator, side stream, "
-                       "overlapped with the median of the interior planes" if world > 1 else "none (one slab)",
+           "exchange": ("peer loads: the neighbour slabs are mapped by CUDA IPC and the median kernel reads their boundary planes "
+                        "over NVLink (PeerSlabPlan); the NCCL plan (mie_halo_exchange_z) is timed beside it" if peer_used else
+                        "mie_halo_exchange_z: ncclSend/ncclRecv group on the process group's communicator, side stream, "
+                        "overlapped with the median of the interior planes") if world > 1 else "none (one slab)",
            "native_exchange": bool(world > 1 and M.volume.nccl_comm_ptr(dev) != 0) if world > 1 else None,
            "ms_nccl_exchange_plan": round(ms_nccl, 4) if world > 1 else None,
            "ms_peer_load_plan": (round(ms_peer, 4) if ms_peer is not None else None) if world > 1 else None,
