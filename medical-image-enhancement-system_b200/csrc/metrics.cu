@@ -169,41 +169,62 @@ ssim_partial_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t as
         sb[i] = (R)pb[(int64_t)y * bsh + x];
     }
     __syncthreads();
-    const int lx = threadIdx.x & 31;
-    for (int r = threadIdx.x >> 5; r < e; r += 8) {
+    // Phase 2: horizontal ws-sums as RUNNING sums — a thread owns 8 consecutive windows of one tile row: the first sum in
+    // full, then one sample in and one out per window (integer planes: exact; float planes: float64, 8 steps).
+    for (int job = threadIdx.x; job < e * 4; job += 256) {
+        const int r = job >> 2, l0 = (job & 3) * 8;
+        const R* ra = sa + r * e + l0;
+        const R* rb = sb + r * e + l0;
         A s_a = 0, s_b = 0, s_aa = 0, s_bb = 0, s_ab = 0;
-        for (int k = 0; k < ws; ++k) {
+        auto add = [&](R xa, R xb, int sign) {
             if constexpr (std::is_same<A, long long>::value) {
-                // |v| <= 65535: every product fits 32 bits (signed), so 32 x 32 + 64-bit multiply-adds are exact
-                const int va = sa[r * e + lx + k], vb = sb[r * e + lx + k];
-                s_a += va; s_b += vb;
-                s_aa += (long long)((unsigned)va * (unsigned)va); s_bb += (long long)((unsigned)vb * (unsigned)vb);   // v^2 < 2^32: exact mod 2^32
-                s_ab += (long long)va * vb;
+                const int va = xa, vb = xb;
+                const long long aa = (long long)((unsigned)va * (unsigned)va), bb = (long long)((unsigned)vb * (unsigned)vb);
+                const long long ab = (long long)va * vb;
+                if (sign > 0) { s_a += va; s_b += vb; s_aa += aa; s_bb += bb; s_ab += ab; }
+                else { s_a -= va; s_b -= vb; s_aa -= aa; s_bb -= bb; s_ab -= ab; }
             } else {
-                const A va = (A)sa[r * e + lx + k], vb = (A)sb[r * e + lx + k];
-                s_a += va; s_b += vb; s_aa += va * va; s_bb += vb * vb; s_ab += va * vb;
+                const A va = (A)xa, vb = (A)xb;
+                if (sign > 0) { s_a += va; s_b += vb; s_aa += va * va; s_bb += vb * vb; s_ab += va * vb; }
+                else { s_a -= va; s_b -= vb; s_aa -= va * va; s_bb -= vb * vb; s_ab -= va * vb; }
             }
+        };
+        for (int k = 0; k < ws; ++k) add(ra[k], rb[k], 1);
+        A* o = hs + r * 32 + l0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j) { add(ra[j + ws - 1], rb[j + ws - 1], 1); add(ra[j - 1], rb[j - 1], -1); }
+            o[j] = s_a; o[e * 32 + j] = s_b; o[2 * e * 32 + j] = s_aa; o[3 * e * 32 + j] = s_bb; o[4 * e * 32 + j] = s_ab;
         }
-        A* o = hs + r * 32 + lx;
-        o[0] = s_a; o[e * 32] = s_b; o[2 * e * 32] = s_aa; o[3 * e * 32] = s_bb; o[4 * e * 32] = s_ab;
     }
     __syncthreads();
+    // Phase 3: vertical ws-sums, again running: a thread owns 4 consecutive windows of one column.
+    const int lx = threadIdx.x & 31, r0 = (threadIdx.x >> 5) * 4;
     const double inv_n = 1.0 / (double)(ws * ws);
     double acc_s = 0.0, acc_c = 0.0;
-    for (int r = threadIdx.x >> 5; r < kSsimTile; r += 8) {
-        if (ty0 + r >= oh || tx0 + lx >= ow) continue;
+    {
         A s_a = 0, s_b = 0, s_aa = 0, s_bb = 0, s_ab = 0;
         for (int k = 0; k < ws; ++k) {
-            const A* p = hs + (r + k) * 32 + lx;
+            const A* p = hs + (r0 + k) * 32 + lx;
             s_a += p[0]; s_b += p[e * 32]; s_aa += p[2 * e * 32]; s_bb += p[3 * e * 32]; s_ab += p[4 * e * 32];
         }
-        const double mu_a = (double)s_a * inv_n, mu_b = (double)s_b * inv_n;
-        const double mu_aa = mu_a * mu_a, mu_bb = mu_b * mu_b, mu_ab = mu_a * mu_b;
-        const double var_a = (double)s_aa * inv_n - mu_aa, var_b = (double)s_bb * inv_n - mu_bb;
-        const double cov = (double)s_ab * inv_n - mu_ab;
-        const double cs = (2.0 * cov + c2) / (var_a + var_b + c2);
-        acc_c += cs;
-        acc_s += ((2.0 * mu_ab + c1) * (2.0 * cov + c2)) / ((mu_aa + mu_bb + c1) * (var_a + var_b + c2));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j) {
+                const A* pi = hs + (r0 + j + ws - 1) * 32 + lx;
+                const A* po = hs + (r0 + j - 1) * 32 + lx;
+                s_a += pi[0] - po[0]; s_b += pi[e * 32] - po[e * 32]; s_aa += pi[2 * e * 32] - po[2 * e * 32];
+                s_bb += pi[3 * e * 32] - po[3 * e * 32]; s_ab += pi[4 * e * 32] - po[4 * e * 32];
+            }
+            if (ty0 + r0 + j >= oh || tx0 + lx >= ow) continue;
+            const double mu_a = (double)s_a * inv_n, mu_b = (double)s_b * inv_n;
+            const double mu_aa = mu_a * mu_a, mu_bb = mu_b * mu_b, mu_ab = mu_a * mu_b;
+            const double var_a = (double)s_aa * inv_n - mu_aa, var_b = (double)s_bb * inv_n - mu_bb;
+            const double cov = (double)s_ab * inv_n - mu_ab;
+            const double cs = (2.0 * cov + c2) / (var_a + var_b + c2);
+            acc_c += cs;
+            acc_s += ((2.0 * mu_ab + c1) * (2.0 * cov + c2)) / ((mu_aa + mu_bb + c1) * (var_a + var_b + c2));
+        }
     }
     const double ts = block_tree_256(acc_s, s8);
     const double tc = block_tree_256(acc_c, s8);
