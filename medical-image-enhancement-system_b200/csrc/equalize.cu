@@ -12,6 +12,7 @@
 // LUT (one block per plane), apply.
 
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "march.cuh"
 #include "window.cuh"
@@ -161,7 +162,7 @@ __device__ __forceinline__ void eq_store8(uint16_t* p, const uint16_t* s_out, co
     o.y = (uint32_t)s_out[i[2]] | ((uint32_t)s_out[i[3]] << 16);
     o.z = (uint32_t)s_out[i[4]] | ((uint32_t)s_out[i[5]] << 16);
     o.w = (uint32_t)s_out[i[6]] | ((uint32_t)s_out[i[7]] << 16);
-    *reinterpret_cast<uint4*>(p) = o;
+    __stcs(reinterpret_cast<uint4*>(p), o);   // streaming store: the output should not push the input out of L2
 }
 __device__ __forceinline__ void eq_store8(int16_t* p, const int16_t* s_out, const uint32_t* i) {
     eq_store8(reinterpret_cast<uint16_t*>(p), reinterpret_cast<const uint16_t*>(s_out), i);
@@ -299,6 +300,18 @@ equalize_fused_cluster_kernel(const SrcT* __restrict__ src, DstT* __restrict__ d
         if constexpr (SLAB) SlabCodes<SrcT>::load8(slab + 8 * g, u);
         else Codes<SrcT>::load8(gsrc + 8 * g, u);
     };
+    // second read of the no-slab variant: last use of the line (ld.global.cs = evict-first), 16-bit pixels; together with
+    // the streaming stores 0.0617 -> 0.0599 ms (ncu before: 221 MB read from DRAM for 134 MB of pixels)
+    auto ld8_last = [&](size_t g, uint32_t* u) {
+        if constexpr (!SLAB && sizeof(SrcT) == 2) {
+            uint4 b = __ldcs(reinterpret_cast<const uint4*>(gsrc + 8 * g));
+            if (std::is_signed<SrcT>::value) { b.x ^= 0x80008000u; b.y ^= 0x80008000u; b.z ^= 0x80008000u; b.w ^= 0x80008000u; }
+            u[0] = b.x & 0xFFFFu; u[1] = b.x >> 16; u[2] = b.y & 0xFFFFu; u[3] = b.y >> 16;
+            u[4] = b.z & 0xFFFFu; u[5] = b.z >> 16; u[6] = b.w & 0xFFFFu; u[7] = b.w >> 16;
+            return;
+        }
+        ld8(g, u);
+    };
     if (SLAB && warp == 0) {   // producer warp: one arrival (with the stage's byte count) per stage, then one copy per row
         if (lane < kEqStages) {
             const int r0 = min(lane * rows_per_stage, rows), r1 = min(r0 + rows_per_stage, rows);
@@ -380,7 +393,7 @@ equalize_fused_cluster_kernel(const SrcT* __restrict__ src, DstT* __restrict__ d
 #pragma unroll 4
         for (int g = tid; g < g1; g += 256) {
             uint32_t idx[8];
-            ld8((size_t)g, idx);
+            ld8_last((size_t)g, idx);
 #pragma unroll
             for (int k = 0; k < 8; ++k) idx[k] = Codes<SrcT>::index(idx[k]);
             eq_store8(dp + 8 * (size_t)g, s_out, idx);
