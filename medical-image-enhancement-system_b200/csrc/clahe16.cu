@@ -326,15 +326,32 @@ clahe16_lut_cluster_kernel(const uint16_t* __restrict__ src, int64_t ssn, int64_
     __syncthreads();
     const int area = g.th * g.tw;
     const bool inside = (ty + 1) * g.th <= g.h && (tx + 1) * g.tw <= g.w;   // block-uniform: no reflect padding
-    for (int i = tid; i < area; i += kClThreads) {
-        const int yy = i / g.tw, xx = i - yy * g.tw;
-        int sy = ty * g.th + yy, sx = tx * g.tw + xx;
-        if (!inside) {
-            sy = border_index(sy, g.h, MIE_BORDER_REFLECT);
-            sx = border_index(sx, g.w, MIE_BORDER_REFLECT);
-        }
-        const uint32_t v = plane[(int64_t)sy * ssh + sx];
+    auto count = [&](uint32_t v) {
         if ((v >> 15) == rank) atomicAdd(&s_w[padw((int)((v & 0x7FFFu) >> 1))], (v & 1u) ? 0x10000u : 1u);
+    };
+    // tiles inside the image with 16-byte aligned rows of a multiple of 8 pixels: ONE 128-bit load per thread and step
+    // (a 64 x 64 tile is one step of the block) instead of eight dependent 2-byte loads — the count phase was the top
+    // stall of the kernel (long_scoreboard 4.7 warps per issue, profiles/r2_ncu_full_clahe16_bounded_lut.txt)
+    const bool vec = inside && (g.tw & 7) == 0 && (ssh & 7) == 0 && (ssn & 7) == 0 && ((uintptr_t)src & 15) == 0;
+    if (vec) {
+        const int gpr = g.tw >> 3, groups = g.th * gpr;
+        const uint16_t* t0 = plane + (int64_t)ty * g.th * ssh + tx * g.tw;
+        for (int i = tid; i < groups; i += kClThreads) {
+            const int yy = i / gpr, c8 = i - yy * gpr;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(t0 + (int64_t)yy * ssh + 8 * c8));
+            count(q.x & 0xFFFFu); count(q.x >> 16); count(q.y & 0xFFFFu); count(q.y >> 16);
+            count(q.z & 0xFFFFu); count(q.z >> 16); count(q.w & 0xFFFFu); count(q.w >> 16);
+        }
+    } else {
+        for (int i = tid; i < area; i += kClThreads) {
+            const int yy = i / g.tw, xx = i - yy * g.tw;
+            int sy = ty * g.th + yy, sx = tx * g.tw + xx;
+            if (!inside) {
+                sy = border_index(sy, g.h, MIE_BORDER_REFLECT);
+                sx = border_index(sx, g.w, MIE_BORDER_REFLECT);
+            }
+            count(plane[(int64_t)sy * ssh + sx]);
+        }
     }
     __syncthreads();
 
