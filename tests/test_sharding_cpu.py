@@ -77,3 +77,18 @@ def test_z_halo_exchange_over_gloo_reproduces_unsharded_median(tmp_path, world, 
     vol = rng.integers(0, 4000, (11, 12, 14)).astype(np.dtype(dtype))
     parts = np.concatenate([np.load(tmp_path / f"part{r}.npy") for r in range(world)])
     assert np.array_equal(parts, O.median3d(vol))
+
+
+def test_peer_halo_mapping_is_a_no_op_without_a_process_group():
+    """map_peer_halos (CUDA IPC mapping of the neighbour slabs) has nothing to map in a single-process run; PeerPlane is
+    the duck-typed halo argument filters.median() inspects."""
+    import torch
+
+    import mie_b200 as M
+    from mie_b200.volume import PeerPlane
+
+    lo, hi, keep = M.map_peer_halos(torch.zeros((3, 4, 5), dtype=torch.int16))
+    assert lo is None and hi is None and keep == ()
+    p = PeerPlane(0x7F0000001000, (4, 5), torch.int16, torch.device("cuda", 3))
+    assert p.data_ptr() == 0x7F0000001000 and p.shape == (4, 5) and p.is_contiguous() and p.is_cuda
+    assert p.dtype == torch.int16 and p.device.index == 3
