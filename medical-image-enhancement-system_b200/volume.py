@@ -280,33 +280,48 @@ def map_peer_halos(slab: torch.Tensor, group=None):
         return None, None, ()
     if not slab.is_cuda or slab.dim() != 3 or not slab.is_contiguous() or slab.shape[0] < 1:
         raise ValueError("map_peer_halos needs a contiguous, non-empty (D, H, W) CUDA slab")
+    def all_ok(ok: bool, what: str):
+        """Every rank learns whether EVERY rank succeeded, so that a failure is raised by all of them together (a rank that
+        raised alone would leave the others waiting in the next collective)."""
+        flag = torch.tensor([1.0 if ok else 0.0], device=slab.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if flag.item() != 1.0:
+            raise RuntimeError(f"peer halos unavailable: {what} failed on at least one rank")
+
     handle = (C.c_ubyte * 64)()
     off = C.c_int64(0)
     with torch.cuda.device(slab.device):
-        check(lib().mie_ipc_export(slab.data_ptr(), handle, C.byref(off)))
+        rc = lib().mie_ipc_export(slab.data_ptr(), handle, C.byref(off))
+    all_ok(rc == 0, "exporting the slab's CUDA IPC handle")
     mine = (bytes(handle), int(off.value), tuple(slab.shape), slab.device.index)
     gathered = [None] * world
     dist.all_gather_object(gathered, mine, group=group)
     lo = hi = None
     keep = []
     plane_bytes = slab.shape[1] * slab.shape[2] * slab.element_size()
+    ok = True
     with torch.cuda.device(slab.device):
         for nb in (rank - 1, rank + 1):
-            if 0 <= nb < world:
+            if 0 <= nb < world and ok:
                 hbytes, offset, shape, dev_index = gathered[nb]
-                if tuple(shape[1:]) != tuple(slab.shape[1:]):
-                    raise ValueError("neighbour slabs must have this slab's plane shape")
                 base = C.c_void_p(0)
                 buf = (C.c_ubyte * 64).from_buffer_copy(hbytes)
-                check(lib().mie_ipc_open(buf, C.byref(base)))
+                if tuple(shape[1:]) != tuple(slab.shape[1:]) or lib().mie_ipc_open(buf, C.byref(base)) != 0:
+                    ok = False
+                    break
                 keep.append(_PeerMapping(base.value))
                 first = base.value + offset
                 if nb < rank:
                     lo = PeerPlane(first + (shape[0] - 1) * plane_bytes, slab.shape[1:], slab.dtype, torch.device("cuda", dev_index))
                 else:
                     hi = PeerPlane(first, slab.shape[1:], slab.dtype, torch.device("cuda", dev_index))
-    dist.barrier(group=group)                     # nobody frees or moves a slab before every neighbour has mapped it
-    return lo, hi, tuple(keep)
+    try:
+        all_ok(ok, "mapping a neighbour's slab (no peer path, or plane shapes differ)")
+    except RuntimeError:
+        for m in keep:
+            m.close()
+        raise
+    return lo, hi, tuple(keep)                    # (the all-reduce above is also the "everybody has mapped" barrier)
 
 
 class PeerSlabPlan:
