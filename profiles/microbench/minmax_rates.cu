@@ -3,6 +3,7 @@
 // (__vimax3_s32, __vimax3_s16x2), and FMNMX for comparison.
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 
 __device__ __forceinline__ unsigned pmin_s(unsigned a, unsigned b) { unsigned d; asm("min.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
 __device__ __forceinline__ unsigned pmax_s(unsigned a, unsigned b) { unsigned d; asm("max.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
@@ -29,6 +30,16 @@ __global__ void __launch_bounds__(1024) k(unsigned* out, long long* cyc, unsigne
             else if (MODE == 5) u[i] = __vimin3_s16x2(u[i], u[(i + 1) % U], m1);
             else if (MODE == 6) f[i] = fmaxf(fminf(f[i], f[(i + 1) % U]), 3.0f);
             else if (MODE == 7) u[i] = __vmaxs2(__vmins2(u[i], u[(i + 1) % U]), m0);
+            else if (MODE == 8) {   // half2 min / max on the same bit patterns (HMNMX2): which pipe, what rate?
+                __half2 a = *reinterpret_cast<__half2*>(&u[i]), b = *reinterpret_cast<__half2*>(&u[(i + 1) % U]);
+                __half2 c = *reinterpret_cast<const __half2*>(&m0);
+                __half2 r = __hmax2(__hmin2(a, b), c);
+                u[i] = *reinterpret_cast<unsigned*>(&r);
+            } else if (MODE == 9) {  // mixed: one packed integer min + one half2 max per step (do the pipes overlap?)
+                __half2 a = *reinterpret_cast<__half2*>(&u[i]), c = *reinterpret_cast<const __half2*>(&m0);
+                __half2 r = __hmax2(a, c);
+                u[i] = pmin_u(*reinterpret_cast<unsigned*>(&r), u[(i + 1) % U]);
+            }
         }
     }
     long long t1 = clock64();
@@ -62,5 +73,7 @@ int main() {
     run<5>("__vimin3_s16x2 (1 instr)", 1);
     run<6>("FMNMX x2", 2);
     run<7>("__vmins2/__vmaxs2 x2", 2);
+    run<8>("__hmin2 / __hmax2 (HMNMX2) x2", 2);
+    run<9>("min.u16x2 + __hmax2 (mixed) x2", 2);
     return 0;
 }
