@@ -779,7 +779,7 @@ def run_ours(args):
 
     if rank == 0:
         step_gbs = ALG_BYTES_PER_PIXEL * PIXELS / (ms_step * 1e-3) / 1e9
-        traffic_total, dom_rec = None, None
+        traffic_total, dom_rec, traffic_seq = None, None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                 tj = json.load(f)
@@ -798,12 +798,18 @@ def run_ours(args):
                        "kernels_ms": {k: round(v, 4) for k, v in kern.items()}}
             allk = [tj.get(k) for k in ("chain_a_march_kernel", "chain_pack_cells_kernel", "chain_b_march_kernel")]
             traffic_total = sum(allk) if all(v is not None for v in allk) else None
+            seq = tj.get("in_sequence", {})
+            seqk = [seq.get(k) for k in ("chain_a_march_kernel", "chain_pack_cells_kernel", "chain_b_march_kernel")]
+            traffic_seq = sum(seqk) if all(isinstance(v, int) for v in seqk) else None
         roof = {"bound": "hbm", "achieved": round(step_gbs, 1), "peak": peak * 1.0, "unit": "GB/s",
                 "frac": round(step_gbs / peak, 4), "traffic": traffic_total,
                 "basis": "SURVEY.md §8(d): 4 B/pixel (uint16 in + uint16 out; intermediates are not algorithmic bytes) x "
                          "67 108 864 pixels / ms_per_step, per GPU",
                 "frac_of_nominal_8TBs": round(step_gbs / 8000.0, 4), "bytes_per_step": ALG_BYTES_PER_PIXEL * PIXELS,
-                "peak_source": peak_src, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write, sum of the step's three launches)",
+                "peak_source": peak_src, "traffic_source": "profiles/traffic.json (ncu dram__bytes_read+write, sum of the step's three launches, caches flushed before each)",
+                "traffic_in_sequence": traffic_seq,
+                "traffic_in_sequence_note": "the same metric with --cache-control none: consecutive steps as they really run, write-backs of "
+                                            "the index plane and the cell tables included; the step is FMA-pipe bound, not DRAM bound",
                 "limiter": "FMA pipe / instruction issue, not HBM (profiles/README.md)", "dominant_kernel": dom_rec}
         cpu = None
         if world == 1:   # the CPU baseline is a rank-0, N = 1 figure (the reference arm times it at every N)

@@ -160,7 +160,7 @@ struct Fast<uint16_t> {
         uint2 o;
         o.x = quant2_u16x2(y[0], y[1]);
         o.y = quant2_u16x2(y[2], y[3]);
-        *reinterpret_cast<uint2*>(p) = o;
+        __stcs(reinterpret_cast<uint2*>(p), o);   // streaming: an operator's output is not read again by that operator
     }
     // rows s and s + 1 of the thread's four columns (raw words a, b) -> packed (row s, row s + 1) pairs
     static __device__ __forceinline__ f32x2 from_bits2(uint32_t m0, uint32_t m1) {
@@ -208,7 +208,7 @@ struct Fast<int16_t> {
         uint2 o;
         o.x = Fast<uint16_t>::quant2_u16x2(y[0], y[1]) ^ 0x80008000u;
         o.y = Fast<uint16_t>::quant2_u16x2(y[2], y[3]) ^ 0x80008000u;
-        *reinterpret_cast<uint2*>(p) = o;
+        __stcs(reinterpret_cast<uint2*>(p), o);
     }
     static __device__ __forceinline__ uint32_t exp_magic() { return Fast<uint16_t>::exp_magic(); }
     static __device__ __forceinline__ void cvt_pair4(raw4 a, raw4 b, f32x2* xp, uint32_t magic = 0x43000000u) {

@@ -83,6 +83,7 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
     // the producer is the first lane of warp 1 when there is one: warps 0 and nwarps-1 already carry the
     // image-border halo work, and every warp waits for the slowest one at the per-step barrier
     const int producer = nwarps > 2 ? 32 : 0;
+    const uint64_t pol = l2_evict_first_policy();
     auto issue_batch = [&](const int b) {  // producer thread only
         const int4 o = *reinterpret_cast<const int4*>(s_off + kRawBatch * b);
         const int off[4] = {o.x, o.y, o.z, o.w};
@@ -94,8 +95,8 @@ chain_a_march_kernel(ChainAArgs a, Taps wx, Taps wy, WinCvt cv) {
 #pragma unroll
         for (int j = 0; j < kRawBatch; ++j)
             if (BORDER != MIE_BORDER_CONSTANT || off[j] >= 0)
-                bulk_g2s(ring32 + (uint32_t)(((kRawBatch * b + j) % kRawRows) * row_bytes), plane0 + (unsigned)off[j],
-                         (uint32_t)row_bytes, mb);
+                bulk_g2s_stream(ring32 + (uint32_t)(((kRawBatch * b + j) % kRawRows) * row_bytes), plane0 + (unsigned)off[j],
+                                (uint32_t)row_bytes, mb, pol);
     };
     if (tid == producer) {
 #pragma unroll
